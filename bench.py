@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- alignment-cells/s of the log-prior + MAS hot path on B200 (one JSON line).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): fused log_prior + MAS at the LRS2 train batch shape,
+B=32 utterances per GPU, n_feats=80, T_text=190, T_mel=1000, synthetic lengths
+(face_gan_tts_b200.synthetic.lrs2_batch, seed 1234).  A "step" is one pass of the hot
+path over one batch: mu_x, y, lengths -> dense fp32 path + durations + frame->token index.
+Metric: alignment cells/s = B*T_text*T_mel / time (padded cells), whole job over all GPUs.
+
+  value     inputs already resident in HBM; K steps back to back on one stream between two
+            CUDA events; the steps rotate over NSETS independent buffer sets whose footprint
+            exceeds L2, so no step finds its inputs in cache.
+  e2e       the same step through the public API with HOST buffers: every step copies
+            mu_x, y and the lengths from pinned host memory, runs the fused call, and reads
+            durations + frame->token index back to pinned host memory (`e2e`), or additionally
+            the whole dense path (`e2e_dense_path`).
+  roofline  dominant kernel (by measured time), algorithmic bytes / its CUDA-event time
+            against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the reference's own implementation (oracle/_ref: core.pyx as shipped, serial)
+            + the torch log-prior expression on this box's host cores, same batch.
+  --impl reference  times that CPU path as its own arm (rank 0 only under torchrun).
+
+Multi-GPU (torchrun, one rank per GPU): utterances are independent, so each rank aligns its
+own 32-utterance shard (weak scaling, no data-path collective); the per-token durations are
+returned to every rank with one asynchronous NCCL all-gather per step (loss bookkeeping),
+overlapped with the next step and completed inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "face-gan-tts_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B, F, TX, TY = 32, 80, 190, 1000
+METRIC = "MAS alignment cells/s (B*T_text*T_mel)"
+UNIT = "cells/s"
+CELLS = B * TX * TY
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference (CPU) arm
+def reference_step_fn():
+    """The reference's CPU implementation of the path: torch log-prior (face_tts.py:165-171, all torch
+    threads) + its compiled core.pyx maximum_path_c as shipped (serial) through the wrapper's numpy steps."""
+    import oracle
+    from face_gan_tts_b200 import synthetic
+
+    core = oracle.reference_core("asis")
+    kind = "reference"
+    if core is None:
+        core, kind = oracle, "port"
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, TX, TY, seed=1234)
+    mask = synthetic.prefix_mask(t_x, t_y, TX, TY)
+    t_x_np, t_y_np = t_x.numpy(), t_y.numpy()
+
+    def step():
+        log_prior = oracle.log_prior_reference(mu_x, y)
+        value = (log_prior * mask).numpy().astype(np.float32)          # __init__.py:13,16
+        path = np.zeros_like(value).astype(np.int32)                     # :17
+        core.maximum_path_c(path, value, t_x_np, t_y_np)                 # :22
+        return torch.from_numpy(path).to(dtype=log_prior.dtype)         # :23
+
+    cores = torch.get_num_threads()
+    sample = (f"full configs[1] batch per step (B={B}, F={F}, Tx={TX}, Ty={TY}): torch CPU log-prior on "
+              f"{cores} threads + reference core.pyx maximum_path_c serial (as shipped, no OpenMP)")
+    return step, kind, cores, sample
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, kind, cores, sample = reference_step_fn()
+    steps = max(1, min(args.steps, 20))
+    sec = time_cpu(step, steps, max(1, min(args.warmup, 3)))
+    v = CELLS / sec
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: log_prior+MAS, LRS2 train batch shape", "B": B, "n_feats": F,
+                   "T_text": TX, "T_mel": TY},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import face_gan_tts_b200 as fgt
+    from face_gan_tts_b200 import _lib, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _lib.lib()
+    K, W = args.steps, max(args.warmup, 3)
+    NSETS = 6      # ~61 MB per set (inputs, value scratch, dense path): 6 sets = 366 MB >> 126 MB L2
+
+    # ---- device-resident buffer sets (each rank its own utterances: independent shards)
+    sets = []
+    for s in range(NSETS):
+        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, TX, TY, seed=1234 + 1000 * rank + s)
+        d = dict(mu=mu_x.to(dev), y=y.to(dev), tx=t_x.to(dev), ty=t_y.to(dev),
+                 path=torch.empty((B, TX, TY), dtype=torch.float32, device=dev),
+                 dur=torch.empty((B, TX), dtype=torch.int32, device=dev),
+                 ft=torch.empty((B, TY), dtype=torch.int32, device=dev),
+                 status=torch.empty((B,), dtype=torch.int32, device=dev))
+        sets.append(d)
+    ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, TX, TY)
+    wss = [torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) for _ in range(NSETS)]
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    def fused(d, ws, dense=True):
+        rc = L.mas_b200_log_prior_maximum_path(
+            d["mu"].data_ptr(), d["y"].data_ptr(), d["tx"].data_ptr(), d["ty"].data_ptr(), B, F, TX, TY, -1e9,
+            d["path"].data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
+            d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes,
+            _lib.LP_AUTO, sp)
+        _lib.check(rc, "mas_b200_log_prior_maximum_path")
+
+    gathered = [torch.empty((world * B, TX), dtype=torch.int32, device=dev) for _ in range(2)] if dist else None
+    comm_stream = torch.cuda.Stream(dev) if dist else None
+
+    def step(i):
+        d = sets[i % NSETS]
+        fused(d, wss[i % NSETS])
+        if dist:
+            # loss-bookkeeping collective: durations of every rank, asynchronous on a side stream
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            comm_stream.wait_event(ev)
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(gathered[i % 2], d["dur"])
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        step(W + i)
+    if dist:
+        stream.wait_stream(comm_stream)      # all gathers complete inside the timed region
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * CELLS / (ms_step * 1e-3)
+
+    # ---- per-kernel breakdown (rank 0): CUDA events around each piece on its own stream
+    def time_piece(fn, reps=K):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(reps):
+            fn(3 + i)
+        b_.record(stream)
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b_) / reps
+
+    out = None
+    if rank == 0:
+        mas_ws = L.mas_b200_workspace_bytes(B, TX, TY)
+        vals = [torch.empty((B, TX, TY), dtype=torch.float32, device=dev) for _ in range(NSETS)]
+
+        def lp_only(i):
+            d = sets[i % NSETS]
+            _lib.check(L.mas_b200_log_prior(d["mu"].data_ptr(), d["y"].data_ptr(), B, F, TX, TY,
+                                            vals[i % NSETS].data_ptr(), _lib.LP_AUTO, sp), "log_prior")
+
+        def mas_only(i, dense=False):
+            d = sets[i % NSETS]
+            _lib.check(L.mas_b200_maximum_path(
+                vals[i % NSETS].data_ptr(), TX * TY, TY, d["tx"].data_ptr(), d["ty"].data_ptr(), B, TX, TY, -1e9,
+                d["path"].data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
+                d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), wss[i % NSETS].data_ptr(), mas_ws,
+                sp), "maximum_path")
+
+        for i in range(NSETS):
+            lp_only(i)
+        t_lp = time_piece(lp_only)
+        t_mas = time_piece(lambda i: mas_only(i, False))
+        t_mas_dense = time_piece(lambda i: mas_only(i, True))
+        t_expand = max(t_mas_dense - t_mas, 0.0)
+        valid_cells = int(sum((d["tx"].long() * d["ty"].long()).sum().item() for d in sets) / NSETS)
+        kernels = {
+            "log_prior": {"ms": t_lp, "algorithmic_bytes": 4 * F * B * (TX + TY) + 4 * CELLS},
+            "mas_forward_backtrack": {"ms": t_mas, "algorithmic_bytes": 4 * CELLS},
+            "path_expand": {"ms": t_expand, "algorithmic_bytes": 4 * CELLS},
+        }
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        peak, peak_src = load_peaks()
+        achieved = kernels[dom]["algorithmic_bytes"] / (kernels[dom]["ms"] * 1e-3) / 1e9
+        step_bytes = 4 * F * B * (TX + TY) + 4 * CELLS        # fused algorithmic traffic: inputs + dense path
+        roofline = {
+            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "kernels_ms": {k: v["ms"] for k, v in kernels.items()},
+            "step_algorithmic_bytes": step_bytes,
+            "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+            "note": "B=32 CTAs on 148 SMs: bounded by the T_mel-long dependency chain of the DP, not by HBM",
+        }
+
+        # ---- e2e: host buffers in, results out, copies inside the timed region
+        mu_h, y_h, tx_h, ty_h = [t.pin_memory() for t in synthetic.lrs2_batch(B, F, TX, TY, seed=1234)]
+        dur_h = torch.empty((B, TX), dtype=torch.int32).pin_memory()
+        ft_h = torch.empty((B, TY), dtype=torch.int32).pin_memory()
+        path_h = torch.empty((B, TX, TY), dtype=torch.float32).pin_memory()
+
+        def e2e_step(i, dense_d2h):
+            d = sets[i % NSETS]
+            d["mu"].copy_(mu_h, non_blocking=True)
+            d["y"].copy_(y_h, non_blocking=True)
+            d["tx"].copy_(tx_h, non_blocking=True)
+            d["ty"].copy_(ty_h, non_blocking=True)
+            res = fgt.log_prior_maximum_path(d["mu"], d["y"], d["tx"], d["ty"], dense_path=True)
+            dur_h.copy_(res.durations, non_blocking=True)
+            ft_h.copy_(res.frame_token, non_blocking=True)
+            if dense_d2h:
+                path_h.copy_(res.path, non_blocking=True)
+            stream.synchronize()              # the caller consumes the result every step
+
+        def time_e2e(dense_d2h):
+            for i in range(3):
+                e2e_step(i, dense_d2h)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for i in range(K):
+                e2e_step(3 + i, dense_d2h)
+            b_.record(stream)
+            torch.cuda.synchronize(dev)
+            wall = (time.perf_counter() - t0) / K
+            return max(a.elapsed_time(b_) / K * 1e-3, wall)
+
+        h2d = 4 * F * B * (TX + TY) + 8 * B
+        sec_e2e = time_e2e(False)
+        sec_e2e_dense = time_e2e(True)
+        e2e = {"value": world * CELLS / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e * 1e3,
+               "result": "durations [B,Tx] + frame->token index [B,Ty] (dense path stays in HBM for mu_y)"}
+        e2e_dense = {"value": world * CELLS / sec_e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": 4 * B * (TX + TY) + 4 * CELLS, "ms_per_step": sec_e2e_dense * 1e3}
+
+        # ---- CPU baseline on this box's host cores (bounded sample: a few full-batch steps)
+        try:
+            cstep, kind, cores, sample = reference_step_fn()
+            sec = time_cpu(cstep, 3, 1)
+            cpu = {"value": CELLS / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + "; 3 steps",
+                   "ms_per_step": sec * 1e3}
+        except Exception as ex:  # the oracle is a reported baseline, never a dependency of the product
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+        launches_per_step = 3      # log_prior + mas_forward + path_expand (no fused kernel selected)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: fused log_prior+MAS, LRS2 train batch shape", "B_per_gpu": B,
+                       "n_feats": F, "T_text": TX, "T_mel": TY, "valid_cells_per_step": valid_cells,
+                       "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 61} MB) larger than the 126 MB L2",
+                       "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
+                       else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense_path": e2e_dense,
+            "gpu_launches": launches_per_step * K, "clocks": clocks,
+        }
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

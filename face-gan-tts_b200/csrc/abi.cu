@@ -1,0 +1,248 @@
+// abi.cu -- the extern "C" surface of libmas_b200.so (include/mas_b200.h).
+#include <atomic>
+#include <climits>
+#include <cstring>
+#include <mutex>
+
+#include "mas_host.h"
+
+namespace masb200 {
+
+// ------------------------------------------------------------------ errors
+static thread_local int g_last_cuda_error = 0;
+void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
+
+// ------------------------------------------------------------------ options
+namespace {
+struct Opt { const char *key; std::atomic<int> value; };
+Opt g_opts[] = {
+    {"mas_rows_per_lane", {0}},      // R: 1,2,4,8 (0 = auto)
+    {"mas_dp_warps", {0}},           // W: 1..4    (0 = auto)
+    {"mas_ring_stages", {0}},        // cap on NS  (0 = auto, up to 8)
+    {"mas_ctas_per_sm", {0}},        // smem budget divisor (0 = auto from B)
+    {"mas_force_global_bits", {0}},  // 1: direction bits always in global scratch
+    {"mas_force_unaligned", {0}},    // 1: never use the TMA bulk path
+    {"mas_cell_impl", {1}},          // 0 portable C cell, 1 predicated-add PTX cell
+    {"mas_fused_path_write", {-1}},  // -1 auto, 0 separate expand kernel, 1 in-kernel
+    {"lp_impl", {0}},                // default log-prior implementation for MAS_B200_LP_AUTO
+    {"fused_impl", {0}},             // 0 auto, 1 force unfused pipeline, 2 force fused kernel
+};
+}  // namespace
+
+int option(const char *key) {
+    for (auto &o : g_opts)
+        if (std::strcmp(o.key, key) == 0) return o.value.load(std::memory_order_relaxed);
+    return INT_MIN;
+}
+
+// ------------------------------------------------------------------ device
+int device_info(DeviceInfo *out) {
+    static std::mutex mu;
+    static DeviceInfo cache[16];
+    static bool have[16] = {};
+    int dev = 0;
+    MASB200_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 16 && have[dev]) { *out = cache[dev]; return MAS_B200_OK; }
+    DeviceInfo di{};
+    MASB200_CUDA_TRY(cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    MASB200_CUDA_TRY(cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (dev >= 0 && dev < 16) { cache[dev] = di; have[dev] = true; }
+    *out = di;
+    return MAS_B200_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace masb200
+
+using namespace masb200;
+
+extern "C" {
+
+int mas_b200_abi_version(void) { return MAS_B200_ABI_VERSION; }
+
+const char *mas_b200_error_string(int status) {
+    switch (status) {
+        case MAS_B200_OK: return "ok";
+        case MAS_B200_ERR_ARG: return "invalid argument";
+        case MAS_B200_ERR_UNSUPPORTED: return "shape not supported by the sm_100a kernels";
+        case MAS_B200_ERR_WORKSPACE: return "workspace missing or too small";
+        case MAS_B200_ERR_CUDA: return "CUDA runtime error (see mas_b200_last_cuda_error)";
+        case MAS_B200_ERR_ALIGN: return "pointer alignment";
+        default: return status > 0 ? "items rejected" : "unknown error";
+    }
+}
+
+int mas_b200_last_cuda_error(void) { return g_last_cuda_error; }
+
+int mas_b200_set_option(const char *key, int value) {
+    if (!key) return INT_MIN;
+    for (auto &o : g_opts)
+        if (std::strcmp(o.key, key) == 0) return o.value.exchange(value, std::memory_order_relaxed);
+    return INT_MIN;
+}
+
+int mas_b200_get_option(const char *key) { return key ? option(key) : INT_MIN; }
+
+size_t mas_b200_workspace_bytes(int B, int Tx, int Ty) {
+    if (B <= 0 || Tx <= 0 || Ty <= 0) return 0;
+    return workspace_layout(B, Tx, Ty).total;
+}
+
+int mas_b200_lengths_from_mask(const float *mask_dev, int B, int Tx, int Ty, int *t_x_dev, int *t_y_dev,
+                               void *stream) {
+    return launch_lengths_from_mask(mask_dev, B, Tx, Ty, t_x_dev, t_y_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_maximum_path(const float *value_dev, long long stride_b, long long stride_x, const int *t_x_dev,
+                          const int *t_y_dev, int B, int Tx, int Ty, float max_neg_val, void *path_dev,
+                          int path_dtype, int *durations_dev, int *frame_token_dev, int *status_dev,
+                          void *workspace_dev, size_t workspace_bytes, void *stream) {
+    MasLaunch L{};
+    L.value = value_dev; L.stride_b = stride_b; L.stride_x = stride_x;
+    L.t_x = t_x_dev; L.t_y = t_y_dev; L.B = B; L.Tx = Tx; L.Ty = Ty; L.neg = max_neg_val;
+    L.path = path_dev; L.path_dtype = path_dtype;
+    L.durations = durations_dev; L.frame_token = frame_token_dev; L.status = status_dev;
+    L.workspace = workspace_dev; L.workspace_bytes = workspace_bytes;
+    L.stream = static_cast<cudaStream_t>(stream);
+    if (stride_x < Ty || stride_b < 0) return MAS_B200_ERR_ARG;
+    return launch_mas(L);
+}
+
+int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev, int B, int F, int Tx, int Ty,
+                       float *log_prior_dev, int impl, void *stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (impl == MAS_B200_LP_AUTO) {
+        const int o = option("lp_impl");
+        impl = (o == MAS_B200_LP_FFMA || o == MAS_B200_LP_TCGEN05) ? o : MAS_B200_LP_AUTO;
+    }
+    if (impl == MAS_B200_LP_FFMA) return launch_log_prior_ffma(mu_x_dev, y_dev, B, F, Tx, Ty, log_prior_dev, s);
+    if (impl == MAS_B200_LP_TCGEN05) return launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, log_prior_dev, s);
+    if (impl != MAS_B200_LP_AUTO) return MAS_B200_ERR_ARG;
+    const int rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, log_prior_dev, s);
+    if (rc != MAS_B200_ERR_UNSUPPORTED) return rc;
+    return launch_log_prior_ffma(mu_x_dev, y_dev, B, F, Tx, Ty, log_prior_dev, s);
+}
+
+size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty) {
+    if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return 0;
+    // MAS workspace + room for the [B,Tx,Ty] value matrix of the unfused pipeline
+    return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256);
+}
+
+int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, const int *t_x_dev,
+                                    const int *t_y_dev, int B, int F, int Tx, int Ty, float max_neg_val,
+                                    void *path_dev, int path_dtype, int *durations_dev, int *frame_token_dev,
+                                    int *status_dev, void *workspace_dev, size_t workspace_bytes, int impl,
+                                    void *stream) {
+    if (!mu_x_dev || !y_dev || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    if (!workspace_dev || workspace_bytes < mas_b200_fused_workspace_bytes(B, F, Tx, Ty)) return MAS_B200_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) return MAS_B200_ERR_ALIGN;
+    const size_t mas_ws = align_up(workspace_layout(B, Tx, Ty).total, 256);
+    float *value = reinterpret_cast<float *>(static_cast<char *>(workspace_dev) + mas_ws);
+    int rc = mas_b200_log_prior(mu_x_dev, y_dev, B, F, Tx, Ty, value, impl, stream);
+    if (rc != MAS_B200_OK) return rc;
+    return mas_b200_maximum_path(value, (long long)Tx * Ty, Ty, t_x_dev, t_y_dev, B, Tx, Ty, max_neg_val, path_dev,
+                                 path_dtype, durations_dev, frame_token_dev, status_dev, workspace_dev, mas_ws, stream);
+}
+
+int mas_b200_generate_path(const int *durations_dev, const int *t_x_dev, const int *t_y_dev, int B, int Tx, int Ty,
+                           void *path_dev, int path_dtype, void *stream) {
+    return launch_generate_path(durations_dev, t_x_dev, t_y_dev, B, Tx, Ty, path_dev, path_dtype,
+                                static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------- host-buffer drop-ins
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+};
+struct Stream {
+    cudaStream_t s = nullptr;
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+};
+int count_bad(const int *status, int B) {
+    int bad = 0;
+    for (int i = 0; i < B; ++i) bad += status[i] != MAS_B200_ITEM_OK;
+    return bad;
+}
+}  // namespace
+
+int mas_b200_maximum_path_host(int *paths, const float *values, const int *t_xs, const int *t_ys, int B, int Tx,
+                               int Ty, float max_neg_val) {
+    if (!paths || !values || !t_xs || !t_ys || B <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    const size_t cells = (size_t)B * Tx * Ty;
+    const size_t ws_bytes = mas_b200_workspace_bytes(B, Tx, Ty);
+    DevBuf d_val, d_path, d_tx, d_ty, d_status, d_ws;
+    Stream st;
+    MASB200_CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    MASB200_CUDA_TRY(d_val.alloc(cells * 4));
+    MASB200_CUDA_TRY(d_path.alloc(cells * 4));
+    MASB200_CUDA_TRY(d_tx.alloc((size_t)B * 4));
+    MASB200_CUDA_TRY(d_ty.alloc((size_t)B * 4));
+    MASB200_CUDA_TRY(d_status.alloc((size_t)B * 4));
+    MASB200_CUDA_TRY(d_ws.alloc(ws_bytes));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_val.p, values, cells * 4, cudaMemcpyHostToDevice, st.s));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_tx.p, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_ty.p, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
+    int rc = mas_b200_maximum_path(static_cast<float *>(d_val.p), (long long)Tx * Ty, Ty, static_cast<int *>(d_tx.p),
+                                   static_cast<int *>(d_ty.p), B, Tx, Ty, max_neg_val, d_path.p, MAS_B200_PATH_I32,
+                                   nullptr, nullptr, static_cast<int *>(d_status.p), d_ws.p, ws_bytes, st.s);
+    if (rc != MAS_B200_OK) return rc;
+    int *status = new int[B];
+    cudaError_t e = cudaMemcpyAsync(paths, d_path.p, cells * 4, cudaMemcpyDeviceToHost, st.s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st.s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st.s);
+    if (e != cudaSuccess) { delete[] status; set_last_cuda_error(e); return MAS_B200_ERR_CUDA; }
+    const int bad = count_bad(status, B);
+    delete[] status;
+    return bad;
+}
+
+int mas_b200_log_prior_maximum_path_host(const float *mu_x, const float *y, const int *t_xs, const int *t_ys,
+                                         int B, int F, int Tx, int Ty, float max_neg_val, int *paths,
+                                         int *durations, int *frame_token) {
+    if (!mu_x || !y || !t_xs || !t_ys || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    const size_t cells = (size_t)B * Tx * Ty;
+    const size_t ws_bytes = mas_b200_fused_workspace_bytes(B, F, Tx, Ty);
+    DevBuf d_mu, d_y, d_path, d_tx, d_ty, d_status, d_dur, d_ft, d_ws;
+    Stream st;
+    MASB200_CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    MASB200_CUDA_TRY(d_mu.alloc((size_t)B * F * Tx * 4));
+    MASB200_CUDA_TRY(d_y.alloc((size_t)B * F * Ty * 4));
+    if (paths) MASB200_CUDA_TRY(d_path.alloc(cells * 4));
+    MASB200_CUDA_TRY(d_tx.alloc((size_t)B * 4));
+    MASB200_CUDA_TRY(d_ty.alloc((size_t)B * 4));
+    MASB200_CUDA_TRY(d_status.alloc((size_t)B * 4));
+    MASB200_CUDA_TRY(d_dur.alloc((size_t)B * Tx * 4));
+    MASB200_CUDA_TRY(d_ft.alloc((size_t)B * Ty * 4));
+    MASB200_CUDA_TRY(d_ws.alloc(ws_bytes));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_mu.p, mu_x, (size_t)B * F * Tx * 4, cudaMemcpyHostToDevice, st.s));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_y.p, y, (size_t)B * F * Ty * 4, cudaMemcpyHostToDevice, st.s));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_tx.p, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_ty.p, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
+    int rc = mas_b200_log_prior_maximum_path(
+        static_cast<float *>(d_mu.p), static_cast<float *>(d_y.p), static_cast<int *>(d_tx.p),
+        static_cast<int *>(d_ty.p), B, F, Tx, Ty, max_neg_val, paths ? d_path.p : nullptr,
+        paths ? MAS_B200_PATH_I32 : MAS_B200_PATH_NONE, static_cast<int *>(d_dur.p), static_cast<int *>(d_ft.p),
+        static_cast<int *>(d_status.p), d_ws.p, ws_bytes, MAS_B200_LP_AUTO, st.s);
+    if (rc != MAS_B200_OK) return rc;
+    int *status = new int[B];
+    cudaError_t e = cudaSuccess;
+    if (paths) e = cudaMemcpyAsync(paths, d_path.p, cells * 4, cudaMemcpyDeviceToHost, st.s);
+    if (e == cudaSuccess && durations)
+        e = cudaMemcpyAsync(durations, d_dur.p, (size_t)B * Tx * 4, cudaMemcpyDeviceToHost, st.s);
+    if (e == cudaSuccess && frame_token)
+        e = cudaMemcpyAsync(frame_token, d_ft.p, (size_t)B * Ty * 4, cudaMemcpyDeviceToHost, st.s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st.s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st.s);
+    if (e != cudaSuccess) { delete[] status; set_last_cuda_error(e); return MAS_B200_ERR_CUDA; }
+    const int bad = count_bad(status, B);
+    delete[] status;
+    return bad;
+}
+
+}  // extern "C"

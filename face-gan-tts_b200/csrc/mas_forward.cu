@@ -1,0 +1,155 @@
+// mas_forward.cu -- plan selection + launch of the MAS kernel (mas_forward.cuh).
+#include <atomic>
+#include <cstdio>
+
+#include "mas_forward.cuh"
+#include "mas_host.h"
+
+namespace masb200 {
+
+// one translation unit per rows-per-lane value (mas_forward_inst.cu, -DMASB200_INST_R=...)
+int launch_mas_r1(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream);
+int launch_mas_r2(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream);
+int launch_mas_r4(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream);
+int launch_mas_r8(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream);
+
+namespace {
+
+struct Plan {
+    int R, W;
+    bool smem_bits;
+    int NS;
+    size_t smem;
+};
+
+constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+constexpr size_t kStaticSmem = 64;    // bt_state + slack
+
+size_t fixed_bytes_rw(int R, int W, int ns) {
+    const int XP = 32 * R * W;
+    const size_t ring = sizeof(float) * (size_t)ns * XP * kTilePitch;
+    const size_t halo = sizeof(float) * (size_t)W * (4 * (ns + 1)) * 8;
+    const size_t ctrl = 8 * (size_t)(2 * ns) + 4 * (size_t)W + 64;
+    return ((ring + halo + ctrl + 127) / 128) * 128;
+}
+
+bool valid_rw(int R, int W) { return (R == 1 || R == 2 || R == 4 || R == 8) && W >= 1 && W <= 4 && 32 * R * W <= 768; }
+
+// Pick rows-per-lane / DP warps / ring depth for (B, Tx, Ty).
+bool make_plan(int B, int Tx, int Ty, int sm_count, Plan *p) {
+    static const int table[][2] = {{1, 1}, {2, 1}, {2, 2}, {2, 3}, {4, 2}, {4, 3}, {4, 4}};
+    int R = 4, W = 4;
+    for (auto &rw : table) {
+        if (32 * rw[0] * rw[1] >= Tx) { R = rw[0]; W = rw[1]; break; }
+    }
+    const int oR = option("mas_rows_per_lane"), oW = option("mas_dp_warps");
+    if (oR > 0 && oW > 0 && valid_rw(oR, oW)) { R = oR; W = oW; }
+    const int XP = 32 * R * W;
+    const int tiles = (Ty + kTileFrames - 1) / kTileFrames;
+
+    // shared-memory budget: one CTA per SM for small batches (deepest ring, lowest latency),
+    // several co-resident CTAs once the batch exceeds the SM count (fill idle issue slots).
+    int per_sm = option("mas_ctas_per_sm");
+    if (per_sm <= 0) per_sm = B <= sm_count ? 1 : (B <= 2 * sm_count ? 2 : 3);
+    size_t budget = kMaxSmem / per_sm - kStaticSmem - (per_sm > 1 ? 1024 : 0);
+
+    const size_t tile_bytes = sizeof(float) * (size_t)XP * kTilePitch;
+    const size_t bits_bytes = sizeof(uint32_t) * (size_t)tiles * XP;
+    const bool single_pass = Tx <= XP;
+    const int ns_cap = option("mas_ring_stages") > 0 ? option("mas_ring_stages") : 8;
+
+    auto ring_for = [&](size_t avail) {
+        int ns = 0;
+        while (ns < ns_cap && fixed_bytes_rw(R, W, ns + 1) <= avail) ++ns;
+        return ns;
+    };
+    bool smem_bits = single_pass && option("mas_force_global_bits") <= 0 && bits_bytes + 2 * tile_bytes + 4096 <= budget;
+    int ns = smem_bits ? ring_for(budget - bits_bytes) : ring_for(budget);
+    if (ns < 2) {
+        // fall back to the full opt-in budget
+        budget = kMaxSmem - kStaticSmem;
+        smem_bits = single_pass && option("mas_force_global_bits") <= 0 && bits_bytes + 2 * tile_bytes + 4096 <= budget;
+        ns = smem_bits ? ring_for(budget - bits_bytes) : ring_for(budget);
+        if (ns < 2) return false;
+    }
+    p->R = R; p->W = W; p->smem_bits = smem_bits; p->NS = ns;
+    p->smem = fixed_bytes_rw(R, W, ns) + (smem_bits ? bits_bytes : 0);
+    return true;
+}
+
+}  // namespace
+
+Workspace workspace_layout(int B, int Tx, int Ty) {
+    Workspace w{};
+    auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    w.tiles = (Ty + kTileFrames - 1) / kTileFrames;
+    w.rows_pitch = (int)up((size_t)Tx + 511, 512);
+    w.line_pitch = (int)up((size_t)Ty, 32) + 32;
+    size_t off = 0;
+    w.start_off = off; off = up(off + sizeof(int) * (size_t)B * Tx, 256);
+    w.dur_off = off;   off = up(off + sizeof(int) * (size_t)B * Tx, 256);
+    w.gbits_off = off; off = up(off + sizeof(uint32_t) * (size_t)B * w.tiles * w.rows_pitch, 256);
+    w.gline_off = off; off = up(off + sizeof(float) * (size_t)B * 2 * w.line_pitch, 256);
+    w.total = off;
+    return w;
+}
+
+int launch_mas(const MasLaunch &L) {
+    if (!L.value || !L.t_x || !L.t_y || L.B <= 0 || L.Tx <= 0 || L.Ty <= 0) return MAS_B200_ERR_ARG;
+    if (L.path_dtype != MAS_B200_PATH_NONE && L.path_dtype != MAS_B200_PATH_F32 && L.path_dtype != MAS_B200_PATH_I32)
+        return MAS_B200_ERR_ARG;
+    if (L.path_dtype != MAS_B200_PATH_NONE && !L.path) return MAS_B200_ERR_ARG;
+    const Workspace ws = workspace_layout(L.B, L.Tx, L.Ty);
+    if (!L.workspace || L.workspace_bytes < ws.total) return MAS_B200_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(L.workspace) & 255) return MAS_B200_ERR_ALIGN;
+
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != MAS_B200_OK) return rc;
+    Plan plan;
+    if (!make_plan(L.B, L.Tx, L.Ty, di.sm_count, &plan)) return MAS_B200_ERR_UNSUPPORTED;
+    const int XP = 32 * plan.R * plan.W;
+    const long long txp = ((long long)L.Tx + XP - 1) / XP * XP;
+    if (txp > ws.rows_pitch) return MAS_B200_ERR_UNSUPPORTED;
+    // the backtrack stages one tile of direction words (rows_pitch of them) through the ring
+    if ((size_t)ws.rows_pitch * 4 > sizeof(float) * (size_t)plan.NS * XP * kTilePitch) return MAS_B200_ERR_UNSUPPORTED;
+
+    char *wsb = static_cast<char *>(L.workspace);
+    MasParams P{};
+    P.value = L.value; P.stride_b = L.stride_b; P.stride_x = L.stride_x;
+    P.t_x = L.t_x; P.t_y = L.t_y; P.B = L.B; P.Tx = L.Tx; P.Ty = L.Ty; P.neg = L.neg;
+    P.aligned = ((reinterpret_cast<uintptr_t>(L.value) & 15) == 0 && (L.stride_b & 3) == 0 && (L.stride_x & 3) == 0 &&
+                 (L.Ty & 3) == 0 && option("mas_force_unaligned") <= 0) ? 1 : 0;
+    P.ring_stages = plan.NS;
+    P.start = reinterpret_cast<int *>(wsb + ws.start_off);
+    P.dur = L.durations ? L.durations : reinterpret_cast<int *>(wsb + ws.dur_off);
+    P.frame_token = L.frame_token;
+    P.status = L.status;
+    P.gbits = reinterpret_cast<uint32_t *>(wsb + ws.gbits_off);
+    P.gbits_rows_pitch = ws.rows_pitch;
+    P.gbits_stride_b = (long long)ws.tiles * ws.rows_pitch;
+    P.gline = reinterpret_cast<float *>(wsb + ws.gline_off);
+    P.line_pitch = ws.line_pitch;
+
+    int fuse = option("mas_fused_path_write");
+    if (fuse < 0) fuse = (L.B >= 2 * di.sm_count) ? 1 : 0;
+    const bool want_path = L.path_dtype != MAS_B200_PATH_NONE;
+    P.path = (want_path && fuse) ? L.path : nullptr;
+    P.path_dtype = (want_path && fuse) ? L.path_dtype : MAS_B200_PATH_NONE;
+
+    const int cell = option("mas_cell_impl") == 0 ? 0 : 1;
+    switch (plan.R) {
+        case 1: rc = launch_mas_r1(P, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
+        case 2: rc = launch_mas_r2(P, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
+        case 4: rc = launch_mas_r4(P, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
+        case 8: rc = launch_mas_r8(P, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
+        default: rc = MAS_B200_ERR_UNSUPPORTED;
+    }
+    if (rc != MAS_B200_OK) return rc;
+
+    if (want_path && !fuse)
+        return launch_path_expand(P.start, P.dur, L.B, L.Tx, L.Ty, L.path, L.path_dtype, L.stream);
+    return MAS_B200_OK;
+}
+
+}  // namespace masb200

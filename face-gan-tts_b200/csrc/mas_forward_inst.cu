@@ -1,0 +1,61 @@
+// mas_forward_inst.cu -- kernel instantiations for one rows-per-lane value R
+// (compiled once per R with -DMASB200_INST_R=R so the translation units build in parallel).
+#include <atomic>
+
+#include "mas_forward.cuh"
+#include "mas_host.h"
+
+#ifndef MASB200_INST_R
+#error "compile with -DMASB200_INST_R=1|2|4|8"
+#endif
+
+namespace masb200 {
+
+namespace {
+
+constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+
+template <int R, int W, bool SB, int CELL>
+int launch_inst(const MasParams &P, size_t smem, cudaStream_t stream) {
+    static std::atomic<int> configured[16];
+    int dev = 0;
+    MASB200_CUDA_TRY(cudaGetDevice(&dev));
+    auto kern = mas_forward_kernel<R, W, SB, CELL>;
+    if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
+        MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem - 1024));
+        if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
+    }
+    kern<<<P.B, (W + 1) * 32, smem, stream>>>(P);
+    MASB200_CUDA_TRY(cudaGetLastError());
+    return MAS_B200_OK;
+}
+
+template <int R, int W>
+int launch_w(const MasParams &P, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
+    if (cell == 0)
+        return smem_bits ? launch_inst<R, W, true, 0>(P, smem, stream) : launch_inst<R, W, false, 0>(P, smem, stream);
+    return smem_bits ? launch_inst<R, W, true, 1>(P, smem, stream) : launch_inst<R, W, false, 1>(P, smem, stream);
+}
+
+template <int R>
+int launch_r(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
+    switch (W) {
+        case 1: return launch_w<R, 1>(P, smem_bits, cell, smem, stream);
+        case 2: return launch_w<R, 2>(P, smem_bits, cell, smem, stream);
+        case 3: return launch_w<R, 3>(P, smem_bits, cell, smem, stream);
+        case 4: return launch_w<R, 4>(P, smem_bits, cell, smem, stream);
+        default: return MAS_B200_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+#define MASB200_CAT2(a, b) a##b
+#define MASB200_CAT(a, b) MASB200_CAT2(a, b)
+
+int MASB200_CAT(launch_mas_r, MASB200_INST_R)(const MasParams &P, int W, bool smem_bits, int cell, size_t smem,
+                                              cudaStream_t stream) {
+    return launch_r<MASB200_INST_R>(P, W, smem_bits, cell, smem, stream);
+}
+
+}  // namespace masb200

@@ -1,0 +1,70 @@
+// mas_host.h -- host-side declarations shared by the translation units of libmas_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mas_b200.h"
+
+namespace masb200 {
+
+// ---- error plumbing -------------------------------------------------------
+void set_last_cuda_error(cudaError_t e);
+#define MASB200_CUDA_TRY(expr)                                   \
+    do {                                                         \
+        cudaError_t _e = (expr);                                 \
+        if (_e != cudaSuccess) {                                 \
+            ::masb200::set_last_cuda_error(_e);                  \
+            return MAS_B200_ERR_CUDA;                            \
+        }                                                        \
+    } while (0)
+
+// ---- options (process-wide tuning knobs, mas_b200_set_option) --------------
+int option(const char *key);   // INT32_MIN if unknown
+
+// ---- device properties cached per device ----------------------------------
+struct DeviceInfo {
+    int sm_count;
+    int max_smem_optin;
+};
+int device_info(DeviceInfo *out);
+
+// ---- workspace layout -------------------------------------------------------
+// [start: B*Tx i32][dur: B*Tx i32][gbits: B*tiles*rows_pitch u32][gline: B*2*line_pitch f32]
+struct Workspace {
+    size_t start_off, dur_off, gbits_off, gline_off, total;
+    int tiles, rows_pitch, line_pitch;
+};
+Workspace workspace_layout(int B, int Tx, int Ty);
+
+// ---- launchers ----------------------------------------------------------------
+struct MasLaunch {
+    const float *value;
+    long long stride_b, stride_x;
+    const int *t_x, *t_y;
+    int B, Tx, Ty;
+    float neg;
+    void *path;
+    int path_dtype;
+    int *durations;     // may be null
+    int *frame_token;   // may be null
+    int *status;        // may be null
+    void *workspace;
+    size_t workspace_bytes;
+    cudaStream_t stream;
+};
+int launch_mas(const MasLaunch &L);
+
+int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, void *path, int path_dtype,
+                       cudaStream_t stream);
+int launch_lengths_from_mask(const float *mask, int B, int Tx, int Ty, int *t_x, int *t_y, cudaStream_t stream);
+int launch_generate_path(const int *durations, const int *t_x, const int *t_y, int B, int Tx, int Ty, void *path,
+                         int path_dtype, cudaStream_t stream);
+int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
+                          cudaStream_t stream);
+// tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.
+int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
+                        cudaStream_t stream);
+
+}  // namespace masb200

@@ -1,0 +1,23 @@
+"""face_gan_tts_b200 -- B200-native (sm_100a) log-prior + Monotonic Alignment Search.
+
+Drop-in for the alignment hot path of CognitiveModeling/Face-GAN-TTS:
+`model/monotonic_align` (Cython, CPU) and the log-prior block of
+`FaceTTS.compute_loss` (model/face_tts.py:165-174).  All compute runs in
+libmas_b200.so (hand-written CUDA behind a C ABI, include/mas_b200.h); this
+package is the thin PyTorch-facing host layer.  No CPU fallback.
+"""
+from . import monotonic_align  # noqa: F401
+from .alignment import (  # noqa: F401
+    AlignmentResult,
+    align,
+    durations_to_logw,
+    generate_path,
+    log_prior,
+    log_prior_maximum_path,
+)
+from .install import install, uninstall  # noqa: F401
+
+__all__ = [
+    "monotonic_align", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
+    "durations_to_logw", "install", "uninstall",
+]

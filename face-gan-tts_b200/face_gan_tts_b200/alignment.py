@@ -1,0 +1,203 @@
+"""PyTorch-facing host layer over libmas_b200.so.
+
+Every function here only validates arguments, allocates outputs/workspace
+with torch (device memory + streams are torch's job) and calls the C ABI on
+`torch.cuda.current_stream()`.  Nothing synchronises the host unless asked
+to (`check=True`).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_IMPL = {"auto": _lib.LP_AUTO, "ffma": _lib.LP_FFMA, "tcgen05": _lib.LP_TCGEN05}
+
+
+@dataclass
+class AlignmentResult:
+    """Outputs of one alignment call (all on the inputs' CUDA device).
+
+    path         [B,Tx,Ty] {0,1} in the requested dtype, or None
+    durations    [B,Tx] int32  frames per token (= path.sum(-1), reference face_tts.py:176)
+    frame_token  [B,Ty] int32  token index of every frame, -1 beyond t_y
+    status       [B]    int32  0 ok, 1 rejected (t_x > t_y, ...: undefined in the reference)
+    """
+    path: Optional[torch.Tensor]
+    durations: torch.Tensor
+    frame_token: torch.Tensor
+    status: torch.Tensor
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (this library has no CPU path)")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _lengths(t, B, device, name):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    if t.shape != (B,):
+        raise ValueError(f"{name} must have shape [{B}]")
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def _path_dtype_code(dtype):
+    if dtype == torch.float32:
+        return _lib.PATH_F32
+    if dtype == torch.int32:
+        return _lib.PATH_I32
+    raise ValueError("dense path dtype must be float32 or int32")
+
+
+def _raise_on_bad(status: torch.Tensor, where: str):
+    bad = torch.nonzero(status != 0).flatten().tolist()     # synchronises
+    if bad:
+        raise ValueError(f"{where}: items {bad} rejected (need 1 <= t_x <= t_y, t_x <= Tx, t_y <= Ty; "
+                         f"the reference is undefined for these, core.pyx:34)")
+
+
+def align(value: torch.Tensor, t_x, t_y, *, dense_path: bool = True, path_dtype=torch.float32,
+          max_neg_val: float = _lib.MAX_NEG_VAL, check: bool = False) -> AlignmentResult:
+    """Monotonic Alignment Search from explicit lengths.
+
+    Replaces maximum_path_c (reference model/monotonic_align/core.pyx:40-45) and the
+    D2H/H2D bounce around it.  `value` [B,Tx,Ty] float32 CUDA, unit stride along Ty,
+    is not modified.  Bit-exact with the reference path for every defined input.
+    """
+    _need_cuda(value, "value")
+    if value.dim() != 3 or value.dtype != torch.float32:
+        raise ValueError("value must be a float32 [B,Tx,Ty] tensor")
+    if value.stride(2) != 1 or value.stride(1) < value.shape[2]:
+        value = value.contiguous()
+    B, Tx, Ty = value.shape
+    dev = value.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        t_x = _lengths(t_x, B, dev, "t_x")
+        t_y = _lengths(t_y, B, dev, "t_y")
+        path = torch.empty((B, Tx, Ty), dtype=path_dtype, device=dev) if dense_path else None
+        dur = torch.empty((B, Tx), dtype=torch.int32, device=dev)
+        ft = torch.empty((B, Ty), dtype=torch.int32, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        ws_bytes = L.mas_b200_workspace_bytes(B, Tx, Ty)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = L.mas_b200_maximum_path(
+            value.data_ptr(), value.stride(0), value.stride(1), t_x.data_ptr(), t_y.data_ptr(), B, Tx, Ty,
+            max_neg_val, path.data_ptr() if dense_path else None,
+            _path_dtype_code(path_dtype) if dense_path else _lib.PATH_NONE,
+            dur.data_ptr(), ft.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "mas_b200_maximum_path")
+        if check:
+            _raise_on_bad(status, "align")
+    return AlignmentResult(path, dur, ft, status)
+
+
+def lengths_from_mask(mask: torch.Tensor):
+    """t_x, t_y (int32 [B]) from a dense prefix mask [B,Tx,Ty], as reference
+    model/monotonic_align/__init__.py:20-21: column 0 summed over x, row 0 summed over y."""
+    _need_cuda(mask, "mask")
+    B, Tx, Ty = mask.shape
+    dev = mask.device
+    if mask.dtype == torch.float32 and mask.is_contiguous():
+        with torch.cuda.device(dev):
+            t_x = torch.empty((B,), dtype=torch.int32, device=dev)
+            t_y = torch.empty((B,), dtype=torch.int32, device=dev)
+            rc = _lib.lib().mas_b200_lengths_from_mask(mask.data_ptr(), B, Tx, Ty, t_x.data_ptr(), t_y.data_ptr(),
+                                                       _stream_ptr(dev))
+            _lib.check(rc, "mas_b200_lengths_from_mask")
+        return t_x, t_y
+    # other dtypes / layouts: two thin strided reductions on the device (plumbing, not the hot path)
+    t_x = mask[:, :, 0].to(torch.float32).sum(1).to(torch.int32)
+    t_y = mask[:, 0, :].to(torch.float32).sum(1).to(torch.int32)
+    return t_x, t_y
+
+
+def log_prior(mu_x: torch.Tensor, y: torch.Tensor, impl: str = "auto") -> torch.Tensor:
+    """Grad-TTS log-prior [B,Tx,Ty] (reference model/face_tts.py:165-171), fp32, within 1e-4
+    relative of the torch expression.  mu_x [B,F,Tx], y [B,F,Ty] float32 CUDA."""
+    _need_cuda(mu_x, "mu_x")
+    _need_cuda(y, "y")
+    if mu_x.dim() != 3 or y.dim() != 3 or mu_x.shape[:2] != y.shape[:2]:
+        raise ValueError("mu_x [B,F,Tx] and y [B,F,Ty] must agree on B and F")
+    mu_x = mu_x.detach().to(torch.float32).contiguous()
+    y = y.detach().to(torch.float32).contiguous()
+    B, F, Tx = mu_x.shape
+    Ty = y.shape[2]
+    dev = mu_x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, Tx, Ty), dtype=torch.float32, device=dev)
+        rc = _lib.lib().mas_b200_log_prior(mu_x.data_ptr(), y.data_ptr(), B, F, Tx, Ty, out.data_ptr(),
+                                           _IMPL[impl], _stream_ptr(dev))
+        _lib.check(rc, "mas_b200_log_prior")
+    return out
+
+
+def log_prior_maximum_path(mu_x: torch.Tensor, y: torch.Tensor, x_lengths, y_lengths, *,
+                           dense_path: bool = True, path_dtype=torch.float32, impl: str = "auto",
+                           max_neg_val: float = _lib.MAX_NEG_VAL, check: bool = False) -> AlignmentResult:
+    """Fused log-prior + MAS: the whole block reference model/face_tts.py:165-174 in one call.
+    mu_x [B,F,Tx], y [B,F,Ty] float32 CUDA; x_lengths/y_lengths [B] true lengths."""
+    _need_cuda(mu_x, "mu_x")
+    _need_cuda(y, "y")
+    if mu_x.dim() != 3 or y.dim() != 3 or mu_x.shape[:2] != y.shape[:2]:
+        raise ValueError("mu_x [B,F,Tx] and y [B,F,Ty] must agree on B and F")
+    mu_x = mu_x.detach().to(torch.float32).contiguous()
+    y = y.detach().to(torch.float32).contiguous()
+    B, F, Tx = mu_x.shape
+    Ty = y.shape[2]
+    dev = mu_x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        t_x = _lengths(x_lengths, B, dev, "x_lengths")
+        t_y = _lengths(y_lengths, B, dev, "y_lengths")
+        path = torch.empty((B, Tx, Ty), dtype=path_dtype, device=dev) if dense_path else None
+        dur = torch.empty((B, Tx), dtype=torch.int32, device=dev)
+        ft = torch.empty((B, Ty), dtype=torch.int32, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, Tx, Ty)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = L.mas_b200_log_prior_maximum_path(
+            mu_x.data_ptr(), y.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), B, F, Tx, Ty, max_neg_val,
+            path.data_ptr() if dense_path else None,
+            _path_dtype_code(path_dtype) if dense_path else _lib.PATH_NONE,
+            dur.data_ptr(), ft.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, _IMPL[impl],
+            _stream_ptr(dev))
+        _lib.check(rc, "mas_b200_log_prior_maximum_path")
+        if check:
+            _raise_on_bad(status, "log_prior_maximum_path")
+    return AlignmentResult(path, dur, ft, status)
+
+
+def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Drop-in for reference model/utils.py:27-40 generate_path(duration, mask):
+    duration [B,Tx] (integer-valued), mask [B,Tx,Ty] prefix mask -> path [B,Tx,Ty] in mask.dtype."""
+    _need_cuda(duration, "duration")
+    _need_cuda(mask, "mask")
+    B, Tx, Ty = mask.shape
+    dev = mask.device
+    t_x, t_y = lengths_from_mask(mask)
+    with torch.cuda.device(dev):
+        d = duration.detach().to(torch.int32).contiguous()
+        path = torch.empty((B, Tx, Ty), dtype=torch.float32, device=dev)
+        rc = _lib.lib().mas_b200_generate_path(d.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), B, Tx, Ty,
+                                               path.data_ptr(), _lib.PATH_F32, _stream_ptr(dev))
+        _lib.check(rc, "mas_b200_generate_path")
+    return path if mask.dtype == torch.float32 else path.to(mask.dtype)
+
+
+def durations_to_logw(durations: torch.Tensor, x_mask: torch.Tensor) -> torch.Tensor:
+    """logw_ = log(1e-8 + sum_t attn) * x_mask  (reference model/face_tts.py:176) straight from the
+    integer durations the backtrack emits -- no dense re-read.  x_mask [B,1,Tx] -> [B,1,Tx]."""
+    return torch.log(1e-8 + durations.to(x_mask.dtype).unsqueeze(1)) * x_mask
+
+
+LOG_PRIOR_CONST_PER_FEAT = -0.5 * math.log(2 * math.pi)

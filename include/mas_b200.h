@@ -1,0 +1,184 @@
+/*
+ * mas_b200.h -- C ABI of the B200-native (sm_100a) log-prior + Monotonic
+ * Alignment Search library, libmas_b200.so.
+ *
+ * This is the drop-in boundary for the ONE native component of
+ * CognitiveModeling/Face-GAN-TTS, model/monotonic_align (a Cython module run
+ * on the CPU every training step), plus the torch log-prior block that feeds
+ * it.  Each entry point cites the reference interface it replaces; paths are
+ * relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain C: raw pointers + sizes, no torch / C++ types.
+ *   - every `*_dev` pointer is DEVICE memory owned by the caller; `stream` is
+ *     a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     asynchronous and stream-ordered; nothing synchronises the host.
+ *   - the library keeps no global mutable state: calls are thread-safe.
+ *   - return value: MAS_B200_OK or a negative MAS_B200_ERR_* code (argument
+ *     errors are detected on the host before anything is launched).  Per-item
+ *     data errors that only the device can see (t_x > t_y, t_x < 1: undefined
+ *     behaviour in the reference, core.pyx:34) are reported through the
+ *     optional `status_dev` array and leave that item's outputs all zero.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point returns MAS_B200_ERR_CUDA.
+ */
+#ifndef MAS_B200_H_
+#define MAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAS_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define MAS_B200_OK               0
+#define MAS_B200_ERR_ARG         -1  /* null pointer / non-positive size / bad enum      */
+#define MAS_B200_ERR_UNSUPPORTED -2  /* shape outside what the kernels cover             */
+#define MAS_B200_ERR_WORKSPACE   -3  /* workspace pointer null or too small              */
+#define MAS_B200_ERR_CUDA        -4  /* CUDA runtime error (see mas_b200_last_cuda_error) */
+#define MAS_B200_ERR_ALIGN       -5  /* pointer not aligned as the entry point requires  */
+
+/* per-item codes written to status_dev[b] */
+#define MAS_B200_ITEM_OK          0
+#define MAS_B200_ITEM_BAD_LENGTH  1  /* t_x < 1, t_y < 1, t_x > Tx, t_y > Ty or t_x > t_y */
+
+/* dtype of the dense path output */
+#define MAS_B200_PATH_NONE 0   /* do not materialise the dense path            */
+#define MAS_B200_PATH_F32  1   /* float32 {0,1}  (what maximum_path returns)    */
+#define MAS_B200_PATH_I32  2   /* int32 {0,1}    (what maximum_path_c fills)    */
+
+/* log-prior implementation selector */
+#define MAS_B200_LP_AUTO   0
+#define MAS_B200_LP_FFMA   1   /* fp32 CUDA-core contraction                     */
+#define MAS_B200_LP_TCGEN05 2  /* tcgen05/TMEM split-bf16 contraction (sm_100a)  */
+
+/* default of core.pyx:40 */
+#define MAS_B200_MAX_NEG_VAL (-1e9f)
+
+int         mas_b200_abi_version(void);
+const char *mas_b200_error_string(int status);
+/* cudaError_t of the last failing CUDA call made by the calling thread, 0 if none. */
+int         mas_b200_last_cuda_error(void);
+
+/* Bytes of device workspace the calls below need for (B, Tx, Ty).  Holds the
+ * per-token [start, duration] table the backtrack emits, and, for shapes whose
+ * direction bits (1 bit / cell) do not fit shared memory, the bit planes. */
+size_t mas_b200_workspace_bytes(int B, int Tx, int Ty);
+
+/*
+ * t_x[b] = sum_x mask[b,x,0], t_y[b] = sum_y mask[b,0,y]  (as int32, truncated).
+ * Replaces: model/monotonic_align/__init__.py:18-21 (D2H of the whole mask +
+ * numpy sums).  mask_dev: [B,Tx,Ty] float32 contiguous prefix mask.
+ */
+int mas_b200_lengths_from_mask(const float *mask_dev, int B, int Tx, int Ty,
+                               int *t_x_dev, int *t_y_dev, void *stream);
+
+/*
+ * Monotonic Alignment Search on device buffers.
+ * Replaces: maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)
+ *           model/monotonic_align/core.pyx:40-45 (+ maximum_path_each :9-35)
+ * and the D2H/H2D bounce around it (model/monotonic_align/__init__.py:16-23).
+ *
+ *   value_dev   [B,Tx,Ty] float32, element (b,x,y) at b*stride_b + x*stride_x + y
+ *               (unit stride along y).  NOT modified (the reference clobbers
+ *               its private host copy; here the caller still owns the tensor).
+ *               Cells outside [0,t_x) x [0,t_y) are never read, so the
+ *               reference's `value * mask` (__init__.py:13) is not needed.
+ *   t_x_dev, t_y_dev   [B] int32 true lengths, 1 <= t_x <= t_y.
+ *   path_dev    [B,Tx,Ty] contiguous, dtype per path_dtype; fully written
+ *               (zeros included); may be NULL with MAS_B200_PATH_NONE.
+ *   durations_dev   [B,Tx] int32 = row sums of the path (what
+ *               model/face_tts.py:176 recovers by re-reading the dense path);
+ *               0 beyond t_x.  May be NULL.
+ *   frame_token_dev [B,Ty] int32: the token index of each frame, -1 beyond
+ *               t_y.  May be NULL.
+ *   status_dev  [B] int32 per-item code, may be NULL.
+ *   workspace_dev / workspace_bytes   >= mas_b200_workspace_bytes(B,Tx,Ty),
+ *               256-byte aligned.
+ * Bit-exact with the reference for every defined input (same fp32 max/add
+ * order, same tie-breaking, same -1e9 substitutions, same NaN behaviour).
+ */
+int mas_b200_maximum_path(const float *value_dev, long long stride_b, long long stride_x,
+                          const int *t_x_dev, const int *t_y_dev,
+                          int B, int Tx, int Ty, float max_neg_val,
+                          void *path_dev, int path_dtype,
+                          int *durations_dev, int *frame_token_dev, int *status_dev,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/*
+ * Grad-TTS log-prior, unfused (materialises [B,Tx,Ty]).
+ * Replaces: model/face_tts.py:165-171
+ *   log_prior[b,x,t] = -0.5*sum_f y[b,f,t]^2 + sum_f mu_x[b,f,x]*y[b,f,t]
+ *                      - 0.5*sum_f mu_x[b,f,x]^2 - 0.5*F*log(2*pi)
+ * combined in the reference's order ((y_square - y_mu_double) + mu_square) + const.
+ *   mu_x_dev [B,F,Tx] float32 contiguous; y_dev [B,F,Ty] float32 contiguous;
+ *   log_prior_dev [B,Tx,Ty] float32 contiguous.
+ * Within 1e-4 relative of the torch fp32 expression.
+ */
+int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev,
+                       int B, int F, int Tx, int Ty,
+                       float *log_prior_dev, int impl, void *stream);
+
+/*
+ * Fused log-prior + MAS: mu_x, y -> path / durations without the [B,Tx,Ty]
+ * value matrix ever being written to HBM when the fused kernel covers the
+ * shape (otherwise the library runs mas_b200_log_prior into the workspace and
+ * mas_b200_maximum_path, still entirely on the device).
+ * Replaces: model/face_tts.py:165-174 (log-prior block + maximum_path call).
+ * workspace: >= mas_b200_fused_workspace_bytes(B,F,Tx,Ty).
+ */
+size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty);
+int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,
+                                    const int *t_x_dev, const int *t_y_dev,
+                                    int B, int F, int Tx, int Ty, float max_neg_val,
+                                    void *path_dev, int path_dtype,
+                                    int *durations_dev, int *frame_token_dev, int *status_dev,
+                                    void *workspace_dev, size_t workspace_bytes,
+                                    int impl, void *stream);
+
+/*
+ * Dense path from integer durations (the inverse op, used at inference).
+ * Replaces: generate_path(duration, mask)  model/utils.py:27-40
+ *   path[b,x,y] = 1 iff cum[b,x-1] <= y < cum[b,x], x < t_x, y < t_y
+ * durations_dev [B,Tx] int32; t_x_dev/t_y_dev [B] int32 (the prefix mask).
+ */
+int mas_b200_generate_path(const int *durations_dev, const int *t_x_dev, const int *t_y_dev,
+                           int B, int Tx, int Ty, void *path_dev, int path_dtype, void *stream);
+
+/*
+ * HOST-buffer drop-in with the exact argument meaning of the Cython
+ * maximum_path_c (model/monotonic_align/core.pyx:40): `paths` int32 [B,Tx,Ty]
+ * (overwritten; need not be pre-zeroed), `values` float32 [B,Tx,Ty] (NOT
+ * clobbered), t_xs/t_ys int32 [B], all in host memory.  Copies to the current
+ * device, runs mas_b200_maximum_path, copies the result back and
+ * synchronises.  Returns the number of rejected items (>= 0) or a negative
+ * MAS_B200_ERR_*.
+ */
+int mas_b200_maximum_path_host(int *paths, const float *values,
+                               const int *t_xs, const int *t_ys,
+                               int B, int Tx, int Ty, float max_neg_val);
+
+/*
+ * HOST-buffer fused call: mu_x [B,F,Tx], y [B,F,Ty], t_xs, t_ys in host memory
+ * -> durations [B,Tx], frame_token [B,Ty] and (if paths != NULL) the dense
+ * int32 path in host memory.  Same return convention as above.
+ */
+int mas_b200_log_prior_maximum_path_host(const float *mu_x, const float *y,
+                                         const int *t_xs, const int *t_ys,
+                                         int B, int F, int Tx, int Ty, float max_neg_val,
+                                         int *paths, int *durations, int *frame_token);
+
+/* Tuning/diagnostic knobs (not part of the reference interface).
+ * mas_b200_set_option("mas_rows_per_lane", R) etc.; returns previous value or
+ * INT32_MIN for an unknown key.  Process-wide, read at launch time. */
+int mas_b200_set_option(const char *key, int value);
+int mas_b200_get_option(const char *key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H_ */

@@ -1,0 +1,106 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads without a GPU and
+exports every symbol include/mas_b200.h declares; host-side argument validation and
+the no-CPU-fallback contract."""
+import os
+import re
+import ctypes
+
+import numpy as np
+import pytest
+
+from face_gan_tts_b200 import _lib
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mas_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mas_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mas_b200.h but not exported"
+    # and the Python binding covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_error_strings():
+    L = _lib.lib()
+    assert L.mas_b200_abi_version() == 1
+    assert L.mas_b200_error_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert L.mas_b200_error_string(code)
+
+
+def test_workspace_sizes_are_monotone_and_aligned():
+    L = _lib.lib()
+    a = L.mas_b200_workspace_bytes(32, 190, 1000)
+    b = L.mas_b200_workspace_bytes(64, 190, 1000)
+    c = L.mas_b200_workspace_bytes(64, 512, 4096)
+    assert 0 < a < b < c and a % 256 == 0
+    assert L.mas_b200_workspace_bytes(0, 1, 1) == 0
+    f = L.mas_b200_fused_workspace_bytes(32, 80, 190, 1000)
+    assert f >= a + 32 * 190 * 1000 * 4
+
+
+def test_options_roundtrip():
+    prev = _lib.set_option("mas_rows_per_lane", 4)
+    assert _lib.get_option("mas_rows_per_lane") == 4
+    _lib.set_option("mas_rows_per_lane", prev)
+    with pytest.raises(KeyError):
+        _lib.get_option("no_such_option")
+
+
+def test_host_argument_validation_happens_before_any_cuda_call():
+    L = _lib.lib()
+    assert L.mas_b200_maximum_path(None, 0, 0, None, None, 1, 1, 1, -1e9, None, 0, None, None, None, None, 0, None) == _lib.ERR_ARG
+    assert L.mas_b200_log_prior(None, None, 1, 80, 1, 1, None, 0, None) == _lib.ERR_ARG
+    assert L.mas_b200_generate_path(None, None, None, 1, 1, 1, None, 1, None) == _lib.ERR_ARG
+    assert L.mas_b200_maximum_path_host(None, None, None, None, 1, 1, 1, -1e9) == _lib.ERR_ARG
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the compute entry points must FAIL, never fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from face_gan_tts_b200 import monotonic_align
+
+    with pytest.raises(RuntimeError):
+        monotonic_align.maximum_path(torch.zeros(1, 2, 3), torch.ones(1, 2, 3))
+    with pytest.raises(_lib.MasB200Error):
+        monotonic_align.core.maximum_path_c(np.zeros((1, 2, 3), np.int32), np.zeros((1, 2, 3), np.float32),
+                                            np.array([2], np.int32), np.array([3], np.int32))
+    with pytest.raises(ValueError):
+        import face_gan_tts_b200 as f
+
+        f.align(torch.zeros(1, 2, 3), [2], [3])
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no file of the product package may reference it."""
+    pkg = os.path.join(ROOT, "face-gan-tts_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "mas_oracle" not in txt, fn
+
+
+def test_install_shim_registers_reference_import_names():
+    import sys
+    import face_gan_tts_b200 as f
+
+    ma = f.install()
+    try:
+        assert sys.modules["model.monotonic_align"] is ma
+        assert sys.modules["model.monotonic_align.model.monotonic_align.core"].maximum_path_c is ma.core.maximum_path_c
+    finally:
+        f.uninstall()
+    assert "model.monotonic_align" not in sys.modules
