@@ -5,6 +5,7 @@
 // in shared memory.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -13,7 +14,7 @@
 namespace masb200 {
 
 constexpr int kTileFrames = 32;        // mel frames per tile == bits per direction word
-constexpr int kTilePitch = 36;         // floats per text-position row of a value tile (32 + 4 pad, see below)
+constexpr int kTilePitch = 32;         // floats per text-position row of a value tile (one 128-byte swizzle row)
 constexpr unsigned kFullMask = 0xffffffffu;
 
 // ---------------------------------------------------------------------------
@@ -63,15 +64,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------
-// TMA bulk copy global -> shared (1-D, no tensor map): one row segment per
-// instruction, completion counted in bytes on an mbarrier.  src, dst and
-// `bytes` must be multiples of 16.
+// TMA tensor-map load global -> shared (3-D tiled box), completion counted in bytes
+// on an mbarrier.  SASS: UTMALDG.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2,
+                                            uint64_t *bar) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
 
@@ -99,18 +99,30 @@ __device__ __forceinline__ int flag_wait_ge(const int *flag, int target) {
 // ---------------------------------------------------------------------------
 // Value tile in shared memory: kTileFrames frames of up to XP text positions.
 //
-// Row x (text position, local to the row pass) is stored as 32 consecutive
-// frames at SLOT sigma(x) with a pitch of kTilePitch = 36 floats (144 bytes):
+// Row x (text position, local to the row pass) is stored as 32 consecutive frames
+// (128 bytes) at SLOT sigma(x):
 //     sigma(x) = (x % R) * (XP / R) + x / R          (R = rows per DP lane)
-// so the rows that the 32 lanes of a warp read in the same instruction
-// (same r = x % R, consecutive lanes) sit in consecutive slots, and because
-// 144 B = 9 * 16 B, a quarter-warp's eight 16-byte loads hit eight distinct
-// 16-byte bank groups: conflict-free LDS.128 of 4 consecutive frames per row.
-// Each row is an independent TMA bulk copy, so the permutation costs nothing.
+// so the rows the 32 lanes of a warp read in the same instruction (same r = x % R,
+// consecutive lanes) sit in consecutive slots.  Inside a slot the eight 16-byte
+// chunks (4 frames each) are XOR-permuted by the slot index, chunk c at position
+// c ^ (slot & 7): exactly the TMA/UMMA 128-byte swizzle, so a tensor-map load with
+// box {32 frames, NB*R rows} and elementStrides {1, R} drops the rows
+// {r, r+R, r+2R, ...} of a tile straight into this layout -- R (or a few more)
+// TMA requests per 32-frame tile, each several KB.  A quarter-warp's eight 16-byte
+// reads of one chunk then hit eight distinct bank groups: conflict-free LDS.128.
+// slot & 7 == lane & 7 for every row of a lane (XP/R is a multiple of 8).
 // ---------------------------------------------------------------------------
 template <int R, int XP>
 __device__ __forceinline__ int tile_slot(int x_local) {
     return (x_local % R) * (XP / R) + x_local / R;
+}
+
+// lanes (= rows of one residue r) covered by one TMA box: a multiple of 32 that divides
+// XP/R and keeps the traversed extent NB*R within the 256-element box limit.
+__host__ __device__ constexpr int tma_box_lanes(int R, int W) {
+    for (int wb = 4; wb >= 1; --wb)
+        if (W % wb == 0 && 32 * wb * R <= 256) return 32 * wb;
+    return 32;
 }
 
 }  // namespace masb200

@@ -21,12 +21,15 @@
 //     substitutes v_cur = max_neg_val exactly like the reference.
 //
 // CTA organisation (template R rows per lane, W DP warps; XP = 32*R*W rows):
-//   producer warp W      one TMA bulk copy (cp.async.bulk, 128 B) per text position per
+//   producer warp W      a handful of TMA tensor-map loads (cp.async.bulk.tensor, box
+//                        {32 frames, NB*R rows}, elementStrides {1,R}, 128B swizzle) per
 //                        32-frame tile into an NS-deep shared-memory ring, completion
-//                        counted on an mbarrier; rows are placed at permuted, padded
-//                        slots (mas_common.cuh) so DP reads are conflict-free.  The ring
-//                        depth is what keeps ~50-150 KB in flight per SM -- enough to
-//                        stream a CTA's value matrix at HBM latency.
+//                        counted on an mbarrier; the strided boxes land the rows in the
+//                        lane-major permuted layout of mas_common.cuh so DP reads are
+//                        conflict-free.  The ring depth keeps ~50-150 KB in flight per SM
+//                        -- enough to stream a CTA's value matrix at HBM latency.  (A first
+//                        version issued one 128-byte bulk copy per row: 6080 requests per
+//                        utterance at ~30 ns each made the kernel request-rate bound.)
 //   DP warps 0..W-1      lane l of warp w owns the R consecutive text positions
 //                        x = rows_base + (32w + l)*R + r.  Per mel frame the lane
 //                        updates its R rows top-down from registers; only row 0 needs a
@@ -73,6 +76,7 @@ struct MasParams {
     int line_pitch;
     void *path;              // optional in-kernel dense path write
     int path_dtype;          // MAS_B200_PATH_*
+    long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
 // One cell of the recurrence; the bit is set iff the diagonal predecessor wins.
@@ -110,9 +114,10 @@ __device__ __forceinline__ float mas_cell(float v_cur, float v_prev, float v, ui
 //   src     lane the rotate-shuffle reads from: (lane + 31) & 31; lane 31 injects the halo
 //   dl      lane_global - (t0+kb)/R  (DIAG only): the lane owns the diagonal cell of frame
 //           t0+kb+i, in row r = i % R, exactly when dl == i / R
-//   lbase   &stage[lane_cta * kTilePitch + kb]
+//   lbase   &stage[lane_cta * kTilePitch]; o0 = swizzled float offset of frames kb..kb+3 in the
+//           lane's rows, ((kb >> 2) ^ (lane & 7)) << 2; frames kb+4..kb+7 sit at o0 ^ 4
 template <int R, int XP, int CELL, bool DIAG, bool HALO_OUT>
-__device__ __forceinline__ void dp_frames8(float (&q)[R], uint32_t (&acc)[R], const float *lbase, int kb,
+__device__ __forceinline__ void dp_frames8(float (&q)[R], uint32_t (&acc)[R], const float *lbase, int kb, int o0,
                                            const float (&h)[8], int lane, int src, int dl, float neg,
                                            float *halo_out) {
     constexpr int kRowStride = (XP / R) * kTilePitch;      // floats between the lane's consecutive rows
@@ -123,7 +128,8 @@ __device__ __forceinline__ void dp_frames8(float (&q)[R], uint32_t (&acc)[R], co
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-        for (int r = 0; r < R; ++r) v4[hh][r] = *reinterpret_cast<const float4 *>(lbase + r * kRowStride + 4 * hh);
+        for (int r = 0; r < R; ++r)
+            v4[hh][r] = *reinterpret_cast<const float4 *>(lbase + r * kRowStride + (hh == 0 ? o0 : (o0 ^ 4)));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         // one shuffle per frame: lane l reads lane l-1's last row; lane 0 reads lane 31, which sends the halo
@@ -160,7 +166,7 @@ __device__ __forceinline__ void dp_frame_generic(float (&q)[R], uint32_t (&acc)[
     float n[R];
 #pragma unroll
     for (int r = R - 1; r >= 0; --r) {
-        const float v = lane_row0[r * kRowStride + k];
+        const float v = lane_row0[r * kRowStride + ((((k >> 2) ^ (lane & 7)) << 2) | (k & 3))];
         const float v_cur = (x0 + r >= t) ? neg : q[r];
         const float v_prev = (r == 0) ? up : q[r - 1];
         n[r] = mas_cell<0>(v_cur, v_prev, v, acc[r], k);
@@ -248,7 +254,8 @@ __device__ __forceinline__ void write_path_any(const MasParams &P, int b, const 
 }
 
 template <int R, int W, bool SMEM_BITS, int CELL>
-__global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasParams P) {
+__global__ void __launch_bounds__((W + 1) * 32, 1)
+mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) {
     using S = MasSmem<R, W>;
     constexpr int XP = S::XP;
     constexpr int NT = kTileFrames;
@@ -291,6 +298,9 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
 
     const int ntiles = (t_y + NT - 1) / NT;
     const int npass = (t_x + XP - 1) / XP;
+    long long *dbg = P.dbg ? P.dbg + (size_t)b * 8 : nullptr;
+    long long dbg_wait = 0;
+    if (dbg && tid == 0) dbg[0] = clock64();
     uint32_t *gbits_b = SMEM_BITS ? nullptr : P.gbits + (size_t)b * P.gbits_stride_b;
     float *gline_b = P.gline ? P.gline + (size_t)b * 2 * P.line_pitch : nullptr;
     const float *vb = P.value + (size_t)b * P.stride_b;
@@ -325,12 +335,18 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
                 const int t0 = j * NT;
                 const int nfr = min(NT, P.Ty - t0);                 // frames that exist in memory
                 if (P.aligned) {
-                    if (lane == 0) mbar_arrive_expect_tx(&ring_full[stage], (uint32_t)rows_here * nfr * 4u);
+                    // lane i issues request (r, qb): rows {rows_base + (qb*NB + l)*R + r : l < NB}
+                    constexpr int NB = tma_box_lanes(R, W);
+                    constexpr int REQS = (XP / R) / NB;
+                    const int rr = lane / REQS, qb = lane - rr * REQS;
+                    const int row0 = rows_base + qb * NB * R + rr;           // first row of the box
+                    const bool issue = (lane < R * REQS) && (row0 < t_x);
+                    const unsigned m = __ballot_sync(kFullMask, issue);
+                    if (lane == 0) mbar_arrive_expect_tx(&ring_full[stage], (uint32_t)__popc(m) * NB * 128u);
                     __syncwarp();
-                    for (int xl = lane; xl < rows_here; xl += 32)
-                        tma_bulk_g2s(dst + tile_slot<R, XP>(xl) * kTilePitch,
-                                     vb + (size_t)(rows_base + xl) * P.stride_x + t0, (uint32_t)nfr * 4u,
-                                     &ring_full[stage]);
+                    if (issue)
+                        tma_load_3d(dst + (rr * (XP / R) + qb * NB) * kTilePitch, &tmap, t0, row0, b,
+                                    &ring_full[stage]);
                 } else {
                     // unaligned fallback: lane = frame, 8 rows in flight
                     const bool tin = lane < nfr;
@@ -342,8 +358,12 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
                             v[u] = (tin && xl0 + u < rows_here)
                                        ? __ldcs(src + (size_t)(rows_base + xl0 + u) * P.stride_x) : 0.f;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (xl0 + u < rows_here) dst[tile_slot<R, XP>(xl0 + u) * kTilePitch + lane] = v[u];
+                        for (int u = 0; u < 8; ++u) {
+                            if (xl0 + u < rows_here) {
+                                const int sl = tile_slot<R, XP>(xl0 + u);
+                                dst[sl * kTilePitch + ((((lane >> 2) ^ (sl & 7)) << 2) | (lane & 3))] = v[u];
+                            }
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ring_full[stage]);
@@ -389,7 +409,14 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
                         hv_tile = (lane == 0) ? carry : gl_in[t0 + lane - 1];
                         carry = gl_in[t0 + 31];
                     }
-                    mbar_wait(&ring_full[stage], phase);
+                    if (dbg) {
+                        const long long c0 = clock64();
+                        mbar_wait(&ring_full[stage], phase);
+                        dbg_wait += clock64() - c0;
+                        if (j == 0 && lane == 0) dbg[1] = clock64();
+                    } else {
+                        mbar_wait(&ring_full[stage], phase);
+                    }
                 }
                 const float *st_lane = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
 
@@ -410,17 +437,18 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
                     }
                     float *hout = hb_out + hs * 8;
                     const int tb = t0 + kb;
+                    const int o0 = ((kb >> 2) ^ (lane & 7)) << 2;
                     const bool below_diag = (tb + 7 < xw0);           // every row of the warp has x > y
                     if (!below_diag) {
                         if (kb + 8 <= kmax) {
                             const bool diag = (tb < xw0 + 32 * R);
                             const int dl = lane_glob - tb / R;
                             if (halo_out) {
-                                if (diag) dp_frames8<R, XP, CELL, true, true>(q, acc, st_lane + kb, kb, h, lane, src, dl, P.neg, hout);
-                                else dp_frames8<R, XP, CELL, false, true>(q, acc, st_lane + kb, kb, h, lane, src, dl, P.neg, hout);
+                                if (diag) dp_frames8<R, XP, CELL, true, true>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
+                                else dp_frames8<R, XP, CELL, false, true>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
                             } else {
-                                if (diag) dp_frames8<R, XP, CELL, true, false>(q, acc, st_lane + kb, kb, h, lane, src, dl, P.neg, hout);
-                                else dp_frames8<R, XP, CELL, false, false>(q, acc, st_lane + kb, kb, h, lane, src, dl, P.neg, hout);
+                                if (diag) dp_frames8<R, XP, CELL, true, false>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
+                                else dp_frames8<R, XP, CELL, false, false>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
                             }
                         } else {
 #pragma unroll
@@ -456,8 +484,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
                 if (++stage == NS) { stage = 0; phase ^= 1; }
             }
         }
+        if (dbg && tid == 0) { dbg[2] = clock64(); dbg[3] = dbg_wait; }   // warp 0 done with this pass
         __syncthreads();
     }
+    if (dbg && tid == 0) dbg[4] = clock64();                               // all DP warps done
 
     // ================================ backtrack ================================
     // Token walk.  State (x, y_end, y): token x owns frames (y, y_end] so far; find the
@@ -506,6 +536,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
         __syncthreads();
     }
 
+    if (dbg && tid == 0) dbg[5] = clock64();                               // backtrack done
     // ================================= outputs =================================
     for (int x = t_x + tid; x < P.Tx; x += nthreads) { start_b[x] = 0; dur_b[x] = 0; }
     if (P.frame_token) {
@@ -518,6 +549,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) mas_forward_kernel(const MasP
     }
     __syncthreads();
     write_path_any(P, b, start_b, dur_b, tid, nthreads);
+    if (dbg && tid == 0) { dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y; }
 }
 
 }  // namespace masb200

@@ -13,37 +13,37 @@ namespace masb200 {
 
 namespace {
 
-constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+constexpr size_t kMaxSmem = 232448 - 1024;   // must match mas_forward.cu
 
 template <int R, int W, bool SB, int CELL>
-int launch_inst(const MasParams &P, size_t smem, cudaStream_t stream) {
+int launch_inst(const MasParams &P, const CUtensorMap &tmap, size_t smem, cudaStream_t stream) {
     static std::atomic<int> configured[16];
     int dev = 0;
     MASB200_CUDA_TRY(cudaGetDevice(&dev));
     auto kern = mas_forward_kernel<R, W, SB, CELL>;
     if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
-        MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem - 1024));
+        MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
     }
-    kern<<<P.B, (W + 1) * 32, smem, stream>>>(P);
+    kern<<<P.B, (W + 1) * 32, smem, stream>>>(P, tmap);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }
 
 template <int R, int W>
-int launch_w(const MasParams &P, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
+int launch_w(const MasParams &P, const CUtensorMap &tmap, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
     if (cell == 0)
-        return smem_bits ? launch_inst<R, W, true, 0>(P, smem, stream) : launch_inst<R, W, false, 0>(P, smem, stream);
-    return smem_bits ? launch_inst<R, W, true, 1>(P, smem, stream) : launch_inst<R, W, false, 1>(P, smem, stream);
+        return smem_bits ? launch_inst<R, W, true, 0>(P, tmap, smem, stream) : launch_inst<R, W, false, 0>(P, tmap, smem, stream);
+    return smem_bits ? launch_inst<R, W, true, 1>(P, tmap, smem, stream) : launch_inst<R, W, false, 1>(P, tmap, smem, stream);
 }
 
 template <int R>
-int launch_r(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
+int launch_r(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
     switch (W) {
-        case 1: return launch_w<R, 1>(P, smem_bits, cell, smem, stream);
-        case 2: return launch_w<R, 2>(P, smem_bits, cell, smem, stream);
-        case 3: return launch_w<R, 3>(P, smem_bits, cell, smem, stream);
-        case 4: return launch_w<R, 4>(P, smem_bits, cell, smem, stream);
+        case 1: return launch_w<R, 1>(P, tmap, smem_bits, cell, smem, stream);
+        case 2: return launch_w<R, 2>(P, tmap, smem_bits, cell, smem, stream);
+        case 3: return launch_w<R, 3>(P, tmap, smem_bits, cell, smem, stream);
+        case 4: return launch_w<R, 4>(P, tmap, smem_bits, cell, smem, stream);
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
 }
@@ -53,9 +53,9 @@ int launch_r(const MasParams &P, int W, bool smem_bits, int cell, size_t smem, c
 #define MASB200_CAT2(a, b) a##b
 #define MASB200_CAT(a, b) MASB200_CAT2(a, b)
 
-int MASB200_CAT(launch_mas_r, MASB200_INST_R)(const MasParams &P, int W, bool smem_bits, int cell, size_t smem,
-                                              cudaStream_t stream) {
-    return launch_r<MASB200_INST_R>(P, W, smem_bits, cell, smem, stream);
+int MASB200_CAT(launch_mas_r, MASB200_INST_R)(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits,
+                                              int cell, size_t smem, cudaStream_t stream) {
+    return launch_r<MASB200_INST_R>(P, tmap, W, smem_bits, cell, smem, stream);
 }
 
 }  // namespace masb200
