@@ -22,7 +22,6 @@ Opt g_opts[] = {
     {"mas_ctas_per_sm", {0}},        // smem budget divisor (0 = auto from B)
     {"mas_force_global_bits", {0}},  // 1: direction bits always in global scratch
     {"mas_force_unaligned", {0}},    // 1: never use the TMA bulk path
-    {"mas_cell_impl", {1}},          // 0 portable C cell, 1 predicated-add PTX cell
     {"mas_fused_path_write", {-1}},  // -1 auto, 0 separate expand kernel, 1 in-kernel
     {"mas_debug_ptr_lo", {0}},       // diagnostics only: clock64 phase stamps buffer (device pointer halves)
     {"mas_debug_ptr_hi", {0}},

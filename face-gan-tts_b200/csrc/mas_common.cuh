@@ -53,6 +53,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe of a phase (mbarrier.test_wait never suspends)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must fail the launch (trap -> cudaErrorLaunchFailure),
 // never hang the GPU.  2^31 cycles (~1 s) is far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -61,6 +75,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > (1ll << 31)) __trap();
     }
+}
+// The same for a whole (converged) warp with a WARP-UNIFORM exit: every lane polls, the loop
+// condition is a vote, so ptxas can prove the warp is still converged afterwards (a per-lane exit
+// makes it emit a divergent fallback copy of every following shuffle region and schedule the
+// common path conservatively).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+    const long long t0 = clock64();
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
+__device__ __forceinline__ bool mbar_test_warp(uint64_t *bar, uint32_t parity) {
+    return __all_sync(0xffffffffu, mbar_test(bar, parity));
+}
+// one lane of the (converged) warp; the predicate is produced afresh by the instruction itself
+__device__ __forceinline__ bool elect_one() {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " elect.sync _|p, 0xffffffff;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok));
+    return ok != 0;
+}
+// lane-predicated (branch-free) arrive / release: `pred` selects the one lane that acts
+__device__ __forceinline__ void mbar_arrive_if(uint64_t *bar, uint32_t pred) {
+    asm volatile("{\n"
+                 " .reg .pred p;\n"
+                 " setp.ne.u32 p, %1, 0;\n"
+                 " @p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+                 "}\n" ::"r"(smem_u32(bar)), "r"(pred) : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -85,6 +133,24 @@ __device__ __forceinline__ int flag_acquire(const int *flag) {
     int v;
     asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(flag)) : "memory");
     return v;
+}
+__device__ __forceinline__ void flag_release_if(int *flag, int v, uint32_t pred) {
+    asm volatile("{\n"
+                 " .reg .pred p;\n"
+                 " setp.ne.u32 p, %2, 0;\n"
+                 " @p st.release.cta.shared::cta.s32 [%0], %1;\n"
+                 "}\n" ::"r"(smem_u32(flag)), "r"(v), "r"(pred) : "memory");
+}
+// whole-warp wait with a warp-uniform exit (see mbar_wait_warp); returns the smallest value seen
+__device__ __forceinline__ int flag_wait_ge_warp(const int *flag, int target) {
+    int v = flag_acquire(flag);
+    if (__all_sync(0xffffffffu, v >= target)) return v;
+    const long long t0 = clock64();
+    while (true) {
+        v = flag_acquire(flag);
+        if (__all_sync(0xffffffffu, v >= target)) return v;
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
 }
 __device__ __forceinline__ int flag_wait_ge(const int *flag, int target) {
     int v = flag_acquire(flag);

@@ -11,14 +11,10 @@
 namespace masb200 {
 
 // one translation unit per rows-per-lane value (mas_forward_inst.cu, -DMASB200_INST_R=...)
-int launch_mas_r1(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits, int cell, size_t smem,
-                  cudaStream_t stream);
-int launch_mas_r2(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits, int cell, size_t smem,
-                  cudaStream_t stream);
-int launch_mas_r4(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits, int cell, size_t smem,
-                  cudaStream_t stream);
-int launch_mas_r8(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits, int cell, size_t smem,
-                  cudaStream_t stream);
+int launch_mas_r1(const MasParams &P, const CUtensorMap &tmap, int W, int mode, size_t smem, cudaStream_t stream);
+int launch_mas_r2(const MasParams &P, const CUtensorMap &tmap, int W, int mode, size_t smem, cudaStream_t stream);
+int launch_mas_r4(const MasParams &P, const CUtensorMap &tmap, int W, int mode, size_t smem, cudaStream_t stream);
+int launch_mas_r8(const MasParams &P, const CUtensorMap &tmap, int W, int mode, size_t smem, cudaStream_t stream);
 
 namespace {
 
@@ -35,8 +31,8 @@ constexpr size_t kStaticSmem = 64;           // bt_state + slack
 size_t fixed_bytes_rw(int R, int W, int ns) {
     const int XP = 32 * R * W;
     const size_t ring = sizeof(float) * (size_t)ns * XP * kTilePitch;
-    const size_t halo = sizeof(float) * (size_t)W * (4 * (ns + 1)) * 8;
-    const size_t ctrl = 8 * (size_t)(2 * ns) + 4 * (size_t)W + 64;
+    const size_t halo = sizeof(float) * ((size_t)(W + 1) * (ns + 1) + W) * kTileFrames;
+    const size_t ctrl = 8 * (size_t)(2 * ns) + 4 * (size_t)(W + 2) + 64;
     return ((ring + halo + ctrl + 127) / 128) * 128;
 }
 
@@ -181,12 +177,12 @@ int launch_mas(const MasLaunch &L) {
     P.path = (want_path && fuse) ? L.path : nullptr;
     P.path_dtype = (want_path && fuse) ? L.path_dtype : MAS_B200_PATH_NONE;
 
-    const int cell = option("mas_cell_impl") == 0 ? 0 : 1;
+    const int mode = plan.smem_bits ? MAS_MODE_SMEM_BITS : (L.Tx > XP ? MAS_MODE_MULTIPASS : MAS_MODE_GLOBAL_BITS);
     switch (plan.R) {
-        case 1: rc = launch_mas_r1(P, tmap, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
-        case 2: rc = launch_mas_r2(P, tmap, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
-        case 4: rc = launch_mas_r4(P, tmap, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
-        case 8: rc = launch_mas_r8(P, tmap, plan.W, plan.smem_bits, cell, plan.smem, L.stream); break;
+        case 1: rc = launch_mas_r1(P, tmap, plan.W, mode, plan.smem, L.stream); break;
+        case 2: rc = launch_mas_r2(P, tmap, plan.W, mode, plan.smem, L.stream); break;
+        case 4: rc = launch_mas_r4(P, tmap, plan.W, mode, plan.smem, L.stream); break;
+        case 8: rc = launch_mas_r8(P, tmap, plan.W, mode, plan.smem, L.stream); break;
         default: rc = MAS_B200_ERR_UNSUPPORTED;
     }
     if (rc != MAS_B200_OK) return rc;

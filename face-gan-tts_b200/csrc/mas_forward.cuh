@@ -17,8 +17,9 @@
 //     backtrack re-derives at core.pyx:34 for 1 <= x < y;
 //   * no lower band bound (core.pyx:18's max(0, t_x+y-t_y) is an optimisation: the
 //     in-band recursion is closed and the backtrack never leaves the band);
-//   * cells with x > y are computed as garbage and never consumed; the cell x == y
-//     substitutes v_cur = max_neg_val exactly like the reference.
+//   * cells with x > y, and frames of the last 32-frame tile beyond t_y, are computed as
+//     garbage and never consumed; the cell x == y substitutes v_cur = max_neg_val exactly
+//     like the reference.
 //
 // CTA organisation (template R rows per lane, W DP warps; XP = 32*R*W rows):
 //   producer warp W      a handful of TMA tensor-map loads (cp.async.bulk.tensor, box
@@ -26,29 +27,28 @@
 //                        32-frame tile into an NS-deep shared-memory ring, completion
 //                        counted on an mbarrier; the strided boxes land the rows in the
 //                        lane-major permuted layout of mas_common.cuh so DP reads are
-//                        conflict-free.  The ring depth keeps ~50-150 KB in flight per SM
-//                        -- enough to stream a CTA's value matrix at HBM latency.  (A first
-//                        version issued one 128-byte bulk copy per row: 6080 requests per
-//                        utterance at ~30 ns each made the kernel request-rate bound.)
+//                        conflict-free LDS.128.
 //   DP warps 0..W-1      lane l of warp w owns the R consecutive text positions
-//                        x = rows_base + (32w + l)*R + r.  Per mel frame the lane
-//                        updates its R rows top-down from registers; only row 0 needs a
-//                        neighbour (lane-1's last row of the previous frame) via
-//                        __shfl_up_sync, issued R-1 cell updates ahead of its use, so
-//                        the shuffle latency is off the dependency chain.
-//   warp skew            warp w trails warp w-1 by one 8-frame slab; the boundary row
-//                        travels through a small shared-memory ring published with
+//                        x = rows_base + (32w + l)*R + r.  A 32-frame tile is ONE
+//                        straight-line block (no branch, no divergence): per frame the
+//                        lane updates its rows bottom-up in place; the bottom row goes
+//                        first and its SHFL.UP to the next lane is issued immediately, so
+//                        the ~26-cycle shuffle is covered by the 2R-2 cell updates until
+//                        the next frame's top row consumes it.  Lane 0 takes the halo (row
+//                        above the warp) with one FSEL; lane 31 leaves it with one
+//                        predicated STS.
+//   warp skew            warp w trails warp w-1 by one tile; the boundary row travels
+//                        through a shared-memory ring of 32-float slots published with
 //                        st.release / ld.acquire progress flags (no __syncthreads, no
-//                        barrier instruction in the frame loop).  Only warp 0 waits on
-//                        the TMA mbarrier; the others inherit the ordering through the
-//                        flag chain.
+//                        barrier instruction in the tile loop).  Only warp 0 waits on the
+//                        TMA mbarrier; the others inherit the ordering through the flag chain.
 //   direction bits       32 frames x 1 bit per row per tile, kept in shared memory when
 //                        they fit (LRS2 shapes), otherwise in an L2-resident global
 //                        scratch that is staged back through the idle ring.
-//   backtrack            one thread walks TOKENS, not frames: for the current token it
-//                        finds the frame where the path leaves it with one masked
-//                        find-leading-one per 32-frame word (~t_x + t_y/32 dependent
-//                        steps instead of t_y), emitting [start, duration] per token.
+//   backtrack            one thread walks TOKENS, not frames: the words of the next 8
+//                        tokens of the current tile are fetched with 8 independent LDS,
+//                        then each token costs one masked find-leading-one (pure ALU
+//                        chain), emitting [start, duration] per token.
 //   text longer than XP  processed in passes of XP rows; the last row of pass p is
 //                        carried to pass p+1 through a global line (L2).
 #pragma once
@@ -63,7 +63,7 @@ struct MasParams {
     const int *t_x, *t_y;    // [B]
     int B, Tx, Ty;
     float neg;               // max_neg_val
-    int aligned;             // 1: every row segment is 16-byte aligned -> TMA bulk path
+    int aligned;             // 1: every row segment is 16-byte aligned -> TMA path
     int ring_stages;         // NS
     int *start;              // [B,Tx] first frame of each token (workspace)
     int *dur;                // [B,Tx] frames per token (user buffer or workspace)
@@ -79,101 +79,155 @@ struct MasParams {
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
-// One cell of the recurrence; the bit is set iff the diagonal predecessor wins.
-// CELL 0: portable C.  CELL 1: inline PTX that keeps the select off the ALU pipe:
-//   setp.gt p, v_prev, v_cur ; q = v_cur + v ; @p q = v_prev + v ; @p bits |= mask
-// (1 ALU-pipe compare + 1 predicated logic op, both adds on the FMA pipe; the
-// dependency chain per frame is compare -> predicated add).  Both are the same
-// arithmetic: (v_prev > v_cur ? v_prev : v_cur) + v in fp32 RN, NaN -> v_cur.
-template <int CELL>
-__device__ __forceinline__ float mas_cell(float v_cur, float v_prev, float v, uint32_t &bits, int bitpos) {
-    if constexpr (CELL == 0) {
-        const bool d = v_prev > v_cur;   // core.pyx max(v_cur, v_prev) -> (v_prev > v_cur) ? v_prev : v_cur
-        bits |= d ? (1u << bitpos) : 0u;
-        return (d ? v_prev : v_cur) + v; // plain fp32 RN add, same association as core.pyx:30
-    } else {
-        float q;
-        const uint32_t m = 1u << bitpos; // folds to an immediate after unrolling
-        asm("{\n"
-            " .reg .pred p;\n"
-            " setp.gt.f32 p, %3, %2;\n"
-            " add.rn.f32 %0, %2, %4;\n"
-            " @p add.rn.f32 %0, %3, %4;\n"
-            " @p or.b32 %1, %1, %5;\n"
-            "}\n"
-            : "=&f"(q), "+r"(bits)
-            : "f"(v_cur), "f"(v_prev), "f"(v), "r"(m));
-        return q;
-    }
+// One cell of the recurrence; bit BITPOS of `bits` is set iff the diagonal predecessor wins.
+//   setp.gt p, v_prev, v_cur ; q = v_cur + v ; @p q = v_prev + v ; @p bits |= 1 << BITPOS
+// = (v_prev > v_cur ? v_prev : v_cur) + v in fp32 RN, NaN -> v_cur: core.pyx:22-30 with Cython's
+// max(v_cur, v_prev) lowering.  The select is folded into the two (independent) adds, so the
+// frame-to-frame dependency chain is compare -> predicated add.
+#ifndef MAS_CELL_VARIANT
+#define MAS_CELL_VARIANT 0
+#endif
+template <int BITPOS>
+__device__ __forceinline__ float mas_cell(float v_cur, float v_prev, float v, uint32_t &bits) {
+#if MAS_CELL_VARIANT == 0
+    float q;
+    asm("{\n"
+        " .reg .pred p;\n"
+        " setp.gt.f32 p, %3, %2;\n"
+        " add.rn.f32 %0, %2, %4;\n"
+        " @p add.rn.f32 %0, %3, %4;\n"
+        " @p or.b32 %1, %1, %5;\n"
+        "}\n"
+        : "=&f"(q), "+r"(bits)
+        : "f"(v_cur), "f"(v_prev), "f"(v), "n"(1u << BITPOS));
+    return q;
+#elif MAS_CELL_VARIANT == 1
+    // predicate-free: d = all-ones iff v_prev > v_cur; both sums off the chain; bitwise select
+    uint32_t d, q;
+    const float s0 = v_cur + v, s1 = v_prev + v;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(v_prev), "f"(v_cur));
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(q) : "r"(__float_as_uint(s0)), "r"(__float_as_uint(s1)), "r"(d));
+    asm("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(bits) : "r"(d), "n"(1u << BITPOS));
+    return __uint_as_float(q);
+#elif MAS_CELL_VARIANT == 2
+    uint32_t d, m;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(v_prev), "f"(v_cur));
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(m) : "r"(__float_as_uint(v_cur)), "r"(__float_as_uint(v_prev)), "r"(d));
+    asm("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(bits) : "r"(d), "n"(1u << BITPOS));
+    return __uint_as_float(m) + v;
+#else
+    const bool d = v_prev > v_cur;
+    bits |= d ? (1u << BITPOS) : 0u;
+    return (d ? v_prev : v_cur) + v;
+#endif
 }
 
-// 8 consecutive frames kb..kb+7 of one tile, fully unrolled.
-//   q[r]    running previous-column Q of the lane's rows
-//   acc[r]  direction word being assembled (bit k <-> frame t0+k)
-//   h[i]    halo: Q of the row above the warp's first row at frame t0+kb+i-1 (same in all lanes)
-//   src     lane the rotate-shuffle reads from: (lane + 31) & 31; lane 31 injects the halo
-//   dl      lane_global - (t0+kb)/R  (DIAG only): the lane owns the diagonal cell of frame
-//           t0+kb+i, in row r = i % R, exactly when dl == i / R
-//   lbase   &stage[lane_cta * kTilePitch]; o0 = swizzled float offset of frames kb..kb+3 in the
-//           lane's rows, ((kb >> 2) ^ (lane & 7)) << 2; frames kb+4..kb+7 sit at o0 ^ 4
-template <int R, int XP, int CELL, bool DIAG, bool HALO_OUT>
-__device__ __forceinline__ void dp_frames8(float (&q)[R], uint32_t (&acc)[R], const float *lbase, int kb, int o0,
-                                           const float (&h)[8], int lane, int src, int dl, float neg,
-                                           float *halo_out) {
+// Predicate registers are the scarce resource of the tile body: every cell needs one for its
+// compare -> predicated add, and ptxas serialises the cells on a single predicate when long-lived
+// booleans occupy the other six (measured: 85-137 instead of 34-49 cycles/frame).  So nothing in
+// the body is predicated on a loop-invariant condition:
+//   * lane 31's halo hand-off is an UNCONDITIONAL 4-byte store whose address is a per-lane register
+//     (the real slot for lane 31 of a warp with a consumer, a dump row otherwise);
+//   * lane 0's halo take-over is a bitwise select on a per-lane mask register;
+//   * loop-invariant flags consumed after the body are laundered through opaque() so their
+//     predicates are materialised after the body, not kept alive across it.
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
+__device__ __forceinline__ float bitselect(uint32_t mask, float a, float b) {      // mask ? a : b, bitwise
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(mask));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+    asm volatile("" : "+r"(x));
+    return x;
+}
+
+template <int I>
+__device__ __forceinline__ float f4_get(const float4 &v) {
+    return I == 0 ? v.x : I == 1 ? v.y : I == 2 ? v.z : v.w;
+}
+
+// The lane's R rows of frame group G (frames 4G..4G+3 of the tile): one LDS.128 per row.
+//   lane_tile = &stage[lane_cta * kTilePitch]; chunk c of a row sits at position c ^ (lane & 7).
+template <int R, int XP, int G>
+__device__ __forceinline__ void load_group(float4 (&v)[R], const float *lane_tile, int lane7) {
     constexpr int kRowStride = (XP / R) * kTilePitch;      // floats between the lane's consecutive rows
-    uint32_t a8[R];
+    const int o = (G ^ lane7) << 2;
 #pragma unroll
-    for (int r = 0; r < R; ++r) a8[r] = 0u;
-    float4 v4[2][R];
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            v4[hh][r] = *reinterpret_cast<const float4 *>(lbase + r * kRowStride + (hh == 0 ? o0 : (o0 ^ 4)));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        // one shuffle per frame: lane l reads lane l-1's last row; lane 0 reads lane 31, which sends the halo
-        const float send = (lane == 31) ? h[i] : q[R - 1];
-        const float up = __shfl_sync(kFullMask, send, src);
-        float n[R];
-#pragma unroll
-        for (int r = R - 1; r >= 0; --r) {
-            const float4 vv = v4[i >> 2][r];
-            const float v = (i & 3) == 0 ? vv.x : (i & 3) == 1 ? vv.y : (i & 3) == 2 ? vv.z : vv.w;
-            float v_cur = q[r];
-            if (DIAG && r == (i % R)) {                    // (t0+kb+i) % R == i % R since R | 8 | (t0+kb)
-                if (dl == i / R) v_cur = neg;              // x == y  (core.pyx:19-20)
-            }
-            const float v_prev = (r == 0) ? up : q[r - 1];
-            n[r] = mas_cell<CELL>(v_cur, v_prev, v, a8[r], i);
-        }
-        if (HALO_OUT && lane == 31) halo_out[i] = n[R - 1];
-#pragma unroll
-        for (int r = 0; r < R; ++r) q[r] = n[r];
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] |= a8[r] << kb;
+    for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const float4 *>(lane_tile + r * kRowStride + o);
 }
 
-// Generic single frame (partial last slab): every row checks x >= t.
-template <int R, int XP, bool HALO_OUT>
-__device__ __forceinline__ void dp_frame_generic(float (&q)[R], uint32_t (&acc)[R], const float *lane_row0, int k,
-                                                 float hk, int lane, int src, int x0, int t, float neg,
-                                                 float *halo_out_k) {
-    constexpr int kRowStride = (XP / R) * kTilePitch;
-    const float send = (lane == 31) ? hk : q[R - 1];
-    const float up = __shfl_sync(kFullMask, send, src);
-    float n[R];
+// One frame (FRAME = position inside the tile) of the lane's R rows.
+//   q[r]    running previous-column Q of the lane's rows, updated in place bottom-up
+//   up      Q of the row above the lane's first row at the previous frame
+//   hq      Q of the row above the WARP at this frame (what lane 0 takes instead of a shuffle)
+//   dl0     DIAG only: lane_global - t0/R; the lane owns the diagonal cell of this frame, in row
+//           FRAME % R, exactly when dl0 == FRAME / R      (R | 32 | t0)
+template <int R, int FRAME, bool DIAG>
+__device__ __forceinline__ void dp_frame(float (&q)[R], uint32_t (&acc)[R], float &up, const float (&v)[R], float hq,
+                                         uint32_t lane0_mask, int dl0, float neg, uint32_t hout_addr) {
+    float up_next = up;
 #pragma unroll
     for (int r = R - 1; r >= 0; --r) {
-        const float v = lane_row0[r * kRowStride + ((((k >> 2) ^ (lane & 7)) << 2) | (k & 3))];
-        const float v_cur = (x0 + r >= t) ? neg : q[r];
+        float v_cur = q[r];
+        if (DIAG && r == FRAME % R) v_cur = (dl0 == FRAME / R) ? neg : v_cur;      // x == y (core.pyx:19-20)
         const float v_prev = (r == 0) ? up : q[r - 1];
-        n[r] = mas_cell<0>(v_cur, v_prev, v, acc[r], k);
+        q[r] = mas_cell<FRAME>(v_cur, v_prev, v[r], acc[r]);
+        if (r == R - 1) {
+            sts_f32(hout_addr + 4u * FRAME, q[R - 1]);
+            const float s = __shfl_up_sync(kFullMask, q[R - 1], 1);
+            up_next = bitselect(lane0_mask, hq, s);
+        }
     }
-    if (HALO_OUT && lane == 31) *halo_out_k = n[R - 1];
+    up = up_next;
+}
+
+template <int R, int G, bool DIAG>
+__device__ __forceinline__ void dp_group(float (&q)[R], uint32_t (&acc)[R], float &up, const float4 (&v4)[R],
+                                         const float4 &h4, uint32_t lane0_mask, int dl0, float neg,
+                                         uint32_t hout_addr) {
+    float v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) q[r] = n[r];
+    for (int r = 0; r < R; ++r) v[r] = v4[r].x;
+    dp_frame<R, 4 * G + 0, DIAG>(q, acc, up, v, h4.x, lane0_mask, dl0, neg, hout_addr);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = v4[r].y;
+    dp_frame<R, 4 * G + 1, DIAG>(q, acc, up, v, h4.y, lane0_mask, dl0, neg, hout_addr);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = v4[r].z;
+    dp_frame<R, 4 * G + 2, DIAG>(q, acc, up, v, h4.z, lane0_mask, dl0, neg, hout_addr);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = v4[r].w;
+    dp_frame<R, 4 * G + 3, DIAG>(q, acc, up, v, h4.w, lane0_mask, dl0, neg, hout_addr);
+}
+
+// A whole 32-frame tile as one basic block; value and halo groups are register double-buffered.
+//   hin   32 floats in shared memory: Q of the row above the warp at the tile's frames
+template <int R, int XP, bool DIAG>
+__device__ __forceinline__ void dp_tile(float (&q)[R], uint32_t (&acc)[R], float &up, const float *lane_tile,
+                                        const float *hin, int lane7, uint32_t lane0_mask, int dl0, float neg,
+                                        uint32_t hout_addr) {
+    float4 va[R], vb[R];
+    float4 ha, hb;
+    const float4 *h4 = reinterpret_cast<const float4 *>(hin);
+    load_group<R, XP, 0>(va, lane_tile, lane7); ha = h4[0];
+    load_group<R, XP, 1>(vb, lane_tile, lane7); hb = h4[1];
+    dp_group<R, 0, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP, 2>(va, lane_tile, lane7); ha = h4[2];
+    dp_group<R, 1, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP, 3>(vb, lane_tile, lane7); hb = h4[3];
+    dp_group<R, 2, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP, 4>(va, lane_tile, lane7); ha = h4[4];
+    dp_group<R, 3, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP, 5>(vb, lane_tile, lane7); hb = h4[5];
+    dp_group<R, 4, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP, 6>(va, lane_tile, lane7); ha = h4[6];
+    dp_group<R, 5, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP, 7>(vb, lane_tile, lane7); hb = h4[7];
+    dp_group<R, 6, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+    dp_group<R, 7, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
 }
 
 template <int R>
@@ -192,18 +246,21 @@ __device__ __forceinline__ void store_words(uint32_t *dst, const uint32_t (&acc)
 }
 
 // Shared-memory carve-up; host (launcher) and device agree through these functions.
+//   [ring: NS value tiles][halo: (W+1) rings of NS+1 slots x 32 floats, W dump rows][ctrl][direction bits]
+// halo ring i < W is written by DP warp i; ring W holds the constant / carried-line input of warp 0.
 template <int R, int W>
 struct MasSmem {
     static constexpr int XP = 32 * R * W;
     static constexpr int kTileFloats = XP * kTilePitch;
     __host__ __device__ static constexpr size_t ring_bytes(int ns) { return sizeof(float) * (size_t)ns * kTileFloats; }
-    __host__ __device__ static constexpr int halo_slabs(int ns) { return 4 * (ns + 1); }
-    __host__ __device__ static constexpr size_t halo_bytes(int ns) { return sizeof(float) * (size_t)W * halo_slabs(ns) * 8; }
-    __host__ __device__ static constexpr size_t ctrl_bytes(int ns) { return 8 * (size_t)(2 * ns) + 4 * (size_t)W + 64; }
+    __host__ __device__ static constexpr int halo_slots(int ns) { return ns + 1; }
+    __host__ __device__ static constexpr size_t halo_bytes(int ns) {
+        return sizeof(float) * ((size_t)(W + 1) * halo_slots(ns) + W) * kTileFrames;
+    }
+    __host__ __device__ static constexpr size_t ctrl_bytes(int ns) { return 8 * (size_t)(2 * ns) + 4 * (size_t)(W + 2) + 64; }
     __host__ __device__ static constexpr size_t fixed_bytes(int ns) {
         return ((ring_bytes(ns) + halo_bytes(ns) + ctrl_bytes(ns) + 127) / 128) * 128;
     }
-    static size_t bits_bytes(int ntiles_max) { return sizeof(uint32_t) * (size_t)ntiles_max * XP; }
 };
 
 template <typename T> __device__ __forceinline__ uint32_t one_bits();
@@ -253,7 +310,47 @@ __device__ __forceinline__ void write_path_any(const MasParams &P, int b, const 
         write_path_rows<int>(reinterpret_cast<int *>(P.path) + off, start_b, dur_b, P.Tx, P.Ty, tid, nthreads);
 }
 
-template <int R, int W, bool SMEM_BITS, int CELL>
+// Token walk over direction words wb[(j - jlo) * wpitch + x] (tile j, text position x), from state
+// (x, y_end, y): token x owns frames (y, y_end] so far.  Finds, token by token, the highest frame
+// y' <= y where the path leaves the token: d[x,y'] set, or y' == x (core.pyx:34's index == y).
+// Returns when x reaches 0 (done) or the walk needs a tile below jlo.
+__device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, int jlo, int &x, int &y_end, int &y,
+                                               int *start_b, int *dur_b) {
+    constexpr int KB = 8;                                   // tokens fetched per batch
+    while (true) {
+        if (x == 0) { start_b[0] = 0; dur_b[0] = y_end + 1; return true; }
+        const int j = y >> 5;
+        if (j < jlo) return false;
+        const uint32_t *row = wb + (size_t)(j - jlo) * wpitch;
+        uint32_t wk[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) wk[k] = row[max(x - k, 0)];
+        const int jb = j << 5;
+        bool leave = false;                                 // left tile j (or reached token 0)
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (!leave) {
+                uint32_t wd = wk[k] & (0xffffffffu >> (31 - (y - jb)));
+                if ((x >> 5) == j) wd |= 1u << (x & 31);    // index == y forces the move
+                if (wd == 0u) {
+                    y = jb - 1;                             // token x continues in tile j-1
+                    leave = true;
+                } else {
+                    const int ys = jb + (31 - __clz(wd));
+                    start_b[x] = ys;
+                    dur_b[x] = y_end - ys + 1;
+                    --x;
+                    y = y_end = ys - 1;
+                    leave = (ys == jb) || (x == 0);
+                }
+            }
+        }
+    }
+}
+
+// MULTIPASS: text longer than XP rows (carry line between row passes); its runtime role flags cost
+// the single-pass instantiations nothing.
+template <int R, int W, bool SMEM_BITS, bool MULTIPASS>
 __global__ void __launch_bounds__((W + 1) * 32, 1)
 mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) {
     using S = MasSmem<R, W>;
@@ -263,11 +360,11 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     constexpr int nthreads = (W + 1) * 32;
 
     const int NS = P.ring_stages;
-    const int HS = S::halo_slabs(NS);
+    const int HS = S::halo_slots(NS);
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
-    float *hbuf = reinterpret_cast<float *>(smem_raw + S::ring_bytes(NS));                 // [W][HS*8]
+    float *hbuf = reinterpret_cast<float *>(smem_raw + S::ring_bytes(NS));                 // [W+1][HS][32]
     uint64_t *ring_full = reinterpret_cast<uint64_t *>(smem_raw + S::ring_bytes(NS) + S::halo_bytes(NS));
     uint64_t *ring_empty = ring_full + NS;
     int *hprog = reinterpret_cast<int *>(ring_empty + NS);                                // [W]
@@ -276,11 +373,12 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(kFullMask, tid >> 5, 0);     // provably warp-uniform for ptxas
     const int lane = tid & 31;
 
-    const int t_x = P.t_x[b];
-    const int t_y = P.t_y[b];
+    // every loop bound below derives from these: broadcast them so the bounds are warp-uniform values
+    const int t_x = __shfl_sync(kFullMask, P.t_x[b], 0);
+    const int t_y = __shfl_sync(kFullMask, P.t_y[b], 0);
     int *start_b = P.start + (size_t)b * P.Tx;
     int *dur_b = P.dur + (size_t)b * P.Tx;
 
@@ -298,12 +396,13 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
 
     const int ntiles = (t_y + NT - 1) / NT;
     const int npass = (t_x + XP - 1) / XP;
-    long long *dbg = P.dbg ? P.dbg + (size_t)b * 8 : nullptr;
-    long long dbg_wait = 0;
+    long long *dbg = P.dbg ? P.dbg + (size_t)b * 16 : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
     uint32_t *gbits_b = SMEM_BITS ? nullptr : P.gbits + (size_t)b * P.gbits_stride_b;
     float *gline_b = P.gline ? P.gline + (size_t)b * 2 * P.line_pitch : nullptr;
     const float *vb = P.value + (size_t)b * P.stride_b;
+    float *hconst = hbuf + (size_t)W * HS * NT;              // warp 0's halo input ring
+    float *hdump = hconst + (size_t)HS * NT;                 // [W][32] where lanes without a consumer store
 
     for (int pass = 0; pass < npass; ++pass) {
         const int rows_base = pass * XP;
@@ -321,8 +420,12 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 mbar_init(&ring_empty[s], w_act);
             }
             for (int i = 0; i < W; ++i) hprog[i] = 0;
+            hprog[W] = 0x7fffffff;                               // the flag a warp without predecessor polls
+            hprog[W + 1] = 0;                                    // where a warp without consumer publishes
             mbar_fence_init();
         }
+        // pass 0: the row above text position 0 is max_neg_val at every frame (core.pyx:26-27)
+        if (pass == 0 && tid < NT) hconst[tid] = P.neg;
         __syncthreads();
 
         if (warp == W) {
@@ -372,126 +475,99 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             }
         } else if (warp < w_act) {
             // ============================== DP warps ==============================
+            // Nothing in the tile loop may branch (or predicate) on a loop-invariant condition: ptxas hoists
+            // the compare out of the loop and parks it in one of the seven predicate registers the cells of
+            // the tile body need (see opaque-free notes at sts_f32).  Role differences between warps are
+            // therefore expressed as ADDRESSES: a warp without a predecessor polls a pre-satisfied flag,
+            // a warp without a consumer publishes to a dump flag and stores its halo to a dump row.
             const int w = warp;
             const int lane_cta = 32 * w + lane;
             const int x0 = rows_base + lane_cta * R;                 // lane's first text position
             const int xw0 = rows_base + 32 * R * w;                  // warp's first text position
             const int lane_glob = x0 / R;
+            const int lane7 = lane & 7;
+            const uint32_t lane0_mask = (lane == 0) ? 0xffffffffu : 0u;
             const bool has_consumer = (w + 1 < w_act);               // boundary (w -> w+1) active
-            const bool line_out = (w == W - 1) && !last_pass;        // feeds the next row pass
-            const bool halo_out = has_consumer || line_out;
-            float *hb_in = hbuf + (size_t)(w > 0 ? w - 1 : 0) * HS * 8;
-            float *hb_out = hbuf + (size_t)w * HS * 8;
-            const int *flag_in = hprog + (w > 0 ? w - 1 : 0);
-            int *flag_out = hprog + w;
-            const float *gl_in = (pass > 0) ? gline_b + ((pass - 1) & 1) * P.line_pitch : nullptr;
+            const bool line_out = MULTIPASS && (w == W - 1) && !last_pass;        // feeds the next row pass
+            const bool line_in = MULTIPASS && (w == 0) && (pass > 0);             // halo from the previous row pass
+            const float *hb_in = (w > 0) ? hbuf + (size_t)(w - 1) * HS * NT : hconst;
+            const int hin_step = (w > 0 || line_in) ? NT : 0;        // warp 0 of pass 0 re-reads one constant row
+            float *hb_out = hbuf + (size_t)w * HS * NT;
+            const uint32_t hout_base = ((has_consumer || line_out) && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * NT);
+            const uint32_t hout_step = ((has_consumer || line_out) && lane == 31) ? NT * 4u : 0u;
+            const int *flag_in = (w > 0) ? hprog + (w - 1) : hprog + W;           // hprog[W] is pre-satisfied
+            int *flag_out = has_consumer ? hprog + w : hprog + W + 1;             // hprog[W+1] is a dump
+            const float *gl_in = (MULTIPASS && pass > 0) ? gline_b + ((pass - 1) & 1) * P.line_pitch : nullptr;
             float *gl_out = line_out ? gline_b + (pass & 1) * P.line_pitch : nullptr;
 
             float q[R];
             uint32_t acc[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) { q[r] = P.neg; acc[r] = 0u; }
-            float carry = P.neg;                                     // halo value of the frame before the slab/tile
-            int known = 0;                                           // last observed producer progress (slabs)
+            // neighbour value for frame 0: only text position 0 has a defined one (core.pyx:24-25, y == 0)
+            float up = (x0 == 0) ? 0.f : P.neg;
+            int known = 0;                 // last observed progress of warp w-1 (tiles completed)
             int stage = 0;
             uint32_t phase = 0;
-            int hs = 0;                                              // halo ring slot of the current slab (c % HS)
-            const int src = (lane + 31) & 31;                        // rotate-shuffle source lane
+            int hs = 0;                    // halo ring slot of the current tile
+            bool tile_ready = false;       // ring_full of the current tile already observed
+            if (MULTIPASS && line_in) {    // carried row of tile 0 into slot 0 of warp 0's input ring
+                hconst[lane] = gl_in[lane];
+                __syncwarp();
+            }
 
             for (int j = 0; j < ntiles; ++j) {
                 const int t0 = j * NT;
-                const int kmax = min(NT, t_y - t0);
-                float hv_tile = P.neg;                                // w == 0: halo of frame t0+lane-1
-                if (w == 0) {
-                    if (pass == 0) {
-                        hv_tile = (t0 + lane == 0) ? 0.f : P.neg;    // core.pyx:23-27 (x == 0)
-                    } else {
-                        hv_tile = (lane == 0) ? carry : gl_in[t0 + lane - 1];
-                        carry = gl_in[t0 + 31];
-                    }
-                    if (dbg) {
-                        const long long c0 = clock64();
-                        mbar_wait(&ring_full[stage], phase);
-                        dbg_wait += clock64() - c0;
-                        if (j == 0 && lane == 0) dbg[1] = clock64();
-                    } else {
-                        mbar_wait(&ring_full[stage], phase);
-                    }
-                }
-                const float *st_lane = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
+                if (!tile_ready) mbar_wait_warp(&ring_full[stage], phase);
+                if (known < j + 1) known = flag_wait_ge_warp(flag_in, j + 1);
+                const int next_stage = (stage + 1 == NS) ? 0 : stage + 1;
+                const uint32_t next_phase = (stage + 1 == NS) ? (phase ^ 1) : phase;
+                const int next_hs = (hs + 1 == HS) ? 0 : hs + 1;
+                // early, non-blocking probe of the next tile's TMA barrier: its latency hides under the tile
+                tile_ready = (j + 1 < ntiles) && mbar_test_warp(&ring_full[next_stage], next_phase);
+                float hv_next = 0.f;
+                if (MULTIPASS) { if (line_in && j + 1 < ntiles) hv_next = gl_in[t0 + NT + lane]; }
 
-                for (int kb = 0; kb < kmax; kb += 8) {
-                    const int c = 4 * j + (kb >> 3);                 // slab counter within the pass
-                    // halo registers: h[i] = Q[row above the warp, frame t0+kb+i-1], identical in all lanes
-                    float h[8];
-                    if (w > 0) {
-                        if (known < c + 1) known = flag_wait_ge(flag_in, c + 1);
-                        const float4 s0 = *reinterpret_cast<const float4 *>(hb_in + hs * 8);
-                        const float4 s1 = *reinterpret_cast<const float4 *>(hb_in + hs * 8 + 4);
-                        h[0] = carry; h[1] = s0.x; h[2] = s0.y; h[3] = s0.z;
-                        h[4] = s0.w;  h[5] = s1.x; h[6] = s1.y; h[7] = s1.z;
-                        carry = s1.w;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) h[i] = __shfl_sync(kFullMask, hv_tile, kb + i);
-                    }
-                    float *hout = hb_out + hs * 8;
-                    const int tb = t0 + kb;
-                    const int o0 = ((kb >> 2) ^ (lane & 7)) << 2;
-                    const bool below_diag = (tb + 7 < xw0);           // every row of the warp has x > y
-                    if (!below_diag) {
-                        if (kb + 8 <= kmax) {
-                            const bool diag = (tb < xw0 + 32 * R);
-                            const int dl = lane_glob - tb / R;
-                            if (halo_out) {
-                                if (diag) dp_frames8<R, XP, CELL, true, true>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
-                                else dp_frames8<R, XP, CELL, false, true>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
-                            } else {
-                                if (diag) dp_frames8<R, XP, CELL, true, false>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
-                                else dp_frames8<R, XP, CELL, false, false>(q, acc, st_lane, kb, o0, h, lane, src, dl, P.neg, hout);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int k = kb + i;
-                                if (k < kmax) {
-                                    if (halo_out) dp_frame_generic<R, XP, true>(q, acc, st_lane, k, h[i], lane, src, x0, t0 + k, P.neg, hout + i);
-                                    else dp_frame_generic<R, XP, false>(q, acc, st_lane, k, h[i], lane, src, x0, t0 + k, P.neg, hout);
-                                }
-                            }
-                        }
-                    }
-                    if (has_consumer) {
-                        __syncwarp();
-                        if (lane == 0) flag_release(flag_out, c + 1);
-                    }
-                    if (++hs == HS) hs = 0;
-                }
+                const float *lane_tile = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
+                const float *hin = hb_in + hs * hin_step;
+                const uint32_t hout_addr = hout_base + hs * hout_step;
+                // Tiles entirely below the diagonal (every row of the warp has x > y) are computed like any
+                // other: their results are never consumed (the x == y cell substitutes max_neg_val) and the
+                // warp would only be waiting for its predecessor anyway.
+                const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
+                const int dl0 = lane_glob - t0 / R;
+                if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+                else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+
                 // ---- direction words of this tile ----
                 if (SMEM_BITS) store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, acc);
                 else store_words<R>(gbits_b + (size_t)j * P.gbits_rows_pitch + x0, acc);
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = 0u;
 
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ring_empty[stage]);
-                if (line_out) {
-                    // the tile's 4 slabs are contiguous in the halo ring (HS is a multiple of 4)
-                    const int hs0 = (4 * j) % HS;
-                    gl_out[t0 + lane] = hb_out[hs0 * 8 + lane];
-                    __syncwarp();
+                __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
+                if (elect_one()) {                              // a fresh predicate every tile, nothing to hoist
+                    flag_release(flag_out, j + 1);
+                    mbar_arrive(&ring_empty[stage]);
                 }
-                if (++stage == NS) { stage = 0; phase ^= 1; }
+                if (MULTIPASS) {
+                    if (line_out) gl_out[t0 + lane] = hb_out[hs * NT + lane];
+                    if (line_in && j + 1 < ntiles) {
+                        hconst[next_hs * NT + lane] = hv_next;
+                        __syncwarp();
+                    }
+                }
+                stage = next_stage;
+                phase = next_phase;
+                hs = next_hs;
             }
         }
-        if (dbg && tid == 0) { dbg[2] = clock64(); dbg[3] = dbg_wait; }   // warp 0 done with this pass
+        if (dbg && tid == 0) { dbg[2] = clock64(); }   // warp 0 done with this pass
         __syncthreads();
     }
     if (dbg && tid == 0) dbg[4] = clock64();                               // all DP warps done
 
     // ================================ backtrack ================================
-    // Token walk.  State (x, y_end, y): token x owns frames (y, y_end] so far; find the
-    // highest frame y' <= y where the path leaves the token: d[x,y'] set, or y' == x.
     const int rows_pitch = SMEM_BITS ? XP : P.gbits_rows_pitch;
     uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
     const int rows_cp = min(rows_pitch, ((t_x + 3) >> 2) << 2);
@@ -511,23 +587,9 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             __syncthreads();
         }
         if (tid == 0) {
-            const uint32_t *wb = SMEM_BITS ? bits_s : stage_bits;
-            const int wpitch = SMEM_BITS ? XP : rows_cp;
             int x = bt_state[0], y_end = bt_state[1], y = bt_state[2];
-            bool done = false;
-            while (true) {
-                if (x == 0) { start_b[0] = 0; dur_b[0] = y_end + 1; done = true; break; }
-                const int j = y >> 5;
-                if (j < jlo) break;                                        // need the next chunk
-                uint32_t wd = wb[(size_t)(j - jlo) * wpitch + x] & (0xffffffffu >> (31 - (y & 31)));
-                if ((x >> 5) == j) wd |= 1u << (x & 31);                   // index == y forces the move (core.pyx:34)
-                if (wd == 0u) { y = (j << 5) - 1; continue; }
-                const int ys = (j << 5) + (31 - __clz(wd));
-                start_b[x] = ys;
-                dur_b[x] = y_end - ys + 1;
-                --x;
-                y = y_end = ys - 1;
-            }
+            const bool done = backtrack_walk(SMEM_BITS ? bits_s : stage_bits, SMEM_BITS ? XP : rows_cp, jlo, x, y_end,
+                                             y, start_b, dur_b);
             bt_state[0] = x; bt_state[1] = y_end; bt_state[2] = y; bt_state[3] = done ? 1 : 0;
         }
         __syncthreads();

@@ -15,12 +15,12 @@ namespace {
 
 constexpr size_t kMaxSmem = 232448 - 1024;   // must match mas_forward.cu
 
-template <int R, int W, bool SB, int CELL>
+template <int R, int W, bool SB, bool MP>
 int launch_inst(const MasParams &P, const CUtensorMap &tmap, size_t smem, cudaStream_t stream) {
     static std::atomic<int> configured[16];
     int dev = 0;
     MASB200_CUDA_TRY(cudaGetDevice(&dev));
-    auto kern = mas_forward_kernel<R, W, SB, CELL>;
+    auto kern = mas_forward_kernel<R, W, SB, MP>;
     if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
@@ -31,19 +31,22 @@ int launch_inst(const MasParams &P, const CUtensorMap &tmap, size_t smem, cudaSt
 }
 
 template <int R, int W>
-int launch_w(const MasParams &P, const CUtensorMap &tmap, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
-    if (cell == 0)
-        return smem_bits ? launch_inst<R, W, true, 0>(P, tmap, smem, stream) : launch_inst<R, W, false, 0>(P, tmap, smem, stream);
-    return smem_bits ? launch_inst<R, W, true, 1>(P, tmap, smem, stream) : launch_inst<R, W, false, 1>(P, tmap, smem, stream);
+int launch_w(const MasParams &P, const CUtensorMap &tmap, int mode, size_t smem, cudaStream_t stream) {
+    switch (mode) {
+        case MAS_MODE_SMEM_BITS: return launch_inst<R, W, true, false>(P, tmap, smem, stream);
+        case MAS_MODE_GLOBAL_BITS: return launch_inst<R, W, false, false>(P, tmap, smem, stream);
+        case MAS_MODE_MULTIPASS: return launch_inst<R, W, false, true>(P, tmap, smem, stream);
+        default: return MAS_B200_ERR_UNSUPPORTED;
+    }
 }
 
 template <int R>
-int launch_r(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits, int cell, size_t smem, cudaStream_t stream) {
+int launch_r(const MasParams &P, const CUtensorMap &tmap, int W, int mode, size_t smem, cudaStream_t stream) {
     switch (W) {
-        case 1: return launch_w<R, 1>(P, tmap, smem_bits, cell, smem, stream);
-        case 2: return launch_w<R, 2>(P, tmap, smem_bits, cell, smem, stream);
-        case 3: return launch_w<R, 3>(P, tmap, smem_bits, cell, smem, stream);
-        case 4: return launch_w<R, 4>(P, tmap, smem_bits, cell, smem, stream);
+        case 1: return launch_w<R, 1>(P, tmap, mode, smem, stream);
+        case 2: return launch_w<R, 2>(P, tmap, mode, smem, stream);
+        case 3: return launch_w<R, 3>(P, tmap, mode, smem, stream);
+        case 4: return launch_w<R, 4>(P, tmap, mode, smem, stream);
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
 }
@@ -53,9 +56,9 @@ int launch_r(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits,
 #define MASB200_CAT2(a, b) a##b
 #define MASB200_CAT(a, b) MASB200_CAT2(a, b)
 
-int MASB200_CAT(launch_mas_r, MASB200_INST_R)(const MasParams &P, const CUtensorMap &tmap, int W, bool smem_bits,
-                                              int cell, size_t smem, cudaStream_t stream) {
-    return launch_r<MASB200_INST_R>(P, tmap, W, smem_bits, cell, smem, stream);
+int MASB200_CAT(launch_mas_r, MASB200_INST_R)(const MasParams &P, const CUtensorMap &tmap, int W, int mode,
+                                              size_t smem, cudaStream_t stream) {
+    return launch_r<MASB200_INST_R>(P, tmap, W, mode, smem, stream);
 }
 
 }  // namespace masb200

@@ -38,6 +38,9 @@ struct Workspace {
 };
 Workspace workspace_layout(int B, int Tx, int Ty);
 
+// ---- MAS kernel flavours (template arguments SMEM_BITS, MULTIPASS of mas_forward_kernel) ----
+enum { MAS_MODE_SMEM_BITS = 0, MAS_MODE_GLOBAL_BITS = 1, MAS_MODE_MULTIPASS = 2 };
+
 // ---- launchers ----------------------------------------------------------------
 struct MasLaunch {
     const float *value;

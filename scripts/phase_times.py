@@ -13,7 +13,7 @@ def run(B, Tx, Ty, opts, dense=False):
         _lib.set_option(k, v)
     v, t_x, t_y = synthetic.mas_value(B, Tx, Ty, seed=3, tx_lo=Tx // 3, ty_lo=Ty // 3)
     v = v.cuda()
-    dbg = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+    dbg = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
     for _ in range(3):
         fgt.align(v, t_x, t_y, dense_path=dense)
     p = dbg.data_ptr()
@@ -32,7 +32,7 @@ def run(B, Tx, Ty, opts, dense=False):
         print(f"{b:3d} {tx:5d} {ty:5d} | {s[1]-s[0]:9d} {s[2]-s[0]:9d} {s[3]:9d} {(s[2]-s[1]-s[3])/max(ty,1):10.1f}      | "
               f"{s[4]-s[2]:9d} {s[5]-s[4]:9d} {s[6]-s[5]:6d} | {s[6]-s[0]:9d}")
     for k in opts:
-        _lib.set_option(k, 0 if k != "mas_cell_impl" else 1)
+        _lib.set_option(k, 0)
 
 run(32, 190, 1000, {})
 run(32, 190, 1000, {"mas_rows_per_lane": 8, "mas_dp_warps": 1})

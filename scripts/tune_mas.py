@@ -56,8 +56,8 @@ def mas_case(B, Tx, Ty, tx_lo, ty_lo, plans, results, tag, nsets=4):
                                      ft.data_ptr(), st.data_ptr(), ws.data_ptr(), ws_bytes, sp)
         assert rc == 0, rc
 
-    for (R, W, cell, extra) in plans:
-        opts = dict(mas_rows_per_lane=R, mas_dp_warps=W, mas_cell_impl=cell)
+    for (R, W, extra) in plans:
+        opts = dict(mas_rows_per_lane=R, mas_dp_warps=W)
         opts.update(extra)
         prev = {k: _lib.set_option(k, val) for k, val in opts.items()}
         try:
@@ -69,7 +69,7 @@ def mas_case(B, Tx, Ty, tx_lo, ty_lo, plans, results, tag, nsets=4):
             err = repr(e)
         for k, val in prev.items():
             _lib.set_option(k, val)
-        rec = dict(tag=tag, B=B, Tx=Tx, Ty=Ty, R=R, W=W, cell=cell, extra=extra, mas_us=us, mas_dense_us=us_dense,
+        rec = dict(tag=tag, B=B, Tx=Tx, Ty=Ty, R=R, W=W, extra=extra, mas_us=us, mas_dense_us=us_dense,
                    gcells_s=(B * Tx * Ty / us / 1e3) if us else None, err=err)
         results.append(rec)
         print(rec, flush=True)
@@ -78,17 +78,17 @@ def mas_case(B, Tx, Ty, tx_lo, ty_lo, plans, results, tag, nsets=4):
 def main():
     quick = "--quick" in sys.argv
     results = []
-    plans_190 = [(R, W, c, {}) for (R, W) in [(2, 3), (4, 2), (2, 4), (8, 1), (4, 3), (1, 4)] for c in (1, 0)]
-    plans_190 += [(2, 3, 1, {"mas_ring_stages": 2}), (2, 3, 1, {"mas_ring_stages": 3}),
-                  (2, 3, 1, {"mas_force_global_bits": 1}), (2, 3, 1, {"mas_force_unaligned": 1})]
+    plans_190 = [(R, W, {}) for (R, W) in [(2, 3), (4, 2), (2, 4), (8, 1), (4, 3), (1, 4)]]
+    plans_190 += [(4, 2, {"mas_ring_stages": 2}), (4, 2, {"mas_ring_stages": 3}),
+                  (4, 2, {"mas_force_global_bits": 1}), (4, 2, {"mas_force_unaligned": 1})]
     mas_case(32, 190, 1000, 60, 300, plans_190, results, "cfg2-shape B=32")
-    mas_case(16, 200, 800, 100, 400, [(4, 2, 1, {}), (2, 4, 1, {}), (8, 1, 1, {}), (4, 2, 0, {})], results, "cfg1 B=16")
+    mas_case(16, 200, 800, 100, 400, [(4, 2, {}), (2, 4, {}), (8, 1, {})], results, "cfg1 B=16")
     if not quick:
-        big = [(2, 3, 1, {"mas_ctas_per_sm": k, "mas_fused_path_write": f}) for k in (1, 2, 3) for f in (0, 1)]
-        big += [(4, 2, 1, {"mas_ctas_per_sm": 2, "mas_fused_path_write": 1})]
+        big = [(R, W, {"mas_ctas_per_sm": k, "mas_fused_path_write": 0}) for (R, W) in [(2, 3), (4, 2), (8, 1)]
+               for k in (1, 2, 3, 4)]
+        big += [(4, 2, {"mas_ctas_per_sm": 3, "mas_fused_path_write": 1})]
         mas_case(1024, 190, 1000, 60, 300, big, results, "cfg5 B=1024", nsets=1)
-        mas_case(64, 512, 4096, 256, 2048, [(4, 4, 1, {}), (8, 2, 1, {}), (8, 4, 1, {}), (4, 4, 0, {})], results,
-                 "cfg4 B=64", nsets=1)
+        mas_case(64, 512, 4096, 256, 2048, [(4, 4, {}), (8, 2, {}), (8, 4, {})], results, "cfg4 B=64", nsets=1)
 
     # log-prior kernels
     for (B, F, Tx, Ty) in [(32, 80, 190, 1000), (32, 128, 190, 1000)]:

@@ -70,18 +70,17 @@ def test_golden_kats_default_plan(kats, name):
     assert_matches_golden(run_align(value, t_x, t_y), kats, name)
 
 
-# every (rows-per-lane, DP-warps) instantiation, both cell implementations
+# every (rows-per-lane, DP-warps) instantiation
 RW = [(r, w) for r in (1, 2, 4, 8) for w in (1, 2, 3, 4) if 32 * r * w <= 768]   # two ring stages must fit in 227 KB
 
 
 @pytest.mark.parametrize("R,W", RW)
-@pytest.mark.parametrize("cell", [0, 1])
-def test_every_kernel_instantiation_bit_exact(kats, R, W, cell):
+def test_every_kernel_instantiation_bit_exact(kats, R, W):
     """cfg-shaped + tie / clamp / NaN / edge cases under a forced (R, W): rows beyond 32*R*W
     exercise the multi-pass (global carry line) path."""
     names = ["rand_small", "small_int_ties", "clamp_random", "nan_cell", "inf_cells", "edge_65x129", "lrs2_shape",
              "padding_garbage", "signed_zeros"]
-    with options(mas_rows_per_lane=R, mas_dp_warps=W, mas_cell_impl=cell):
+    with options(mas_rows_per_lane=R, mas_dp_warps=W):
         for name in names:
             value, t_x, t_y = cases.CASES[name]()
             assert_matches_golden(run_align(value, t_x, t_y), kats, name)
