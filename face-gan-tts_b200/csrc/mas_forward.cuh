@@ -310,42 +310,63 @@ __device__ __forceinline__ void write_path_any(const MasParams &P, int b, const 
         write_path_rows<int>(reinterpret_cast<int *>(P.path) + off, start_b, dur_b, P.Tx, P.Ty, tid, nthreads);
 }
 
-// Token walk over direction words wb[(j - jlo) * wpitch + x] (tile j, text position x), from state
-// (x, y_end, y): token x owns frames (y, y_end] so far.  Finds, token by token, the highest frame
-// y' <= y where the path leaves the token: d[x,y'] set, or y' == x (core.pyx:34's index == y).
-// Returns when x reaches 0 (done) or the walk needs a tile below jlo.
-__device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, int jlo, int &x, int &y_end, int &y,
-                                               int *start_b, int *dur_b) {
-    constexpr int KB = 8;                                   // tokens fetched per batch
-    while (true) {
-        if (x == 0) { start_b[0] = 0; dur_b[0] = y_end + 1; return true; }
-        const int j = y >> 5;
+// Token walk over direction words wb[(j - jlo) * wpitch + x] (tile j, text position x), the backtrack
+// of core.pyx:32-35 restated per TOKEN: token x ends where token x+1 starts, and starts at the highest
+// frame y' of its span with d[x,y'] set, or y' == x (core.pyx:34's index == y).
+//
+// The DP stores the words BIT-REVERSED (bit 31-k <-> frame 32j + k), so "highest frame" is "lowest set
+// bit"; with m = word & mask,
+//     mask' = m ^ -m            (the bits strictly above the lowest set bit of m; 0 stays 0)
+// is the mask of the next token in the same tile: a token costs two dependent ALU ops (IADD3, LOP3)
+// once the words are in registers.  KB tokens are fetched per batch with independent loads; a batch
+// ends early (m == 0, sticky) when the walk leaves the tile.  One thread runs this chain and leaves
+// only raw material behind -- m per token, the entry token per tile -- which all threads turn into
+// start frames afterwards.
+//   state  x     current token (its start is not known yet)
+//          j     tile the walk is in
+//          mask  mask of the (reversed) frames of tile j still available to token x
+//   tokm[x]  receives m of the tile token x starts in (1 <= x)
+//   xin[j]   receives the token the walk enters tile j with (pre-zeroed by the caller)
+// Returns true when token 0 is reached, false when the walk needs a tile below jlo.
+__device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, int jlo, int &x, int &j,
+                                               uint32_t &mask, uint32_t *tokm, int *xin) {
+    constexpr int KB = 8;
+    while (x > 0) {
+        if (mask == 0u) { --j; mask = 0xffffffffu; if (j >= 0) xin[j] = x; }
         if (j < jlo) return false;
-        const uint32_t *row = wb + (size_t)(j - jlo) * wpitch;
-        uint32_t wk[KB];
+        const uint32_t *row = wb + (size_t)(j - jlo) * wpitch + x;
+        uint32_t w[KB], m[KB];
+        if (x >= KB && (x >> 5) < j) {
+            // common case: 8 real tokens, tile strictly above the diagonal (no forced move possible)
 #pragma unroll
-        for (int k = 0; k < KB; ++k) wk[k] = row[max(x - k, 0)];
-        const int jb = j << 5;
-        bool leave = false;                                 // left tile j (or reached token 0)
+            for (int k = 0; k < KB; ++k) w[k] = row[-k];
+        } else {
 #pragma unroll
-        for (int k = 0; k < KB; ++k) {
-            if (!leave) {
-                uint32_t wd = wk[k] & (0xffffffffu >> (31 - (y - jb)));
-                if ((x >> 5) == j) wd |= 1u << (x & 31);    // index == y forces the move
-                if (wd == 0u) {
-                    y = jb - 1;                             // token x continues in tile j-1
-                    leave = true;
-                } else {
-                    const int ys = jb + (31 - __clz(wd));
-                    start_b[x] = ys;
-                    dur_b[x] = y_end - ys + 1;
-                    --x;
-                    y = y_end = ys - 1;
-                    leave = (ys == jb) || (x == 0);
-                }
+            for (int k = 0; k < KB; ++k) {
+                const int xi = x - k;
+                uint32_t v = row[-min(k, x)];
+                if ((xi >> 5) == j) v |= 0x80000000u >> (xi & 31);     // index == y forces the move
+                w[k] = (xi > 0) ? v : 0u;                               // token 0 never moves (index != 0)
             }
         }
+        uint32_t mk = mask;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            m[k] = w[k] & mk;
+            mk = m[k] ^ (0u - m[k]);
+        }
+        // unconditional: an unresolved token (m == 0) is overwritten when it is resolved in a lower tile
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+            if (k == 0 || x - k > 0) tokm[x - k] = m[k];
+        // m != 0 is a prefix property (sticky zero): count it by bisection
+        int n;
+        if (m[3] != 0u) n = (m[5] != 0u) ? ((m[7] != 0u) ? 8 : ((m[6] != 0u) ? 7 : 6)) : ((m[4] != 0u) ? 5 : 4);
+        else n = (m[1] != 0u) ? ((m[2] != 0u) ? 3 : 2) : ((m[0] != 0u) ? 1 : 0);
+        x -= n;
+        mask = (n == KB) ? mk : 0u;                                      // 0: continue in tile j-1 (top of loop)
     }
+    return true;
 }
 
 // MULTIPASS: text longer than XP rows (carry line between row passes); its runtime role flags cost
@@ -539,7 +560,9 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
                 else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
 
-                // ---- direction words of this tile ----
+                // ---- direction words of this tile, bit-reversed for the token walk (bit 31-k <-> frame k) ----
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = __brev(acc[r]);
                 if (SMEM_BITS) store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, acc);
                 else store_words<R>(gbits_b + (size_t)j * P.gbits_rows_pitch + x0, acc);
 #pragma unroll
@@ -572,7 +595,19 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
     const int rows_cp = min(rows_pitch, ((t_x + 3) >> 2) << 2);
     const int chunk_tiles = SMEM_BITS ? ntiles : max(1, (int)((S::ring_bytes(NS) / 4) / rows_cp));
-    if (tid == 0) { bt_state[0] = t_x - 1; bt_state[1] = t_y - 1; bt_state[2] = t_y - 1; bt_state[3] = 0; }
+    // per-token / per-tile scratch of the walk: the idle ring when the bits have their own shared-memory
+    // region (4*(Tx + tiles) bytes always fit below two value tiles there), else global (start table, carry line)
+    int *tok = SMEM_BITS ? reinterpret_cast<int *>(ring) : start_b;
+    int *xin = SMEM_BITS ? tok + XP : reinterpret_cast<int *>(gline_b);
+    for (int jj = tid; jj < ntiles; jj += nthreads) xin[jj] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        bt_state[0] = t_x - 1;                                           // token
+        bt_state[1] = ntiles - 1;                                        // tile
+        bt_state[2] = (int)(0u - (1u << (31 - ((t_y - 1) & 31))));       // frames <= t_y-1 of the last tile
+        bt_state[3] = 0;
+        xin[ntiles - 1] = t_x - 1;
+    }
     __syncthreads();
     int jhi = ntiles;
     while (true) {
@@ -587,28 +622,45 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             __syncthreads();
         }
         if (tid == 0) {
-            int x = bt_state[0], y_end = bt_state[1], y = bt_state[2];
-            const bool done = backtrack_walk(SMEM_BITS ? bits_s : stage_bits, SMEM_BITS ? XP : rows_cp, jlo, x, y_end,
-                                             y, start_b, dur_b);
-            bt_state[0] = x; bt_state[1] = y_end; bt_state[2] = y; bt_state[3] = done ? 1 : 0;
+            int x = bt_state[0], j = bt_state[1];
+            uint32_t mask = (uint32_t)bt_state[2];
+            const bool done = backtrack_walk(SMEM_BITS ? bits_s : stage_bits, SMEM_BITS ? XP : rows_cp, jlo, x, j, mask,
+                                             reinterpret_cast<uint32_t *>(tok), xin);
+            bt_state[0] = x; bt_state[1] = j; bt_state[2] = (int)mask; bt_state[3] = done ? 1 : 0;
         }
         __syncthreads();
         if (bt_state[3]) break;
         jhi = jlo;
         __syncthreads();
     }
+    // start frames, one thread per tile: tile j holds the starts of tokens (xin[j-1], xin[j]]
+    for (int jj = tid; jj < ntiles; jj += nthreads) {
+        const int hi = xin[jj], lo = jj > 0 ? xin[jj - 1] : 0;
+        for (int x = hi; x > lo; --x) tok[x] = (jj << 5) + 32 - __ffs(tok[x]);
+    }
+    if (tid == 0) tok[0] = 0;
+    __syncthreads();
 
     if (dbg && tid == 0) dbg[5] = clock64();                               // backtrack done
     // ================================= outputs =================================
-    for (int x = t_x + tid; x < P.Tx; x += nthreads) { start_b[x] = 0; dur_b[x] = 0; }
-    if (P.frame_token) {
-        int *ft = P.frame_token + (size_t)b * P.Ty;
-        for (int x = tid; x < t_x; x += nthreads) {
-            const int s = start_b[x], e = s + dur_b[x];
-            for (int y = s; y < e; ++y) ft[y] = x;
+    // [start, duration] per token from the start frames; frame -> token index; dense path
+    int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
+    for (int x = tid; x < P.Tx; x += nthreads) {
+        int s = 0, d = 0;
+        if (x < t_x) {
+            s = tok[x];
+            d = ((x + 1 < t_x) ? tok[x + 1] : t_y) - s;
         }
-        for (int y = t_y + tid; y < P.Ty; y += nthreads) ft[y] = -1;
+        if (SMEM_BITS) start_b[x] = s;
+        dur_b[x] = d;
+        if (ft)
+            for (int y = s; y < s + d; ++y) ft[y] = x;
     }
+    if (ft)
+        for (int y = t_y + tid; y < P.Ty; y += nthreads) ft[y] = -1;
+    __syncthreads();
+    if (!SMEM_BITS)                                                        // tok aliases start_b: zero the padding rows
+        for (int x = t_x + tid; x < P.Tx; x += nthreads) start_b[x] = 0;
     __syncthreads();
     write_path_any(P, b, start_b, dur_b, tid, nthreads);
     if (dbg && tid == 0) { dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y; }
