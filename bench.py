@@ -58,6 +58,24 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of the same shape (profiles/r1_ncu_full_*.json); None if there is none."""
+    name = {"mas_forward_backtrack": "r1_ncu_full_mas_forward_B32.json"}.get(kernel)
+    if not name:
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[k]
+            tot += float(v.replace(",", "")) * scale[u]
+        return tot
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -302,7 +320,7 @@ def run_cuda(args):
         step_bytes = 4 * F * B * (TX + TY) + 4 * CELLS        # fused algorithmic traffic: inputs + dense path
         roofline = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
             "kernels_ms": {k: v["ms"] for k, v in kernels.items()},
             "step_algorithmic_bytes": step_bytes,
             "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,

@@ -40,7 +40,9 @@ bool valid_rw(int R, int W) { return (R == 1 || R == 2 || R == 4 || R == 8) && W
 
 // Pick rows-per-lane / DP warps / ring depth for (B, Tx, Ty).
 bool make_plan(int B, int Tx, int Ty, int sm_count, Plan *p) {
-    static const int table[][2] = {{1, 1}, {2, 1}, {2, 2}, {2, 3}, {4, 2}, {4, 3}, {4, 4}};
+    // R = 4 rows per lane hides the lane-to-lane shuffle behind the other rows' updates (29 static
+    // cycles/frame against 33 for R = 2 and 41 for R = 8, scripts/tools/sass_stalls.py)
+    static const int table[][2] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 3}, {4, 4}};
     int R = 4, W = 4;
     for (auto &rw : table) {
         if (32 * rw[0] * rw[1] >= Tx) { R = rw[0]; W = rw[1]; break; }
