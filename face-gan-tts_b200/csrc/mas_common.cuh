@@ -123,6 +123,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *t
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP): src/dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_bulk_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // progress flags in shared memory (one writer warp, one reader warp)
 // ---------------------------------------------------------------------------
