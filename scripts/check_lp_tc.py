@@ -35,3 +35,17 @@ for (B, F, Tx, Ty) in [(2, 80, 61, 200), (4, 80, 190, 1000), (32, 80, 190, 1000)
         ab = (o.double() - r).abs().max().item()
         us = t(lambda: fgt.log_prior(mu, y, impl=impl))
         print(f"B={B} F={F} Tx={Tx} Ty={Ty} {impl:8s} max rel {rel:.3e} max abs {ab:.3e}  {us:.1f} us", flush=True)
+
+# raw kernel timing through the C ABI (no allocation in the loop)
+from face_gan_tts_b200 import _lib
+L = _lib.lib()
+for (B, F, Tx, Ty) in [(32, 80, 190, 1000), (64, 80, 190, 1000), (148, 80, 190, 1000), (16, 80, 200, 800)]:
+    mu, y, tx, ty = synthetic.lrs2_batch(B, F, Tx, Ty, seed=5, tx_lo=Tx // 3, ty_lo=Ty // 3)
+    mu, y = mu.cuda(), y.cuda()
+    out = torch.empty((B, Tx, Ty), device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+    for name, impl in (("ffma", 1), ("tcgen05", 2)):
+        def call():
+            rc = L.mas_b200_log_prior(mu.data_ptr(), y.data_ptr(), B, F, Tx, Ty, out.data_ptr(), impl, sp)
+            assert rc == 0, rc
+        print(f"raw B={B} F={F} Tx={Tx} Ty={Ty} {name:8s} {t(call, 50):.1f} us", flush=True)
