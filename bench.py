@@ -135,6 +135,11 @@ def reference_step_fn():
     import oracle
     from face_gan_tts_b200 import synthetic
 
+    # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host thread it can use
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     core = oracle.reference_core("asis")
     kind = "reference"
     if core is None:
@@ -187,7 +192,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
     import face_gan_tts_b200 as fgt
-    from face_gan_tts_b200 import _lib, synthetic
+    from face_gan_tts_b200 import _lib, sharding, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,7 +245,7 @@ def run_cuda(args):
             ev.record(stream)
             comm_stream.wait_event(ev)
             with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(gathered[i % 2], d["dur"])
+                sharding.all_gather_durations_into(gathered[i % 2], d["dur"])
 
     def barrier():
         if dist:

@@ -6,7 +6,7 @@ Drop-in for the alignment hot path of CognitiveModeling/Face-GAN-TTS:
 libmas_b200.so (hand-written CUDA behind a C ABI, include/mas_b200.h); this
 package is the thin PyTorch-facing host layer.  No CPU fallback.
 """
-from . import monotonic_align  # noqa: F401
+from . import monotonic_align, sharding  # noqa: F401
 from .alignment import (  # noqa: F401
     AlignmentResult,
     align,
