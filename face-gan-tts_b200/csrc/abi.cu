@@ -55,6 +55,24 @@ int device_info(DeviceInfo *out) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// One auxiliary stream + fork/join events per (host thread, device): the overlapped log-prior || MAS pipeline
+// forks from and joins back into the caller's stream, so the call stays stream-ordered for the caller.
+struct AuxStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static AuxStream *aux_stream() {
+    static thread_local AuxStream cache[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    AuxStream &a = cache[dev];
+    if (a.stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) { a.stream = nullptr; return nullptr; }
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(a.stream); a.stream = nullptr; return nullptr;
+        }
+    }
+    return &a;
+}
+
 }  // namespace masb200
 
 using namespace masb200;
@@ -128,8 +146,9 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev, int B, int F, 
 
 size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty) {
     if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return 0;
-    // MAS workspace + room for the [B,Tx,Ty] value matrix of the unfused pipeline
-    return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256);
+    // MAS workspace + the [B,Tx,Ty] value matrix (L2-resident hand-off) + per-group ready flags
+    return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256) +
+           align_up(sizeof(int) * (size_t)B * ((Ty + 63) / 64), 256);
 }
 
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, const int *t_x_dev,
@@ -142,7 +161,43 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) return MAS_B200_ERR_ALIGN;
     const size_t mas_ws = align_up(workspace_layout(B, Tx, Ty).total, 256);
     float *value = reinterpret_cast<float *>(static_cast<char *>(workspace_dev) + mas_ws);
-    int rc = mas_b200_log_prior(mu_x_dev, y_dev, B, F, Tx, Ty, value, impl, stream);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    // Overlapped pipeline: the tcgen05 log-prior kernel (aux stream, on the SMs the B MAS CTAs leave free)
+    // publishes every 64-frame group of every utterance with a device-scope flag; the MAS kernel's TMA
+    // producer acquires the flag before loading the tiles of that group.  The value matrix is handed over
+    // through L2, and the alignment search starts while most of the log-prior is still being computed.
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != MAS_B200_OK) return rc;
+    const int fi = option("fused_impl");
+    const bool tc_ok = (impl == MAS_B200_LP_AUTO || impl == MAS_B200_LP_TCGEN05) && option("lp_impl") != MAS_B200_LP_FFMA &&
+                       log_prior_tc_supported(mu_x_dev, y_dev, value, B, F, Tx, Ty);
+    if (tc_ok && fi != 1 && 2 * B <= di.sm_count) {
+        AuxStream *aux = aux_stream();
+        if (aux != nullptr) {
+            const int ngroups = (Ty + 63) / 64;
+            int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(value) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256));
+            MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B * ngroups, s));
+            MASB200_CUDA_TRY(cudaEventRecord(aux->fork, s));
+            MASB200_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+            rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, aux->stream, flags, ngroups, di.sm_count - B);
+            if (rc != MAS_B200_OK) return rc;
+            MASB200_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
+            MasLaunch L{};
+            L.value = value; L.stride_b = (long long)Tx * Ty; L.stride_x = Ty;
+            L.t_x = t_x_dev; L.t_y = t_y_dev; L.B = B; L.Tx = Tx; L.Ty = Ty; L.neg = max_neg_val;
+            L.path = path_dev; L.path_dtype = path_dtype;
+            L.durations = durations_dev; L.frame_token = frame_token_dev; L.status = status_dev;
+            L.workspace = workspace_dev; L.workspace_bytes = mas_ws; L.stream = s;
+            L.gate = flags; L.gate_pitch = ngroups;
+            rc = launch_mas(L);
+            // join even on error so the aux stream never runs ahead of the caller's stream
+            MASB200_CUDA_TRY(cudaStreamWaitEvent(s, aux->join, 0));
+            return rc;
+        }
+    }
+    rc = mas_b200_log_prior(mu_x_dev, y_dev, B, F, Tx, Ty, value, impl, stream);
     if (rc != MAS_B200_OK) return rc;
     return mas_b200_maximum_path(value, (long long)Tx * Ty, Ty, t_x_dev, t_y_dev, B, Tx, Ty, max_neg_val, path_dev,
                                  path_dtype, durations_dev, frame_token_dev, status_dev, workspace_dev, mas_ws, stream);

@@ -24,6 +24,10 @@ struct LpTcParams {
     int B, Tx, Ty;
     float cst;
     int groups_per_cta, ngroups;
+    int chunks;          // CTAs per utterance
+    int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
+    int *flags;          // optional [B][flag_pitch]: set to 1 when a 64-frame group of an utterance is in memory
+    int flag_pitch;
 };
 
 template <int KS>
@@ -39,8 +43,9 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
     const int lane = tid & 31;
     const int b = blockIdx.y;
-    const int g0 = blockIdx.x * P.groups_per_cta;
-    const int ng = min(P.groups_per_cta, P.ngroups - g0);                     // groups of this CTA
+    const int gs = P.strided ? P.chunks : 1;                                  // group stride of this CTA
+    const int g0 = P.strided ? (int)blockIdx.x : (int)blockIdx.x * P.groups_per_cta;
+    const int ng = P.strided ? (P.ngroups - g0 + gs - 1) / gs : min(P.groups_per_cta, P.ngroups - g0);   // groups of this CTA
     if (ng <= 0) return;
     const int MT = (P.Tx + 127) >> 7;                                         // M-tiles of 128 text positions
 
@@ -52,7 +57,7 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     const uint32_t tmem = __shfl_sync(kFullMask, *S.tmem_slot, 0);
 
     if (warp == 4) {
-        lp_mma_warp<KS>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, ng, MT, tmem);
+        lp_mma_warp<KS>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng, MT, tmem);
     } else {
         float musq[2];
         lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [](int mt, int m) { return mt * 128 + m; }, musq);
@@ -62,7 +67,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
             if (g >= 1) {
                 // ---- epilogue of group g-1: thread = text position, 64 consecutive frames per M-tile
                 const int gg = g - 1, p = gg & 1;
-                const int t0 = (g0 + gg) * kLpGroup;
+                const int gidx = g0 + gg * gs;
+                const int t0 = gidx * kLpGroup;
                 uint32_t d0[2][32], d1[2][32];
                 lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1);
 #pragma unroll
@@ -85,6 +91,12 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                             }
                         }
                     }
+                }
+                if (P.flags != nullptr) {
+                    // publish the group to the MAS kernel running next to this one (device-scope release)
+                    __threadfence();
+                    lp_aux_bar();
+                    if (tid == 0) gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
                 }
             }
         }
@@ -123,13 +135,18 @@ int make_y_tensor_map(const float *y, int B, int F, int Ty, CUtensorMap *out) {
     return r == CUDA_SUCCESS ? MAS_B200_OK : MAS_B200_ERR_ARG;
 }
 
-int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream) {
-    if (!mu_x || !y || !out || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
-    // shapes the tensor-core kernel takes; everything else goes to the FFMA kernel
-    if (F % 8 != 0 || F > kMaxF || Tx > 256 || Ty % 4 != 0 || B > 65535) return MAS_B200_ERR_UNSUPPORTED;
+// shapes the tensor-core kernel takes; everything else goes to the FFMA kernel
+bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty) {
+    if (!(F == 64 || F == 80 || F == 96) || Tx > 256 || Ty % 4 != 0 || B > 65535) return false;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(mu_x) & 15))
-        return MAS_B200_ERR_UNSUPPORTED;
+        return false;
+    return true;
+}
+
+int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
+                        cudaStream_t stream, int *flags, int flag_pitch, int max_ctas) {
+    if (!mu_x || !y || !out || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    if (!log_prior_tc_supported(mu_x, y, out, B, F, Tx, Ty)) return MAS_B200_ERR_UNSUPPORTED;
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc != MAS_B200_OK) return rc;
@@ -141,10 +158,14 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     LpTcParams P{};
     P.mu = mu_x; P.out = out; P.B = B; P.Tx = Tx; P.Ty = Ty; P.cst = log_prior_const(F);
     P.ngroups = (Ty + kLpGroup - 1) / kLpGroup;
-    int chunks = di.sm_count / B;                               // one wave of CTAs (one CTA per SM: TMEM + smem)
+    P.flags = flags; P.flag_pitch = flag_pitch;
+    const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;
+    int chunks = cta_budget / B;                                // one wave of CTAs (one CTA per SM: TMEM + smem)
     chunks = chunks < 1 ? 1 : (chunks > P.ngroups ? P.ngroups : chunks);
     P.groups_per_cta = (P.ngroups + chunks - 1) / chunks;
     chunks = (P.ngroups + P.groups_per_cta - 1) / P.groups_per_cta;
+    P.chunks = chunks;
+    P.strided = flags != nullptr ? 1 : 0;
     size_t smem = ((LpFrontSmem::total(F) + 127) / 128) * 128 + (size_t)F * Tx * 4 + 1024;
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;   // > half an SM: one CTA per SM (each allocates all of TMEM)
 

@@ -96,11 +96,11 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// MMA / TMA warp: all 32 lanes run this (warp-uniform); ng groups of 64 frames starting at frame t_begin.
+// MMA / TMA warp: all 32 lanes run this (warp-uniform); ng groups of 64 frames: frames t_begin + k*t_stride.
 // ---------------------------------------------------------------------------------------------------
 template <int KS>
 __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap *ymap, const float *mu_b, float *mu_stage,
-                                            int Tx, int b, int t_begin, int ng, int MT, uint32_t tmem) {
+                                            int Tx, int b, int t_begin, int t_stride, int ng, int MT, uint32_t tmem) {
     constexpr int F = 8 * KS;
     constexpr uint32_t kSbo = (uint32_t)F * 32u;                 // 8 frames x F mel bins x 4 B per row group
     const uint32_t idesc = umma_idesc_tf32_ts(128, kLpGroup);
@@ -120,7 +120,7 @@ __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap 
         // every aux thread is done with the raw buffer: fetch the next group into it
         if (g + 1 < ng && elect_one()) {
             mbar_arrive_expect_tx(S.bar_raw, LpFrontSmem::raw_bytes(F));
-            tma_load_3d(S.raw, ymap, t_begin + (g + 1) * kLpGroup, 0, b, S.bar_raw);
+            tma_load_3d(S.raw, ymap, t_begin + (g + 1) * t_stride, 0, b, S.bar_raw);
         }
         __syncwarp();
         if (g >= 1) mbar_wait_warp(S.bar_dempty, (uint32_t)(g - 1) & 1u);

@@ -148,6 +148,15 @@ __device__ __forceinline__ void flag_release_if(int *flag, int v, uint32_t pred)
                  " @p st.release.cta.shared::cta.s32 [%0], %1;\n"
                  "}\n" ::"r"(smem_u32(flag)), "r"(v), "r"(pred) : "memory");
 }
+// device-scope flags in global memory (cross-CTA hand-off between the log-prior and MAS kernels)
+__device__ __forceinline__ void gflag_release(int *flag, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ int gflag_acquire(const int *flag) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
+}
 // whole-warp wait with a warp-uniform exit (see mbar_wait_warp); returns the smallest value seen
 __device__ __forceinline__ int flag_wait_ge_warp(const int *flag, int target) {
     int v = flag_acquire(flag);

@@ -76,6 +76,8 @@ struct MasParams {
     int line_pitch;
     void *path;              // optional in-kernel dense path write
     int path_dtype;          // MAS_B200_PATH_*
+    const int *gate;         // optional [B][gate_pitch]: group g of utterance b may be read once gate != 0
+    int gate_pitch;          //   (written by the log-prior kernel running concurrently), 64 frames per group
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
@@ -457,6 +459,16 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 mbar_wait(&ring_empty[stage], phase ^ 1);
                 float *dst = ring + (size_t)stage * kTileFloats;
                 const int t0 = j * NT;
+                if (P.gate != nullptr && (j & 1) == 0) {
+                    // the value matrix is being produced by another kernel: wait for this 64-frame group
+                    const int *gf = P.gate + (size_t)b * P.gate_pitch + (j >> 1);
+                    const long long c0 = clock64();
+                    while (gflag_acquire(gf) == 0) {
+                        if (clock64() - c0 > (1ll << 31)) __trap();
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> the TMA reads below
+                    __syncwarp();
+                }
                 const int nfr = min(NT, P.Ty - t0);                 // frames that exist in memory
                 if (P.aligned) {
                     // lane i issues request (r, qb): rows {rows_base + (qb*NB + l)*R + r : l < NB}

@@ -56,6 +56,8 @@ struct MasLaunch {
     void *workspace;
     size_t workspace_bytes;
     cudaStream_t stream;
+    const int *gate;    // optional device flags [B][gate_pitch] (see MasParams::gate); null normally
+    int gate_pitch;
 };
 int launch_mas(const MasLaunch &L);
 
@@ -68,6 +70,7 @@ int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int T
                           cudaStream_t stream);
 // tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int *flags = nullptr, int flag_pitch = 0, int max_ctas = 0);
+bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty);
 
 }  // namespace masb200
