@@ -148,7 +148,7 @@ size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty) {
     if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return 0;
     // MAS workspace + the [B,Tx,Ty] value matrix (L2-resident hand-off) + per-group ready flags
     return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256) +
-           align_up(sizeof(int) * (size_t)B * ((Ty + 63) / 64), 256);
+           align_up(sizeof(int) * (size_t)B * ((Ty + 63) / 64 + 1), 256);
 }
 
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, const int *t_x_dev,
@@ -178,20 +178,34 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
         if (aux != nullptr) {
             const int ngroups = (Ty + 63) / 64;
             int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(value) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256));
-            MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B * ngroups, s));
+            int *done = flags + (size_t)B * ngroups;            // [B] "table final" flags, same memset
+            const bool want_path = path_dtype != MAS_B200_PATH_NONE && path_dev != nullptr;
+            PathJob job{};
+            if (want_path) {
+                job.start = mas_start_table(workspace_dev, B, Tx, Ty);
+                job.dur = mas_dur_table(workspace_dev, B, Tx, Ty, durations_dev);
+                job.done = done; job.path = path_dev; job.path_dtype = path_dtype;
+            }
+            MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)B * ngroups + B), s));
             MASB200_CUDA_TRY(cudaEventRecord(aux->fork, s));
             MASB200_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-            rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, aux->stream, flags, ngroups, di.sm_count - B);
-            if (rc != MAS_B200_OK) return rc;
-            MASB200_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
+            // validate the consumer's plan before anything is launched (each kernel waits for the other's flags)
             MasLaunch L{};
             L.value = value; L.stride_b = (long long)Tx * Ty; L.stride_x = Ty;
             L.t_x = t_x_dev; L.t_y = t_y_dev; L.B = B; L.Tx = Tx; L.Ty = Ty; L.neg = max_neg_val;
             L.path = path_dev; L.path_dtype = path_dtype;
             L.durations = durations_dev; L.frame_token = frame_token_dev; L.status = status_dev;
             L.workspace = workspace_dev; L.workspace_bytes = mas_ws; L.stream = s;
-            L.gate = flags; L.gate_pitch = ngroups;
+            L.gate = flags; L.gate_pitch = ngroups; L.done = want_path ? done : nullptr;
+            L.dry_run = 1;
             rc = launch_mas(L);
+            if (rc != MAS_B200_OK) return rc;
+            L.dry_run = 0;
+            // producer first (the block scheduler must place its CTAs before the consumer's start spinning)
+            rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, aux->stream, flags, ngroups, di.sm_count - B,
+                                     want_path ? &job : nullptr);
+            if (rc == MAS_B200_OK) rc = launch_mas(L);
+            MASB200_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
             // join even on error so the aux stream never runs ahead of the caller's stream
             MASB200_CUDA_TRY(cudaStreamWaitEvent(s, aux->join, 0));
             return rc;

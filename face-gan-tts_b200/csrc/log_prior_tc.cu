@@ -7,6 +7,7 @@
 #include <cudaTypedefs.h>
 
 #include "lp_tc_frontend.cuh"
+#include "mas_forward.cuh"
 #include "mas_host.h"
 
 namespace masb200 {
@@ -26,6 +27,7 @@ struct LpTcParams {
     int groups_per_cta, ngroups;
     int chunks;          // CTAs per utterance
     int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
+    PathJob job;         // optional: expand the dense path of utterance b once the MAS kernel reports it done
     int *flags;          // optional [B][flag_pitch]: set to 1 when a 64-frame group of an utterance is in memory
     int flag_pitch;
 };
@@ -104,6 +106,30 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kLpTmemCols);
+
+    // ---- dense path of this utterance: the CTAs that computed its log-prior share the rows once the MAS
+    // kernel (running on other SMs) has published the [start,dur] table.  A pure streaming write.
+    if (P.job.path != nullptr) {
+        if (tid == 0) {
+            const long long c0 = clock64();
+            while (gflag_acquire(P.job.done + b) == 0) {
+                __nanosleep(200);
+                if (clock64() - c0 > (1ll << 33)) __trap();
+            }
+        }
+        __syncthreads();
+        const int nchunk = (int)gridDim.x, c = (int)blockIdx.x;
+        const int rows_per = (P.Tx + nchunk - 1) / nchunk;
+        const int x0 = c * rows_per, rows = min(rows_per, P.Tx - x0);
+        if (rows > 0) {
+            const int *sb = P.job.start + (size_t)b * P.Tx + x0, *db = P.job.dur + (size_t)b * P.Tx + x0;
+            const size_t off = ((size_t)b * P.Tx + x0) * P.Ty;
+            if (P.job.path_dtype == MAS_B200_PATH_F32)
+                write_path_rows<float>(reinterpret_cast<float *>(P.job.path) + off, sb, db, rows, P.Ty, tid, kTcThreads);
+            else
+                write_path_rows<int>(reinterpret_cast<int *>(P.job.path) + off, sb, db, rows, P.Ty, tid, kTcThreads);
+        }
+    }
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 encoder() {
@@ -144,7 +170,7 @@ bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out,
 }
 
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream, int *flags, int flag_pitch, int max_ctas) {
+                        cudaStream_t stream, int *flags, int flag_pitch, int max_ctas, const PathJob *job) {
     if (!mu_x || !y || !out || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!log_prior_tc_supported(mu_x, y, out, B, F, Tx, Ty)) return MAS_B200_ERR_UNSUPPORTED;
     DeviceInfo di;
@@ -159,6 +185,7 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     P.mu = mu_x; P.out = out; P.B = B; P.Tx = Tx; P.Ty = Ty; P.cst = log_prior_const(F);
     P.ngroups = (Ty + kLpGroup - 1) / kLpGroup;
     P.flags = flags; P.flag_pitch = flag_pitch;
+    if (job) P.job = *job;
     const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;
     int chunks = cta_budget / B;                                // one wave of CTAs (one CTA per SM: TMEM + smem)
     chunks = chunks < 1 ? 1 : (chunks > P.ngroups ? P.ngroups : chunks);
@@ -176,7 +203,14 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
         case 96: kern = log_prior_tc_kernel<12>; break;
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
-    MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    static std::atomic<int> configured[16][3];
+    int dev = 0;
+    MASB200_CUDA_TRY(cudaGetDevice(&dev));
+    const int ki = F == 64 ? 0 : (F == 80 ? 1 : 2);
+    if (dev < 0 || dev >= 16 || !configured[dev][ki].load(std::memory_order_acquire)) {
+        MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        if (dev >= 0 && dev < 16) configured[dev][ki].store(1, std::memory_order_release);
+    }
     kern<<<dim3(chunks, B), kTcThreads, smem, stream>>>(P, ymap);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;

@@ -114,6 +114,14 @@ int make_value_tensor_map(const MasLaunch &L, int R, int W, CUtensorMap *out) {
 
 }  // namespace
 
+const int *mas_start_table(void *workspace, int B, int Tx, int Ty) {
+    return reinterpret_cast<const int *>(static_cast<char *>(workspace) + workspace_layout(B, Tx, Ty).start_off);
+}
+const int *mas_dur_table(void *workspace, int B, int Tx, int Ty, const int *user_durations) {
+    return user_durations ? user_durations
+                          : reinterpret_cast<const int *>(static_cast<char *>(workspace) + workspace_layout(B, Tx, Ty).dur_off);
+}
+
 Workspace workspace_layout(int B, int Tx, int Ty) {
     Workspace w{};
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
@@ -168,7 +176,7 @@ int launch_mas(const MasLaunch &L) {
     P.gbits_stride_b = (long long)ws.tiles * ws.rows_pitch;
     P.gline = reinterpret_cast<float *>(wsb + ws.gline_off);
     P.line_pitch = ws.line_pitch;
-    P.gate = L.gate; P.gate_pitch = L.gate_pitch;
+    P.gate = L.gate; P.gate_pitch = L.gate_pitch; P.done = L.done;
     {   // diagnostics: device pointer to a [B][8] int64 buffer smuggled through two int options
         const unsigned lo = (unsigned)option("mas_debug_ptr_lo"), hi = (unsigned)option("mas_debug_ptr_hi");
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
@@ -176,10 +184,11 @@ int launch_mas(const MasLaunch &L) {
 
     int fuse = option("mas_fused_path_write");
     if (fuse < 0) fuse = (L.B >= 2 * di.sm_count) ? 1 : 0;
-    const bool want_path = L.path_dtype != MAS_B200_PATH_NONE;
+    const bool want_path = L.path_dtype != MAS_B200_PATH_NONE && L.done == nullptr;
     P.path = (want_path && fuse) ? L.path : nullptr;
     P.path_dtype = (want_path && fuse) ? L.path_dtype : MAS_B200_PATH_NONE;
 
+    if (L.dry_run) P.B = 0;     // launchers only load the kernel image
     const int mode = plan.smem_bits ? MAS_MODE_SMEM_BITS : (L.Tx > XP ? MAS_MODE_MULTIPASS : MAS_MODE_GLOBAL_BITS);
     switch (plan.R) {
         case 1: rc = launch_mas_r1(P, tmap, plan.W, mode, plan.smem, L.stream); break;
@@ -188,7 +197,7 @@ int launch_mas(const MasLaunch &L) {
         case 8: rc = launch_mas_r8(P, tmap, plan.W, mode, plan.smem, L.stream); break;
         default: rc = MAS_B200_ERR_UNSUPPORTED;
     }
-    if (rc != MAS_B200_OK) return rc;
+    if (rc != MAS_B200_OK || L.dry_run) return rc;
 
     if (want_path && !fuse)
         return launch_path_expand(P.start, P.dur, L.B, L.Tx, L.Ty, L.path, L.path_dtype, L.stream);

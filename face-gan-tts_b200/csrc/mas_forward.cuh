@@ -76,6 +76,7 @@ struct MasParams {
     int line_pitch;
     void *path;              // optional in-kernel dense path write
     int path_dtype;          // MAS_B200_PATH_*
+    int *done;               // optional [B]: set to 1 (device-scope release) once the [start,dur] table of item b is final
     const int *gate;         // optional [B][gate_pitch]: group g of utterance b may be read once gate != 0
     int gate_pitch;          //   (written by the log-prior kernel running concurrently), 64 frames per group
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
@@ -413,6 +414,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_BAD_LENGTH;
         __syncthreads();
         write_path_any(P, b, start_b, dur_b, tid, nthreads);
+        if (P.done != nullptr) { __threadfence(); __syncthreads(); if (tid == 0) gflag_release(P.done + b, 1); }
         return;
     }
     if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_OK;
@@ -455,6 +457,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             // ============================ producer warp ============================
             int stage = 0;
             uint32_t phase = 0;
+            long long gate_spins = 0;
             for (int j = 0; j < ntiles; ++j) {
                 mbar_wait(&ring_empty[stage], phase ^ 1);
                 float *dst = ring + (size_t)stage * kTileFloats;
@@ -464,6 +467,8 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                     const int *gf = P.gate + (size_t)b * P.gate_pitch + (j >> 1);
                     const long long c0 = clock64();
                     while (gflag_acquire(gf) == 0) {
+                        __nanosleep(64);
+                        ++gate_spins;
                         if (clock64() - c0 > (1ll << 31)) __trap();
                     }
                     asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> the TMA reads below
@@ -506,6 +511,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 }
                 if (++stage == NS) { stage = 0; phase ^= 1; }
             }
+            if (dbg && lane == 0) dbg[10] = gate_spins;
         } else if (warp < w_act) {
             // ============================== DP warps ==============================
             // Nothing in the tile loop may branch (or predicate) on a loop-invariant condition: ptxas hoists
@@ -674,6 +680,11 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     if (!SMEM_BITS)                                                        // tok aliases start_b: zero the padding rows
         for (int x = t_x + tid; x < P.Tx; x += nthreads) start_b[x] = 0;
     __syncthreads();
+    if (P.done != nullptr) {                     // the dense path of this item is written by the kernel watching `done`
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) gflag_release(P.done + b, 1);
+    }
     write_path_any(P, b, start_b, dur_b, tid, nthreads);
     if (dbg && tid == 0) { dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y; }
 }

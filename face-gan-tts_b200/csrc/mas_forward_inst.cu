@@ -25,6 +25,17 @@ int launch_inst(const MasParams &P, const CUtensorMap &tmap, size_t smem, cudaSt
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
     }
+    if (P.B <= 0) {
+        // prepare only: force the (lazily loaded) kernel image onto the device now.  A later launch that has to
+        // load it would wait for running kernels -- a deadlock when one of them is waiting for THIS kernel.
+        static std::atomic<int> loaded[16];
+        if (dev < 0 || dev >= 16 || !loaded[dev].load(std::memory_order_acquire)) {
+            cudaFuncAttributes attr;
+            MASB200_CUDA_TRY(cudaFuncGetAttributes(&attr, kern));
+            if (dev >= 0 && dev < 16) loaded[dev].store(1, std::memory_order_release);
+        }
+        return MAS_B200_OK;
+    }
     kern<<<P.B, (W + 1) * 32, smem, stream>>>(P, tmap);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;

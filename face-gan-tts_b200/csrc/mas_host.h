@@ -58,7 +58,20 @@ struct MasLaunch {
     cudaStream_t stream;
     const int *gate;    // optional device flags [B][gate_pitch] (see MasParams::gate); null normally
     int gate_pitch;
+    int dry_run;        // 1: validate arguments / plan only, launch nothing
+    int *done;          // optional device flags [B]: when set, the dense path is NOT written here; the kernel
+                        // watching `done` expands it from the [start,dur] table (see PathJob)
 };
+
+// dense-path expansion job handed to the log-prior kernel of the overlapped pipeline
+struct PathJob {
+    const int *start, *dur;   // [B,Tx] tables in the MAS workspace
+    const int *done;          // [B]
+    void *path;
+    int path_dtype;
+};
+const int *mas_start_table(void *workspace, int B, int Tx, int Ty);
+const int *mas_dur_table(void *workspace, int B, int Tx, int Ty, const int *user_durations);
 int launch_mas(const MasLaunch &L);
 
 int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, void *path, int path_dtype,
@@ -70,7 +83,8 @@ int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int T
                           cudaStream_t stream);
 // tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream, int *flags = nullptr, int flag_pitch = 0, int max_ctas = 0);
+                        cudaStream_t stream, int *flags = nullptr, int flag_pitch = 0, int max_ctas = 0,
+                        const PathJob *job = nullptr);
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty);
 
 }  // namespace masb200
