@@ -59,7 +59,8 @@ bool make_plan(int B, int Tx, int Ty, int sm_count, Plan *p) {
     size_t budget = kMaxSmem / per_sm - kStaticSmem - (per_sm > 1 ? 1024 : 0);
 
     const size_t tile_bytes = sizeof(float) * (size_t)XP * kTilePitch;
-    const size_t bits_bytes = sizeof(uint32_t) * (size_t)tiles * XP;
+    // direction words + the per-tile transfer table (one byte per row and tile) of the backtrack
+    const size_t bits_bytes = (sizeof(uint32_t) + 1) * (size_t)tiles * XP;
     const bool single_pass = Tx <= XP;
     const int ns_cap = option("mas_ring_stages") > 0 ? option("mas_ring_stages") : 8;
 

@@ -313,6 +313,54 @@ __device__ __forceinline__ void write_path_any(const MasParams &P, int b, const 
         write_path_rows<int>(reinterpret_cast<int *>(P.path) + off, start_b, dur_b, P.Tx, P.Ty, tid, nthreads);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backtrack, latency path (direction words in shared memory).  The token walk below is a chain of
+// ~t_x + tiles dependent steps run by one thread; most of it moves off the critical path like this:
+//   transfer table   nj[j][x] = number of tokens the path completes inside tile j when it enters the tile
+//                    (at its last frame) on token x.  Computed for ALL x of a tile by one warp, 32 rows per
+//                    lane group, as soon as the DP warps are done with the tile -- by the TMA producer warp,
+//                    which is otherwise idle and learns exactly that from the ring's `empty` barrier.
+//   after the DP     x_in(j-1) = x_in(j) - nj[j][x_in(j)]: one dependent shared-memory load per TILE, then one
+//                    thread per tile re-walks its own tile from x_in(j) and emits the token start frames.
+// Same m / mask' = m ^ -m chain as backtrack_walk (words bit-reversed, forced move on the diagonal,
+// token 0 never moves).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bt_tile_mask(int j, int ntiles, int t_y) {
+    return (j == ntiles - 1) ? (0u - (1u << (31 - ((t_y - 1) & 31)))) : 0xffffffffu;     // frames <= t_y-1
+}
+
+// The DP stores the words of the shared-memory path "walk ready": the forced move of the diagonal cell
+// (core.pyx:34, index == y) is OR-ed in and the word of token 0 (which never moves) is zero.
+// Entry tokens far from the path complete a token per frame (their words are all ones), so the chain is cut
+// after kBtSteps tokens: an entry that is still moving then gets kBtUnknown and, in the unlikely case the
+// real path enters the tile there, the tile is re-walked serially after the DP.
+constexpr int kBtSteps = 16;
+constexpr int kBtUnknown = 255;
+
+template <int G>
+__device__ __forceinline__ void bt_tile_transfer(const uint32_t *bits_j, unsigned char *nj_j, int j, int t_x,
+                                                 uint32_t mask0, int lane) {
+    uint32_t mk[G];
+    int n[G];
+    const int xmax = min(t_x - 1, 32 * j + 31);               // entry tokens that can be on the path (x <= y)
+#pragma unroll
+    for (int g = 0; g < G; ++g) { mk[g] = (32 * g + lane <= xmax) ? mask0 : 0u; n[g] = 0; }
+    // token 0's word is zero, so a chain that reaches it stops there (sticky zero): indices below row 0 are
+    // only ever read with mk == 0 and need no bounds check (they stay inside the CTA's shared memory)
+    const uint32_t *p = bits_j + lane;
+#pragma unroll 4
+    for (int k = 0; k < kBtSteps; ++k) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const uint32_t m = p[32 * g - k] & mk[g];
+            if (m != 0u) n[g] = k + 1;
+            mk[g] = m ^ (0u - m);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) nj_j[32 * g + lane] = (unsigned char)(mk[g] != 0u ? kBtUnknown : n[g]);
+}
+
 // Token walk over direction words wb[(j - jlo) * wpitch + x] (tile j, text position x), the backtrack
 // of core.pyx:32-35 restated per TOKEN: token x ends where token x+1 starts, and starts at the highest
 // frame y' of its span with d[x,y'] set, or y' == x (core.pyx:34's index == y).
@@ -374,14 +422,15 @@ __device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, i
 
 // MULTIPASS: text longer than XP rows (carry line between row passes); its runtime role flags cost
 // the single-pass instantiations nothing.
+// Warps: 0..W-1 DP, W TMA producer, W+1 (SMEM_BITS only) backtrack helper.
 template <int R, int W, bool SMEM_BITS, bool MULTIPASS>
-__global__ void __launch_bounds__((W + 1) * 32, 1)
+__global__ void __launch_bounds__((W + 1 + (SMEM_BITS ? 1 : 0)) * 32, 1)
 mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) {
     using S = MasSmem<R, W>;
     constexpr int XP = S::XP;
     constexpr int NT = kTileFrames;
     constexpr int kTileFloats = S::kTileFloats;
-    constexpr int nthreads = (W + 1) * 32;
+    constexpr int nthreads = (W + 1 + (SMEM_BITS ? 1 : 0)) * 32;
 
     const int NS = P.ring_stages;
     const int HS = S::halo_slots(NS);
@@ -420,6 +469,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_OK;
 
     const int ntiles = (t_y + NT - 1) / NT;
+    unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XP);   // [ntiles][XP] transfer table
     const int npass = (t_x + XP - 1) / XP;
     long long *dbg = P.dbg ? P.dbg + (size_t)b * 16 : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
@@ -512,6 +562,16 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 if (++stage == NS) { stage = 0; phase ^= 1; }
             }
             if (dbg && lane == 0) dbg[10] = gate_spins;
+        } else if (SMEM_BITS && warp == W + 1) {
+            // ========================== backtrack helper warp ==========================
+            // trails the LAST active DP warp (its progress flag implies every earlier warp is past the tile too)
+            const int *flag_last = hprog + (w_act - 1);
+            int known = 0;
+            for (int jt = 0; jt < ntiles; ++jt) {
+                if (known < jt + 1) known = flag_wait_ge_warp(flag_last, jt + 1);
+                bt_tile_transfer<XP / 32>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x,
+                                          bt_tile_mask(jt, ntiles, t_y), lane);
+            }
         } else if (warp < w_act) {
             // ============================== DP warps ==============================
             // Nothing in the tile loop may branch (or predicate) on a loop-invariant condition: ptxas hoists
@@ -535,7 +595,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             const uint32_t hout_base = ((has_consumer || line_out) && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * NT);
             const uint32_t hout_step = ((has_consumer || line_out) && lane == 31) ? NT * 4u : 0u;
             const int *flag_in = (w > 0) ? hprog + (w - 1) : hprog + W;           // hprog[W] is pre-satisfied
-            int *flag_out = has_consumer ? hprog + w : hprog + W + 1;             // hprog[W+1] is a dump
+            int *flag_out = hprog + w;                                            // also read by the backtrack helper
             const float *gl_in = (MULTIPASS && pass > 0) ? gline_b + ((pass - 1) & 1) * P.line_pitch : nullptr;
             float *gl_out = line_out ? gline_b + (pass & 1) * P.line_pitch : nullptr;
 
@@ -578,7 +638,14 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
                 else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
 
-                // ---- direction words of this tile, bit-reversed for the token walk (bit 31-k <-> frame k) ----
+                // ---- direction words of this tile, walk-ready: forced move of the diagonal cell (index == y,
+                // core.pyx:34) OR-ed in, token 0 (never moves) cleared, bit-reversed (bit 31-k <-> frame k) ----
+                if (diag) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (((x0 + r) >> 5) == j) acc[r] |= 1u << ((x0 + r) & 31);
+                }
+                if (x0 == 0) acc[0] = 0u;
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = __brev(acc[r]);
                 if (SMEM_BITS) store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, acc);
@@ -609,28 +676,61 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     if (dbg && tid == 0) dbg[4] = clock64();                               // all DP warps done
 
     // ================================ backtrack ================================
-    const int rows_pitch = SMEM_BITS ? XP : P.gbits_rows_pitch;
-    uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
-    const int rows_cp = min(rows_pitch, ((t_x + 3) >> 2) << 2);
-    const int chunk_tiles = SMEM_BITS ? ntiles : max(1, (int)((S::ring_bytes(NS) / 4) / rows_cp));
-    // per-token / per-tile scratch of the walk: the idle ring when the bits have their own shared-memory
-    // region (4*(Tx + tiles) bytes always fit below two value tiles there), else global (start table, carry line)
+    // per-token / per-tile scratch: the idle ring when the bits have their own shared-memory region
+    // (4*(Tx + tiles) bytes always fit below two value tiles there), else global (start table, carry line)
     int *tok = SMEM_BITS ? reinterpret_cast<int *>(ring) : start_b;
     int *xin = SMEM_BITS ? tok + XP : reinterpret_cast<int *>(gline_b);
-    for (int jj = tid; jj < ntiles; jj += nthreads) xin[jj] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        bt_state[0] = t_x - 1;                                           // token
-        bt_state[1] = ntiles - 1;                                        // tile
-        bt_state[2] = (int)(0u - (1u << (31 - ((t_y - 1) & 31))));       // frames <= t_y-1 of the last tile
-        bt_state[3] = 0;
-        xin[ntiles - 1] = t_x - 1;
-    }
-    __syncthreads();
-    int jhi = ntiles;
-    while (true) {
-        const int jlo = max(0, jhi - chunk_tiles);
-        if (!SMEM_BITS) {
+    if constexpr (SMEM_BITS) {
+        if (tid == 0) {                                                       // one dependent load per tile
+            int x = t_x - 1;
+            for (int jt = ntiles - 1; jt >= 0; --jt) {
+                xin[jt] = x;
+                int n = nj_s[(size_t)jt * XP + x];
+                if (n == kBtUnknown) {                                        // entry the helper gave up on
+                    const uint32_t *bj = bits_s + (size_t)jt * XP;
+                    uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
+                    n = 0;
+                    for (int r = x; r > 0; --r) {
+                        const uint32_t m = bj[r] & mk;
+                        if (m == 0u) break;
+                        ++n;
+                        mk = m ^ (0u - m);
+                    }
+                }
+                x -= n;
+            }
+            tok[0] = 0;
+        }
+        __syncthreads();
+        for (int jt = tid; jt < ntiles; jt += nthreads) {                     // one thread per tile: start frames
+            const uint32_t *bj = bits_s + (size_t)jt * XP;
+            const int lo = jt > 0 ? xin[jt - 1] : 0;
+            uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
+            for (int x = xin[jt]; x > lo; --x) {
+                const uint32_t m = bj[x] & mk;
+                tok[x] = (jt << 5) + 32 - __ffs((int)m);
+                mk = m ^ (0u - m);
+            }
+        }
+        __syncthreads();
+    } else {
+        const int rows_pitch = P.gbits_rows_pitch;
+        uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
+        const int rows_cp = min(rows_pitch, ((t_x + 3) >> 2) << 2);
+        const int chunk_tiles = max(1, (int)((S::ring_bytes(NS) / 4) / rows_cp));
+        for (int jj = tid; jj < ntiles; jj += nthreads) xin[jj] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            bt_state[0] = t_x - 1;                                           // token
+            bt_state[1] = ntiles - 1;                                        // tile
+            bt_state[2] = (int)bt_tile_mask(ntiles - 1, ntiles, t_y);        // frames <= t_y-1 of the last tile
+            bt_state[3] = 0;
+            xin[ntiles - 1] = t_x - 1;
+        }
+        __syncthreads();
+        int jhi = ntiles;
+        while (true) {
+            const int jlo = max(0, jhi - chunk_tiles);
             const int n4 = rows_cp >> 2;
             for (int i = tid; i < (jhi - jlo) * n4; i += nthreads) {
                 const int jj = i / n4, cc = i - jj * n4;
@@ -638,26 +738,25 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                     reinterpret_cast<const uint4 *>(gbits_b + (size_t)(jlo + jj) * rows_pitch)[cc];
             }
             __syncthreads();
+            if (tid == 0) {
+                int x = bt_state[0], j = bt_state[1];
+                uint32_t mask = (uint32_t)bt_state[2];
+                const bool done = backtrack_walk(stage_bits, rows_cp, jlo, x, j, mask, reinterpret_cast<uint32_t *>(tok), xin);
+                bt_state[0] = x; bt_state[1] = j; bt_state[2] = (int)mask; bt_state[3] = done ? 1 : 0;
+            }
+            __syncthreads();
+            if (bt_state[3]) break;
+            jhi = jlo;
+            __syncthreads();
         }
-        if (tid == 0) {
-            int x = bt_state[0], j = bt_state[1];
-            uint32_t mask = (uint32_t)bt_state[2];
-            const bool done = backtrack_walk(SMEM_BITS ? bits_s : stage_bits, SMEM_BITS ? XP : rows_cp, jlo, x, j, mask,
-                                             reinterpret_cast<uint32_t *>(tok), xin);
-            bt_state[0] = x; bt_state[1] = j; bt_state[2] = (int)mask; bt_state[3] = done ? 1 : 0;
+        // start frames, one thread per tile: tile j holds the starts of tokens (xin[j-1], xin[j]]
+        for (int jj = tid; jj < ntiles; jj += nthreads) {
+            const int hi = xin[jj], lo = jj > 0 ? xin[jj - 1] : 0;
+            for (int x = hi; x > lo; --x) tok[x] = (jj << 5) + 32 - __ffs(tok[x]);
         }
-        __syncthreads();
-        if (bt_state[3]) break;
-        jhi = jlo;
+        if (tid == 0) tok[0] = 0;
         __syncthreads();
     }
-    // start frames, one thread per tile: tile j holds the starts of tokens (xin[j-1], xin[j]]
-    for (int jj = tid; jj < ntiles; jj += nthreads) {
-        const int hi = xin[jj], lo = jj > 0 ? xin[jj - 1] : 0;
-        for (int x = hi; x > lo; --x) tok[x] = (jj << 5) + 32 - __ffs(tok[x]);
-    }
-    if (tid == 0) tok[0] = 0;
-    __syncthreads();
 
     if (dbg && tid == 0) dbg[5] = clock64();                               // backtrack done
     // ================================= outputs =================================

@@ -36,7 +36,7 @@ int launch_inst(const MasParams &P, const CUtensorMap &tmap, size_t smem, cudaSt
         }
         return MAS_B200_OK;
     }
-    kern<<<P.B, (W + 1) * 32, smem, stream>>>(P, tmap);
+    kern<<<P.B, (W + 1 + (SB ? 1 : 0)) * 32, smem, stream>>>(P, tmap);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }
