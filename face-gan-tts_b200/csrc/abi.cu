@@ -25,6 +25,8 @@ Opt g_opts[] = {
     {"mas_fused_path_write", {-1}},  // -1 auto, 0 separate expand kernel, 1 in-kernel
     {"mas_debug_ptr_lo", {0}},       // diagnostics only: clock64 phase stamps buffer (device pointer halves)
     {"mas_debug_ptr_hi", {0}},
+    {"lp_debug_ptr_lo", {0}},        // diagnostics only: [ctas][4] globaltimer stamps of the tcgen05 log-prior kernel
+    {"lp_debug_ptr_hi", {0}},
     {"lp_impl", {0}},                // default log-prior implementation for MAS_B200_LP_AUTO
     {"fused_impl", {0}},             // 0 auto, 1 force unfused pipeline, 2 force fused kernel
 };

@@ -28,6 +28,7 @@ struct LpTcParams {
     int chunks;          // CTAs per utterance
     int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
     PathJob job;         // optional: expand the dense path of utterance b once the MAS kernel reports it done
+    long long *dbg;      // diagnostics: [ctas][4] globaltimer stamps
     int *flags;          // optional [B][flag_pitch]: set to 1 when a 64-frame group of an utterance is in memory
     int flag_pitch;
 };
@@ -51,6 +52,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     if (ng <= 0) return;
     const int MT = (P.Tx + 127) >> 7;                                         // M-tiles of 128 text positions
 
+    long long *dbg = P.dbg ? P.dbg + ((size_t)b * gridDim.x + blockIdx.x) * 4 : nullptr;
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[0] = t; }
     if (tid == 0) { S.init_barriers(); mbar_fence_init(); }
     if (warp == 0) { __syncwarp(); tmem_alloc(S.tmem_slot, kLpTmemCols); tmem_relinquish(); }
     tc_fence_before();
@@ -106,29 +109,47 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kLpTmemCols);
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[1] = t; }
 
-    // ---- dense path of this utterance: the CTAs that computed its log-prior share the rows once the MAS
-    // kernel (running on other SMs) has published the [start,dur] table.  A pure streaming write.
+    // ---- dense path: every warp of this kernel owns the rows {gw, gw + total_warps, ...} of EVERY utterance and
+    // streams them out as soon as the MAS kernel (running on other SMs) publishes that utterance's [start,dur]
+    // table -- the last utterance to finish is written by all SMs of the kernel at once.  32 done-flags are
+    // polled per load (one lane each), so a sweep costs one L2 round trip.
     if (P.job.path != nullptr) {
-        if (tid == 0) {
+        const int total_warps = (int)(gridDim.x * gridDim.y) * (kTcThreads / 32);
+        const int gw = (int)(blockIdx.y * gridDim.x + blockIdx.x) * (kTcThreads / 32) + warp;
+        if (gw < P.Tx) {
+            uint32_t proc[4] = {0u, 0u, 0u, 0u};
+            int remaining = P.B;
             const long long c0 = clock64();
-            while (gflag_acquire(P.job.done + b) == 0) {
-                __nanosleep(200);
-                if (clock64() - c0 > (1ll << 33)) __trap();
+            while (remaining > 0) {
+                for (int base = 0; base < P.B; base += 32) {
+                    const int u = base + lane;
+                    const int f = (u < P.B) ? gflag_acquire(P.job.done + u) : 0;
+                    uint32_t ready = __ballot_sync(kFullMask, f != 0) & ~proc[base >> 5];
+                    proc[base >> 5] |= ready;
+                    while (ready != 0u) {
+                        const int ub = base + __ffs((int)ready) - 1;
+                        ready &= ready - 1;
+                        --remaining;
+                        for (int x = gw; x < P.Tx; x += total_warps) {
+                            const size_t row = (size_t)ub * P.Tx + x;
+                            if (P.job.path_dtype == MAS_B200_PATH_F32)
+                                write_path_row<float>(reinterpret_cast<float *>(P.job.path) + row * P.Ty, P.job.start[row],
+                                                      P.job.dur[row], P.Ty, lane);
+                            else
+                                write_path_row<int>(reinterpret_cast<int *>(P.job.path) + row * P.Ty, P.job.start[row],
+                                                    P.job.dur[row], P.Ty, lane);
+                        }
+                    }
+                }
+                if (remaining > 0) {
+                    __nanosleep(256);
+                    if (clock64() - c0 > (1ll << 33)) __trap();
+                }
             }
         }
-        __syncthreads();
-        const int nchunk = (int)gridDim.x, c = (int)blockIdx.x;
-        const int rows_per = (P.Tx + nchunk - 1) / nchunk;
-        const int x0 = c * rows_per, rows = min(rows_per, P.Tx - x0);
-        if (rows > 0) {
-            const int *sb = P.job.start + (size_t)b * P.Tx + x0, *db = P.job.dur + (size_t)b * P.Tx + x0;
-            const size_t off = ((size_t)b * P.Tx + x0) * P.Ty;
-            if (P.job.path_dtype == MAS_B200_PATH_F32)
-                write_path_rows<float>(reinterpret_cast<float *>(P.job.path) + off, sb, db, rows, P.Ty, tid, kTcThreads);
-            else
-                write_path_rows<int>(reinterpret_cast<int *>(P.job.path) + off, sb, db, rows, P.Ty, tid, kTcThreads);
-        }
+        if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[2] = t; }
     }
 }
 
@@ -185,6 +206,10 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     P.mu = mu_x; P.out = out; P.B = B; P.Tx = Tx; P.Ty = Ty; P.cst = log_prior_const(F);
     P.ngroups = (Ty + kLpGroup - 1) / kLpGroup;
     P.flags = flags; P.flag_pitch = flag_pitch;
+    {
+        const unsigned lo = (unsigned)option("lp_debug_ptr_lo"), hi = (unsigned)option("lp_debug_ptr_hi");
+        P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
+    }
     if (job) P.job = *job;
     const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;
     int chunks = cta_budget / B;                                // one wave of CTAs (one CTA per SM: TMEM + smem)

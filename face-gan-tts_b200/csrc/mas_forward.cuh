@@ -270,35 +270,46 @@ template <typename T> __device__ __forceinline__ uint32_t one_bits();
 template <> __device__ __forceinline__ uint32_t one_bits<float>() { return 0x3f800000u; }
 template <> __device__ __forceinline__ uint32_t one_bits<int>() { return 1u; }
 
-// Dense path rows of one utterance from the [start, dur] table (4-byte elements).
+// One dense path row [Ty] from its (start, duration) entry, written by one warp: zero the row with plain
+// 16-byte streaming stores, then patch the few chunks that overlap [s, e).  A chunk is always written by the
+// same lane (c & 31), so the two stores to it are ordered.
 template <typename T>
-__device__ __forceinline__ void write_path_rows(T *path_b, const int *start_b, const int *dur_b, int Tx, int Ty,
-                                                int tid, int nthreads) {
+__device__ __forceinline__ void write_path_row(T *row_ptr, int s, int d, int Ty, int lane) {
     const uint32_t one = one_bits<T>();
-    uint32_t *out = reinterpret_cast<uint32_t *>(path_b);
-    if ((Ty & 3) == 0 && (reinterpret_cast<uintptr_t>(path_b) & 15) == 0) {
-        const int Ty4 = Ty >> 2;
-        const int total = Tx * Ty4;
-        for (int i = tid; i < total; i += nthreads) {
-            const int x = i / Ty4;
-            const int y = (i - x * Ty4) << 2;
-            const int s = start_b[x];
-            const int e = s + dur_b[x];                  // exclusive; dur == 0 -> empty
+    const int e = s + d;                                 // exclusive; d == 0 -> empty
+    uint32_t *out = reinterpret_cast<uint32_t *>(row_ptr);
+    if ((Ty & 3) == 0 && (reinterpret_cast<uintptr_t>(row_ptr) & 15) == 0) {
+        uint4 *row = reinterpret_cast<uint4 *>(out);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = lane; c < (Ty >> 2); c += 32) __stcs(row + c, z);
+        for (int c = (s >> 2) + ((lane - (s >> 2)) & 31); c <= ((e - 1) >> 2) && e > s; c += 32) {
+            const int y = c << 2;
             uint4 o;
             o.x = (y + 0 >= s && y + 0 < e) ? one : 0u;
             o.y = (y + 1 >= s && y + 1 < e) ? one : 0u;
             o.z = (y + 2 >= s && y + 2 < e) ? one : 0u;
             o.w = (y + 3 >= s && y + 3 < e) ? one : 0u;
-            __stcs(reinterpret_cast<uint4 *>(out) + i, o);
+            __stcs(row + c, o);
         }
     } else {
-        const long long total = (long long)Tx * Ty;
-        for (long long i = tid; i < total; i += nthreads) {
-            const int x = (int)(i / Ty);
-            const int y = (int)(i - (long long)x * Ty);
-            const int s = start_b[x];
-            const int e = s + dur_b[x];
-            out[i] = (y >= s && y < e) ? one : 0u;
+        for (int y = lane; y < Ty; y += 32) out[y] = (y >= s && y < e) ? one : 0u;
+    }
+}
+
+// Dense path rows from the [start, dur] table (4-byte elements): a pure streaming write, one warp per row.
+// Lane k fetches the table entry of the warp's k-th row up front (one round trip to L2 per 32 rows).
+template <typename T>
+__device__ __forceinline__ void write_path_rows(T *path_b, const int *start_b, const int *dur_b, int Tx, int Ty,
+                                                int tid, int nthreads) {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    for (int k0 = 0; warp + k0 * nwarps < Tx; k0 += 32) {
+        const int xl = warp + (k0 + lane) * nwarps;
+        int s_l = 0, d_l = 0;
+        if (xl < Tx) { s_l = start_b[xl]; d_l = dur_b[xl]; }
+        for (int k = 0; k < 32; ++k) {
+            const int x = warp + (k0 + k) * nwarps;
+            if (x >= Tx) break;
+            write_path_row<T>(path_b + (size_t)x * Ty, __shfl_sync(kFullMask, s_l, k), __shfl_sync(kFullMask, d_l, k), Ty, lane);
         }
     }
 }
@@ -331,34 +342,53 @@ __device__ __forceinline__ uint32_t bt_tile_mask(int j, int ntiles, int t_y) {
 
 // The DP stores the words of the shared-memory path "walk ready": the forced move of the diagonal cell
 // (core.pyx:34, index == y) is OR-ed in and the word of token 0 (which never moves) is zero.
-// Entry tokens far from the path complete a token per frame (their words are all ones), so the chain is cut
-// after kBtSteps tokens: an entry that is still moving then gets kBtUnknown and, in the unlikely case the
-// real path enters the tile there, the tile is re-walked serially after the DP.
-constexpr int kBtSteps = 16;
-constexpr int kBtUnknown = 255;
-
-template <int G>
-__device__ __forceinline__ void bt_tile_transfer(const uint32_t *bits_j, unsigned char *nj_j, int j, int t_x,
-                                                 uint32_t mask0, int lane) {
-    uint32_t mk[G];
-    int n[G];
-    const int xmax = min(t_x - 1, 32 * j + 31);               // entry tokens that can be on the path (x <= y)
+// Entry tokens far from the path complete a token per frame (their words are all ones), and real paths run
+// along such stretches too, so every chain is followed to its end (at most 32 tokens per tile).  The row
+// groups of a tile are split between the helper warp (groups [0, kGH)) and the TMA producer warp (the rest,
+// in the slack the NS-deep ring gives it); what the producer did not get to is shared by all warps after the DP.
+template <int NG>
+__device__ __forceinline__ void bt_transfer_groups(const uint32_t *p, unsigned char *nj, int xbase, int xmax, uint32_t mask0,
+                                                   int lane) {
+    uint32_t mk[NG];
+    int n[NG];
 #pragma unroll
-    for (int g = 0; g < G; ++g) { mk[g] = (32 * g + lane <= xmax) ? mask0 : 0u; n[g] = 0; }
+    for (int g = 0; g < NG; ++g) { mk[g] = (xbase + 32 * g + lane <= xmax) ? mask0 : 0u; n[g] = 0; }
     // token 0's word is zero, so a chain that reaches it stops there (sticky zero): indices below row 0 are
     // only ever read with mk == 0 and need no bounds check (they stay inside the CTA's shared memory)
-    const uint32_t *p = bits_j + lane;
-#pragma unroll 4
-    for (int k = 0; k < kBtSteps; ++k) {
+    for (int k0 = 0; k0 < 32; k0 += 8) {
+        uint32_t alive = 0u;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const uint32_t m = p[32 * g - k] & mk[g];
-            if (m != 0u) n[g] = k + 1;
-            mk[g] = m ^ (0u - m);
+        for (int kk = 0; kk < 8; ++kk) {
+            const int k = k0 + kk;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t m = p[32 * g - k] & mk[g];
+                if (m != 0u) n[g] = k + 1;
+                mk[g] = m ^ (0u - m);
+                if (kk == 7) alive |= mk[g];
+            }
         }
+        if (!__any_sync(kFullMask, alive != 0u)) break;
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) nj_j[32 * g + lane] = (unsigned char)(mk[g] != 0u ? kBtUnknown : n[g]);
+    for (int g = 0; g < NG; ++g) nj[32 * g + lane] = (unsigned char)n[g];
+}
+
+// groups [G0, G1) of tile j, four at a time, only as many as hold tokens that can be entered (x <= y, x < t_x)
+template <int G0, int G1>
+__device__ __forceinline__ void bt_tile_transfer(const uint32_t *bits_j, unsigned char *nj_j, int j, int t_x,
+                                                 uint32_t mask0, int lane) {
+    const int xmax = min(t_x - 1, 32 * j + 31);
+#pragma unroll
+    for (int gq = G0; gq < G1; gq += 4) {
+        const int ng = min(min(4, G1 - gq), (xmax >> 5) + 1 - gq);  // warp-uniform
+        const uint32_t *p = bits_j + 32 * gq + lane;
+        unsigned char *nj = nj_j + 32 * gq;
+        if (ng >= 4) bt_transfer_groups<4>(p, nj, 32 * gq, xmax, mask0, lane);
+        else if (ng == 3) bt_transfer_groups<3>(p, nj, 32 * gq, xmax, mask0, lane);
+        else if (ng == 2) bt_transfer_groups<2>(p, nj, 32 * gq, xmax, mask0, lane);
+        else if (ng == 1) bt_transfer_groups<1>(p, nj, 32 * gq, xmax, mask0, lane);
+    }
 }
 
 // Token walk over direction words wb[(j - jlo) * wpitch + x] (tile j, text position x), the backtrack
@@ -431,6 +461,8 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     constexpr int NT = kTileFrames;
     constexpr int kTileFloats = S::kTileFloats;
     constexpr int nthreads = (W + 1 + (SMEM_BITS ? 1 : 0)) * 32;
+    constexpr int kG = XP / 32;                    // row groups of a tile (backtrack transfer tables)
+    constexpr int kGH = (kG + 1) / 2;              // groups [0, kGH) -> helper warp, [kGH, kG) -> producer warp
 
     const int NS = P.ring_stages;
     const int HS = S::halo_slots(NS);
@@ -472,7 +504,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XP);   // [ntiles][XP] transfer table
     const int npass = (t_x + XP - 1) / XP;
     long long *dbg = P.dbg ? P.dbg + (size_t)b * 16 : nullptr;
-    if (dbg && tid == 0) dbg[0] = clock64();
+    if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
     uint32_t *gbits_b = SMEM_BITS ? nullptr : P.gbits + (size_t)b * P.gbits_stride_b;
     float *gline_b = P.gline ? P.gline + (size_t)b * 2 * P.line_pitch : nullptr;
     const float *vb = P.value + (size_t)b * P.stride_b;
@@ -508,15 +540,24 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             int stage = 0;
             uint32_t phase = 0;
             long long gate_spins = 0;
+            int gate_known = 0;                                // groups [0, gate_known) are known to be in memory
+            int jt_next = 0;                                   // next tile whose transfer table (upper groups) is owed
+            const int *flag_last = hprog + (w_act - 1);
             for (int j = 0; j < ntiles; ++j) {
                 mbar_wait(&ring_empty[stage], phase ^ 1);
                 float *dst = ring + (size_t)stage * kTileFloats;
                 const int t0 = j * NT;
-                if (P.gate != nullptr && (j & 1) == 0) {
-                    // the value matrix is being produced by another kernel: wait for this 64-frame group
-                    const int *gf = P.gate + (size_t)b * P.gate_pitch + (j >> 1);
+                if (P.gate != nullptr && (j >> 1) >= gate_known) {
+                    // the value matrix is being produced by another kernel: wait for this 64-frame group.  Lane l
+                    // looks at group (j/2 + l), so one L2 round trip also learns how far ahead the producer is.
+                    const int g0 = j >> 1;
+                    const int *gf = P.gate + (size_t)b * P.gate_pitch;
                     const long long c0 = clock64();
-                    while (gflag_acquire(gf) == 0) {
+                    while (true) {
+                        const int g = g0 + lane;
+                        const int f = (g < P.gate_pitch) ? gflag_acquire(gf + g) : 0;
+                        const unsigned ready = __ballot_sync(kFullMask, f != 0);
+                        if (ready & 1u) { gate_known = g0 + __ffs((int)~ready) - 1; break; }    // consecutive ready groups
                         __nanosleep(64);
                         ++gate_spins;
                         if (clock64() - c0 > (1ll << 31)) __trap();
@@ -560,8 +601,20 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                     if (lane == 0) mbar_arrive(&ring_full[stage]);
                 }
                 if (++stage == NS) { stage = 0; phase ^= 1; }
+                if (SMEM_BITS && kGH < kG && j + 1 < ntiles) {
+                    // while the ring is full (the DP is not waiting for this warp) use the slack for the transfer
+                    // tables this warp owes; tiles the DP warps have all released are final
+                    while (jt_next < ntiles && !mbar_test_warp(&ring_empty[stage], phase ^ 1)) {
+                        const int done_tiles = __shfl_sync(kFullMask, flag_acquire(flag_last), 0);
+                        if (done_tiles <= jt_next) break;
+                        bt_tile_transfer<kGH, kG>(bits_s + (size_t)jt_next * XP, nj_s + (size_t)jt_next * XP, jt_next, t_x,
+                                                  bt_tile_mask(jt_next, ntiles, t_y), lane);
+                        ++jt_next;
+                    }
+                }
             }
-            if (dbg && lane == 0) dbg[10] = gate_spins;
+            if (lane == 0) bt_state[3] = jt_next;      // the rest is shared by all warps once the DP is done
+            if (dbg && lane == 0) { dbg[10] = gate_spins; dbg[11] = jt_next; dbg[15] = clock64(); }
         } else if (SMEM_BITS && warp == W + 1) {
             // ========================== backtrack helper warp ==========================
             // trails the LAST active DP warp (its progress flag implies every earlier warp is past the tile too)
@@ -569,9 +622,10 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             int known = 0;
             for (int jt = 0; jt < ntiles; ++jt) {
                 if (known < jt + 1) known = flag_wait_ge_warp(flag_last, jt + 1);
-                bt_tile_transfer<XP / 32>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x,
-                                          bt_tile_mask(jt, ntiles, t_y), lane);
+                bt_tile_transfer<0, kGH>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x,
+                                         bt_tile_mask(jt, ntiles, t_y), lane);
             }
+            if (dbg && lane == 0) dbg[14] = clock64();
         } else if (warp < w_act) {
             // ============================== DP warps ==============================
             // Nothing in the tile loop may branch (or predicate) on a loop-invariant condition: ptxas hoists
@@ -681,22 +735,19 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     int *tok = SMEM_BITS ? reinterpret_cast<int *>(ring) : start_b;
     int *xin = SMEM_BITS ? tok + XP : reinterpret_cast<int *>(gline_b);
     if constexpr (SMEM_BITS) {
+        if constexpr (kGH < kG) {
+            // transfer tables (upper row groups) the producer warp did not get to: one tile per warp
+            constexpr int nwarps = nthreads / 32;
+            for (int jt = bt_state[3] + warp; jt < ntiles; jt += nwarps)
+                bt_tile_transfer<kGH, kG>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x,
+                                          bt_tile_mask(jt, ntiles, t_y), lane);
+            __syncthreads();
+        }
         if (tid == 0) {                                                       // one dependent load per tile
             int x = t_x - 1;
             for (int jt = ntiles - 1; jt >= 0; --jt) {
                 xin[jt] = x;
-                int n = nj_s[(size_t)jt * XP + x];
-                if (n == kBtUnknown) {                                        // entry the helper gave up on
-                    const uint32_t *bj = bits_s + (size_t)jt * XP;
-                    uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
-                    n = 0;
-                    for (int r = x; r > 0; --r) {
-                        const uint32_t m = bj[r] & mk;
-                        if (m == 0u) break;
-                        ++n;
-                        mk = m ^ (0u - m);
-                    }
-                }
+                const int n = nj_s[(size_t)jt * XP + x];
                 x -= n;
             }
             tok[0] = 0;
@@ -785,7 +836,10 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (tid == 0) gflag_release(P.done + b, 1);
     }
     write_path_any(P, b, start_b, dur_b, tid, nthreads);
-    if (dbg && tid == 0) { dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y; }
+    if (dbg && tid == 0) {
+        dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y;
+        long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[13] = t;
+    }
 }
 
 }  // namespace masb200

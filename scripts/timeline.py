@@ -1,0 +1,54 @@
+"""Diagnostics: globaltimer timeline of one overlapped log-prior || MAS step (ns relative to the first stamp)."""
+import os, sys
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "face-gan-tts_b200"))
+import torch
+from face_gan_tts_b200 import _lib, synthetic
+B, F, TX, TY = 32, 80, 190, 1000
+L = _lib.lib(); dev = torch.device("cuda", 0)
+mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, TX, TY, seed=1234)
+d = dict(mu=mu_x.to(dev), y=y.to(dev), tx=t_x.to(dev), ty=t_y.to(dev), dur=torch.empty((B, TX), dtype=torch.int32, device=dev),
+         ft=torch.empty((B, TY), dtype=torch.int32, device=dev), status=torch.empty((B,), dtype=torch.int32, device=dev),
+         path=torch.empty((B, TX, TY), device=dev))
+ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, TX, TY)
+ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+sp = torch.cuda.current_stream(dev).cuda_stream
+def call():
+    rc = L.mas_b200_log_prior_maximum_path(d["mu"].data_ptr(), d["y"].data_ptr(), d["tx"].data_ptr(), d["ty"].data_ptr(), B, F, TX, TY, -1e9,
+                                           d["path"].data_ptr(), _lib.PATH_F32, d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes, _lib.LP_AUTO, sp)
+    assert rc == 0, rc
+for _ in range(5): call()
+torch.cuda.synchronize()
+dm = torch.zeros((B, 16), dtype=torch.int64, device=dev); dl = torch.zeros((B * 8, 4), dtype=torch.int64, device=dev)
+def setp(name, t):
+    p = t.data_ptr(); lo, hi = p & 0xFFFFFFFF, p >> 32
+    _lib.set_option(name + "_lo", lo - (1 << 32) if lo >= (1 << 31) else lo); _lib.set_option(name + "_hi", hi)
+setp("mas_debug_ptr", dm); setp("lp_debug_ptr", dl)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); call(); e1.record(); torch.cuda.synchronize()
+for n in ("mas_debug_ptr", "lp_debug_ptr"):
+    _lib.set_option(n + "_lo", 0); _lib.set_option(n + "_hi", 0)
+dm, dl = dm.cpu(), dl.cpu()
+lp = dl[dl[:, 0] != 0]
+t0 = min(int(lp[:, 0].min()), int(dm[:, 12].min()))
+print(f"event time {e0.elapsed_time(e1)*1e3:.1f} us; {lp.shape[0]} LP CTAs")
+print("LP  start  min/max us:", (int(lp[:, 0].min()) - t0) / 1e3, (int(lp[:, 0].max()) - t0) / 1e3)
+print("LP  gemm end min/max :", (int(lp[:, 1].min()) - t0) / 1e3, (int(lp[:, 1].max()) - t0) / 1e3)
+pass
+print("LP  path end min/max :", (int(lp[:, 2].min()) - t0) / 1e3, (int(lp[:, 2].max()) - t0) / 1e3)
+print("MAS start  min/max   :", (int(dm[:, 12].min()) - t0) / 1e3, (int(dm[:, 12].max()) - t0) / 1e3)
+print("MAS end    min/max   :", (int(dm[:, 13].min()) - t0) / 1e3, (int(dm[:, 13].max()) - t0) / 1e3)
+print("MAS gate spins       :", dm[:8, 10].tolist())
+i = int(torch.argmax(dm[:, 13]))
+s_ = dm[i].tolist()
+print(f"slowest MAS CTA b={i} t_x={s_[7] >> 32} t_y={s_[7] & 0xffffffff}: dp_done {s_[2]-s_[0]} all_warps {s_[4]-s_[0]} backtrack {s_[5]-s_[4]} tail {s_[6]-s_[5]} total {s_[6]-s_[0]} cycles; spins {s_[10]}")
+print(f"  helper done {s_[14]-s_[0]}  producer done {s_[15]-s_[0]}")
+# same batch through the serial pipeline (MAS ungated)
+_lib.set_option("fused_impl", 1)
+for _ in range(3): call()
+dm2 = torch.zeros((B, 16), dtype=torch.int64, device=dev)
+setp("mas_debug_ptr", dm2); call(); torch.cuda.synchronize()
+_lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0); _lib.set_option("fused_impl", 0)
+s2 = dm2.cpu()[i].tolist()
+print(f"ungated    b={i}: dp_done {s2[2]-s2[0]} all_warps {s2[4]-s2[0]} backtrack {s2[5]-s2[4]} tail {s2[6]-s2[5]} total {s2[6]-s2[0]}; helper done {s2[14]-s2[0]} producer done {s2[15]-s2[0]}")
+
