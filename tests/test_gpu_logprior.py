@@ -21,7 +21,7 @@ def rel_err(a, b):
     return ((a.double() - b.double()).abs() / b.double().abs().clamp_min(1e-30)).max().item()
 
 
-IMPLS = ["ffma", "auto"]
+IMPLS = ["ffma", "auto"]       # "auto" = tcgen05/TMEM kernel where it covers the shape (F in {64,80,96}, Tx <= 256), else FFMA
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -126,3 +126,60 @@ def test_compute_loss_call_site_quantities():
     # :233-234 prior loss
     prior = torch.sum(0.5 * ((y_d - mu_y) ** 2 + math.log(2 * math.pi)) * y_mask) / (torch.sum(y_mask) * F)
     assert torch.isfinite(prior)
+
+
+def test_tcgen05_kernel_is_the_one_running_and_matches_ffma():
+    """impl="tcgen05" must not silently fall back: supported shapes run the tensor-core kernel (3xTF32, fp32-class
+    accuracy), unsupported ones raise.  Against the FFMA kernel the two agree far inside the 1e-4 bar."""
+    from face_gan_tts_b200 import _lib
+
+    for (B, F, Tx, Ty) in [(3, 80, 190, 1000), (2, 64, 129, 136), (2, 96, 256, 420), (5, 80, 37, 68)]:
+        mu_x, y, _, _ = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=7, tx_lo=max(1, Tx // 3), ty_lo=max(Tx // 3, Ty // 3))
+        mu_d, y_d = mu_x.to(DEV), y.to(DEV)
+        tc = fgt.log_prior(mu_d, y_d, impl="tcgen05")
+        ff = fgt.log_prior(mu_d, y_d, impl="ffma")
+        ref64 = oracle.log_prior_direct(mu_d, y_d)
+        assert rel_err(tc, ref64) < 2e-6 and rel_err(tc, ff) < 2e-6
+    mu_x, y, _, _ = synthetic.lrs2_batch(B=2, F=128, Tx=190, Ty=1000, seed=7)
+    with pytest.raises(_lib.MasB200Error):
+        fgt.log_prior(mu_x.to(DEV), y.to(DEV), impl="tcgen05")          # F = 128: 4F + 128 TMEM columns do not fit
+
+
+@pytest.mark.parametrize("B", [3, 32, 80])
+def test_overlapped_pipeline_equals_serial_pipeline(B):
+    """mas_b200_log_prior_maximum_path: the overlapped log-prior || MAS pipeline (device flags, dense path written
+    by the log-prior CTAs; taken for 2*B <= SM count) and the serial one (fused_impl=1; also what B=80 gets) must
+    produce identical outputs -- same kernels, same arithmetic, only the scheduling differs."""
+    from face_gan_tts_b200 import _lib
+
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=80, Tx=190, Ty=1000, seed=11)
+    mu_d, y_d = mu_x.to(DEV), y.to(DEV)
+    outs = []
+    for mode in (0, 1):
+        prev = _lib.set_option("fused_impl", mode)
+        try:
+            r = None
+            for _ in range(4):                      # back to back, no host sync in between: flag reuse across calls
+                r = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, path_dtype=torch.float32)
+            torch.cuda.synchronize()
+            outs.append(r)
+        finally:
+            _lib.set_option("fused_impl", prev)
+    a, b = outs
+    assert torch.equal(a.path, b.path) and torch.equal(a.durations, b.durations)
+    assert torch.equal(a.frame_token, b.frame_token) and torch.equal(a.status, b.status)
+    assert torch.equal(a.path.sum(-1).int(), a.durations)
+    assert int(a.status.abs().sum()) == 0
+
+
+def test_overlapped_pipeline_rejects_bad_items_without_hanging():
+    """t_x > t_y is undefined in the reference (core.pyx:34); here the item is rejected, its outputs are zero, and the
+    producer/consumer flag protocol of the overlapped pipeline still terminates."""
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=4, F=80, Tx=61, Ty=200, seed=5, tx_lo=21, ty_lo=90)
+    t_x = t_x.clone(); t_y = t_y.clone()
+    t_x[1] = 61; t_y[1] = 40                       # t_x > t_y
+    res = fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, path_dtype=torch.int32)
+    torch.cuda.synchronize()
+    assert res.status.tolist() == [0, 1, 0, 0]
+    assert int(res.path[1].sum()) == 0 and int(res.durations[1].sum()) == 0
+    assert torch.equal(res.path[0].sum(-1).int(), res.durations[0])
