@@ -24,6 +24,7 @@ UNITS = [
     ("mas_forward_inst.cu", "mas_forward_r4", ["-DMASB200_INST_R=4"]),
     ("mas_forward_inst.cu", "mas_forward_r8", ["-DMASB200_INST_R=8"]),
     ("path_ops.cu", "path_ops", []),
+    ("loss_ops.cu", "loss_ops", []),
     ("log_prior_ffma.cu", "log_prior_ffma", []),
     ("log_prior_tc.cu", "log_prior_tc", []),
 ]

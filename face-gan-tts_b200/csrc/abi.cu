@@ -1,6 +1,7 @@
 // abi.cu -- the extern "C" surface of libmas_b200.so (include/mas_b200.h).
 #include <atomic>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -56,6 +57,20 @@ int device_info(DeviceInfo *out) {
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The overlapped pipeline runs two kernels that wait for each other's flags; a tool that serialises kernel
+// launches (ncu replay, compute-sanitizer) would starve it, so it is switched off when one is attached.
+// MAS_B200_PIPELINE=serial|overlap overrides the detection.
+static bool kernels_may_overlap() {
+    static const bool v = [] {
+        const char *e = std::getenv("MAS_B200_PIPELINE");
+        if (e && std::strcmp(e, "serial") == 0) return false;
+        if (e && std::strcmp(e, "overlap") == 0) return true;
+        return std::getenv("CUDA_INJECTION64_PATH") == nullptr && std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr &&
+               std::getenv("NV_SANITIZER_INJECTION_PORT_BASE") == nullptr;
+    }();
+    return v;
+}
 
 // One auxiliary stream + fork/join events per (host thread, device): the overlapped log-prior || MAS pipeline
 // forks from and joins back into the caller's stream, so the call stays stream-ordered for the caller.
@@ -175,7 +190,7 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
     const int fi = option("fused_impl");
     const bool tc_ok = (impl == MAS_B200_LP_AUTO || impl == MAS_B200_LP_TCGEN05) && option("lp_impl") != MAS_B200_LP_FFMA &&
                        log_prior_tc_supported(mu_x_dev, y_dev, value, B, F, Tx, Ty);
-    if (tc_ok && fi != 1 && 2 * B <= di.sm_count) {
+    if (tc_ok && fi != 1 && 2 * B <= di.sm_count && (fi == 2 || kernels_may_overlap())) {
         AuxStream *aux = aux_stream();
         if (aux != nullptr) {
             const int ngroups = (Ty + 63) / 64;
@@ -222,6 +237,52 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
 int mas_b200_generate_path(const int *durations_dev, const int *t_x_dev, const int *t_y_dev, int B, int Tx, int Ty,
                            void *path_dev, int path_dtype, void *stream) {
     return launch_generate_path(durations_dev, t_x_dev, t_y_dev, B, Tx, Ty, path_dev, path_dtype,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_sequence_mask(const int *lengths_dev, int B, int T, float *mask_dev, void *stream) {
+    return launch_sequence_mask(lengths_dev, B, T, mask_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_crop_frames(const float *y_dev, const int *frame_token_dev, const int *y_lengths_dev,
+                         const int *offsets_dev, int B, int F, int Ty, int out_size, float *y_cut_dev,
+                         int *frame_token_cut_dev, int *cut_lengths_dev, float *cut_mask_dev, void *stream) {
+    return launch_crop_frames(y_dev, frame_token_dev, y_lengths_dev, offsets_dev, B, F, Ty, out_size, y_cut_dev,
+                              frame_token_cut_dev, cut_lengths_dev, cut_mask_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_gather_mu_y(const float *mu_x_dev, const int *frame_token_dev, int B, int F, int Tx, int Ty,
+                         float *mu_y_dev, void *stream) {
+    return launch_gather_mu_y(mu_x_dev, frame_token_dev, B, F, Tx, Ty, mu_y_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_gather_mu_y_backward(const float *grad_mu_y_dev, const int *start_dev, const int *durations_dev,
+                                  const int *offsets_dev, const int *lengths_dev, int B, int F, int Tx, int Ty,
+                                  float *grad_mu_x_dev, void *stream) {
+    return launch_gather_mu_y_bwd(grad_mu_y_dev, start_dev, durations_dev, offsets_dev, lengths_dev, B, F, Tx, Ty,
+                                  grad_mu_x_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t mas_b200_prior_loss_workspace_bytes(int B, int F, int Ty) { return prior_loss_workspace_bytes(B, F, Ty); }
+
+int mas_b200_prior_loss(const float *y_dev, const float *mu_x_dev, const int *frame_token_dev,
+                        const int *y_lengths_dev, int B, int F, int Tx, int Ty, float *mu_y_dev, float *loss_dev,
+                        void *workspace_dev, size_t workspace_bytes, void *stream) {
+    return launch_prior_loss(y_dev, mu_x_dev, frame_token_dev, y_lengths_dev, B, F, Tx, Ty, mu_y_dev, loss_dev,
+                             workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_prior_loss_backward(const float *y_dev, const float *mu_x_dev, const int *start_dev,
+                                 const int *durations_dev, const int *offsets_dev, const int *y_lengths_dev,
+                                 const float *grad_loss_dev, int B, int F, int Tx, int Ty, float *grad_mu_x_dev,
+                                 void *stream) {
+    return launch_prior_loss_bwd(y_dev, mu_x_dev, start_dev, durations_dev, offsets_dev, y_lengths_dev, grad_loss_dev,
+                                 B, F, Tx, Ty, grad_mu_x_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_duration_loss(const float *logw_dev, const int *durations_dev, const int *x_lengths_dev, int B, int Tx,
+                           float *loss_dev, float *logw_target_dev, float *grad_logw_dev, void *stream) {
+    return launch_duration_loss(logw_dev, durations_dev, x_lengths_dev, B, Tx, loss_dev, logw_target_dev, grad_logw_dev,
                                 static_cast<cudaStream_t>(stream));
 }
 

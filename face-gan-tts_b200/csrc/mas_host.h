@@ -79,6 +79,24 @@ int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, 
 int launch_lengths_from_mask(const float *mask, int B, int Tx, int Ty, int *t_x, int *t_y, cudaStream_t stream);
 int launch_generate_path(const int *durations, const int *t_x, const int *t_y, int B, int Tx, int Ty, void *path,
                          int path_dtype, cudaStream_t stream);
+// loss_ops.cu: consumers of the alignment in index form
+int launch_sequence_mask(const int *lengths, int B, int T, float *mask, cudaStream_t stream);
+int launch_crop_frames(const float *y, const int *frame_token, const int *y_lengths, const int *offsets, int B, int F,
+                       int Ty, int out_size, float *y_cut, int *ft_cut, int *cut_lengths, float *cut_mask,
+                       cudaStream_t stream);
+size_t prior_loss_workspace_bytes(int B, int F, int Ty);
+int launch_gather_mu_y(const float *mu_x, const int *frame_token, int B, int F, int Tx, int Ty, float *mu_y,
+                       cudaStream_t stream);
+int launch_gather_mu_y_bwd(const float *grad_mu_y, const int *start, const int *dur, const int *offsets,
+                           const int *lengths, int B, int F, int Tx, int Ty, float *grad_mu_x, cudaStream_t stream);
+int launch_prior_loss(const float *y, const float *mu_x, const int *frame_token, const int *y_lengths, int B, int F,
+                      int Tx, int Ty, float *mu_y, float *loss, void *workspace, size_t workspace_bytes,
+                      cudaStream_t stream);
+int launch_prior_loss_bwd(const float *y, const float *mu_x, const int *start, const int *dur, const int *offsets,
+                          const int *y_lengths, const float *grad_loss, int B, int F, int Tx, int Ty, float *grad_mu_x,
+                          cudaStream_t stream);
+int launch_duration_loss(const float *logw, const int *durations, const int *x_lengths, int B, int Tx, float *loss,
+                         float *logw_target, float *grad_logw, cudaStream_t stream);
 int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
                           cudaStream_t stream);
 // tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.

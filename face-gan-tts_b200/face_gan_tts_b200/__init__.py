@@ -6,7 +6,7 @@ Drop-in for the alignment hot path of CognitiveModeling/Face-GAN-TTS:
 libmas_b200.so (hand-written CUDA behind a C ABI, include/mas_b200.h); this
 package is the thin PyTorch-facing host layer.  No CPU fallback.
 """
-from . import monotonic_align, sharding  # noqa: F401
+from . import losses, monotonic_align, sharding  # noqa: F401
 from .alignment import (  # noqa: F401
     AlignmentResult,
     align,
@@ -16,8 +16,18 @@ from .alignment import (  # noqa: F401
     log_prior_maximum_path,
 )
 from .install import install, uninstall  # noqa: F401
+from .losses import (  # noqa: F401
+    AlignmentLosses,
+    alignment_losses,
+    crop_frames,
+    duration_loss,
+    gather_mu_y,
+    prior_loss,
+    sequence_mask,
+)
 
 __all__ = [
     "monotonic_align", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
-    "durations_to_logw", "install", "uninstall",
+    "durations_to_logw", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
+    "duration_loss", "gather_mu_y", "prior_loss", "sequence_mask",
 ]

@@ -37,6 +37,19 @@ SIGNATURES = {
                                                 c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_size_t, c_int, c_void_p]),
     "mas_b200_generate_path": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mas_b200_sequence_mask": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mas_b200_crop_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mas_b200_gather_mu_y": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mas_b200_gather_mu_y_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_int, c_void_p, c_void_p]),
+    "mas_b200_prior_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mas_b200_prior_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mas_b200_prior_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mas_b200_duration_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
     "mas_b200_maximum_path_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float]),
     "mas_b200_log_prior_maximum_path_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                                      c_int, c_float, c_void_p, c_void_p, c_void_p]),

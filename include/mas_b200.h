@@ -149,6 +149,83 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,
 int mas_b200_generate_path(const int *durations_dev, const int *t_x_dev, const int *t_y_dev,
                            int B, int Tx, int Ty, void *path_dev, int path_dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Consumers of the alignment inside FaceTTS.compute_loss (SURVEY.md section 8
+ * rows a1, a6-a8 and f1, f2, f4), driven by the INDEX form of the path that
+ * mas_b200_maximum_path emits -- durations [B,Tx], frame_token [B,Ty] and
+ * start = exclusive prefix sum of durations -- so the dense [B,Tx,Ty] path is
+ * never re-read.  All tensors float32 / int32, contiguous, device memory.
+ * Reductions are two-stage in a fixed order: results are deterministic.
+ * ------------------------------------------------------------------------ */
+
+/*
+ * mask[b,t] = (t < lengths[b]) as float32 0/1, [B,T].
+ * Replaces: sequence_mask(length, max_length)  model/utils.py:6-11 (+ the .to(x_mask) cast at
+ * model/face_tts.py:161).
+ */
+int mas_b200_sequence_mask(const int *lengths_dev, int B, int T, float *mask_dev, void *stream);
+
+/*
+ * Random-window crop of the mel target and of the path, one launch for the batch.
+ * Replaces: the per-utterance Python loop model/face_tts.py:204-211.
+ *   cut_len[b] = min(y_lengths[b], out_size)                                  (:205)
+ *   y_cut[b,f,t'] = y[b,f,offsets[b]+t']  for t' < cut_len[b], else 0          (:208)
+ *   frame_token_cut[b,t'] = frame_token[b,offsets[b]+t'] likewise, else -1     (:209, index form)
+ *   cut_mask[b,t'] = (t' < cut_len[b])                                         (:211)
+ * offsets_dev [B] int32 is drawn by the caller (the reference draws it with Python's `random`, :188).
+ * y [B,F,Ty] -> y_cut [B,F,out_size]; frame_token [B,Ty] -> [B,out_size].  frame_token_dev /
+ * frame_token_cut_dev / cut_lengths_dev / cut_mask_dev may be NULL.
+ */
+int mas_b200_crop_frames(const float *y_dev, const int *frame_token_dev, const int *y_lengths_dev,
+                         const int *offsets_dev, int B, int F, int Ty, int out_size,
+                         float *y_cut_dev, int *frame_token_cut_dev, int *cut_lengths_dev,
+                         float *cut_mask_dev, void *stream);
+
+/*
+ * mu_y from the index form of the path.
+ * Replaces: mu_y = attn^T @ mu_x^T   model/face_tts.py:217-218 -- a K = Tx GEMM over a one-hot attn that is
+ * really the gather mu_y[b,f,t] = mu_x[b,f,frame_token[b,t]] (0 where frame_token < 0, i.e. beyond t_y).
+ * The backward is the matching segmented sum over each token's contiguous frames:
+ *   grad_mu_x[b,f,x] = sum_{t in [start-off, start-off+dur) and 0 <= t < len} grad_mu_y[b,f,t]
+ * with off = offsets_dev[b] (NULL: 0) and len = lengths_dev[b] (NULL: Ty) describing the crop window.
+ *   mu_x / grad_mu_x [B,F,Tx], mu_y / grad_mu_y [B,F,Ty] (Ty = out_size when cropped).
+ */
+int mas_b200_gather_mu_y(const float *mu_x_dev, const int *frame_token_dev, int B, int F, int Tx, int Ty,
+                         float *mu_y_dev, void *stream);
+int mas_b200_gather_mu_y_backward(const float *grad_mu_y_dev, const int *start_dev, const int *durations_dev,
+                                  const int *offsets_dev, const int *lengths_dev,
+                                  int B, int F, int Tx, int Ty, float *grad_mu_x_dev, void *stream);
+
+/*
+ * Prior loss fused with the mu_y gather.
+ * Replaces: model/face_tts.py:217-218 + :233-234
+ *   loss = sum_{b,f,t<len[b]} 0.5*((y - mu_y)^2 + log(2*pi)) / (sum_b len[b] * F)
+ * mu_y_dev (may be NULL) receives the gathered mu_y for the decoder; loss_dev is one float.
+ * Backward (w.r.t. mu_x, both through mu_y): grad_mu_x[b,f,x] =
+ *   -grad_loss / (sum len * F) * sum_{t in token x's frames, t < len} (y[b,f,t] - mu_x[b,f,x]).
+ * workspace: >= mas_b200_prior_loss_workspace_bytes(B,F,Ty), 8-byte aligned.
+ */
+size_t mas_b200_prior_loss_workspace_bytes(int B, int F, int Ty);
+int mas_b200_prior_loss(const float *y_dev, const float *mu_x_dev, const int *frame_token_dev,
+                        const int *y_lengths_dev, int B, int F, int Tx, int Ty,
+                        float *mu_y_dev, float *loss_dev, void *workspace_dev, size_t workspace_bytes,
+                        void *stream);
+int mas_b200_prior_loss_backward(const float *y_dev, const float *mu_x_dev, const int *start_dev,
+                                 const int *durations_dev, const int *offsets_dev, const int *y_lengths_dev,
+                                 const float *grad_loss_dev, int B, int F, int Tx, int Ty,
+                                 float *grad_mu_x_dev, void *stream);
+
+/*
+ * Duration loss straight from the integer durations of the backtrack.
+ * Replaces: logw_ = log(1e-8 + sum_t attn) * x_mask   model/face_tts.py:176  (a dense re-read of the path)
+ *           duration_loss(logw, logw_, x_lengths)      model/utils.py:43-45, call face_tts.py:179
+ *   loss = sum_{b,x} (logw[b,x] - logw_[b,x])^2 / sum_b x_lengths[b]
+ * logw [B,Tx] float32; logw_target_dev (logw_) and grad_logw_dev (= d loss / d logw) [B,Tx] may be NULL.
+ */
+int mas_b200_duration_loss(const float *logw_dev, const int *durations_dev, const int *x_lengths_dev,
+                           int B, int Tx, float *loss_dev, float *logw_target_dev, float *grad_logw_dev,
+                           void *stream);
+
 /*
  * HOST-buffer drop-in with the exact argument meaning of the Cython
  * maximum_path_c (model/monotonic_align/core.pyx:40): `paths` int32 [B,Tx,Ty]

@@ -192,3 +192,85 @@ def reference_core(variant: str = "asis"):
     from . import build_ref
 
     return build_ref.load(variant)
+
+
+# ---------------------------------------------------------------------------------------------
+# The alignment block of FaceTTS.compute_loss (model/face_tts.py:161-218, 233-234) restated in torch.
+# Pinned against the reference's real FaceTTS.compute_loss by tests/golden/make_compute_loss_golden.py
+# (fixture tests/golden/compute_loss_block.npz).
+# ---------------------------------------------------------------------------------------------
+def sequence_mask(length, max_length=None):
+    """model/utils.py:6-11."""
+    import torch
+
+    if max_length is None:
+        max_length = length.max()
+    x = torch.arange(int(max_length), dtype=length.dtype, device=length.device)
+    return x.unsqueeze(0) < length.unsqueeze(1)
+
+
+def duration_loss(logw, logw_, lengths):
+    """model/utils.py:43-45."""
+    import torch
+
+    return torch.sum((logw - logw_) ** 2) / torch.sum(lengths)
+
+
+def generate_path(duration, mask):
+    """model/utils.py:27-40."""
+    import torch
+
+    b, t_x, t_y = mask.shape
+    cum_duration = torch.cumsum(duration, 1)
+    path = sequence_mask(cum_duration.view(b * t_x), t_y).to(mask.dtype).view(b, t_x, t_y)
+    path = path - torch.nn.functional.pad(path, [0, 0, 1, 0, 0, 0])[:, :-1]
+    return path * mask
+
+
+def compute_loss_block(mu_x, logw, x_mask, y, y_lengths, x_lengths, n_feats, out_size=None, out_offset=None,
+                       maximum_path_fn=None):
+    """model/face_tts.py:159-218 + 233-234, dense formulation, autograd-differentiable w.r.t. mu_x and logw.
+    mu_x [B,F,Tx], logw [B,1,Tx], x_mask [B,1,Tx] float, y [B,F,Ty]; lengths int64 [B].
+    `out_offset` (int64 [B]) replaces the reference's `random.choice` draw (:186-194) when given.
+    Returns dict(dur_loss, prior_loss, mu_y, y, y_mask, attn, logw_)."""
+    import random
+
+    import torch
+
+    if maximum_path_fn is None:
+        maximum_path_fn = maximum_path
+    y_max_length = y.shape[-1]                                                            # :159
+    y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask)               # :161
+    attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)                                # :162
+    with torch.no_grad():
+        log_prior = log_prior_reference(mu_x, y)                                          # :166-171
+        attn = maximum_path_fn(log_prior, attn_mask.squeeze(1))                           # :173
+        attn = attn.detach()                                                              # :174
+    logw_ = torch.log(1e-8 + torch.sum(attn.unsqueeze(1), -1)) * x_mask                   # :176
+    dur_loss = duration_loss(logw, logw_, x_lengths)                                      # :179
+    attn_full = attn
+    if out_size is not None:                                                              # :181
+        max_offset = (y_lengths - out_size).clamp(0)                                      # :182
+        if out_offset is None:
+            offset_ranges = list(zip([0] * max_offset.shape[0], max_offset.cpu().numpy()))    # :183-185
+            out_offset = torch.LongTensor(
+                [torch.tensor(random.choice(range(start, end)) if end > start else 0)
+                 for start, end in offset_ranges]).to(y_lengths)                          # :186-191
+        attn_cut = torch.zeros(attn.shape[0], attn.shape[1], out_size, dtype=attn.dtype, device=attn.device)
+        y_cut = torch.zeros(y.shape[0], n_feats, out_size, dtype=y.dtype, device=y.device)
+        y_cut_lengths = []
+        for i, (y_, out_offset_) in enumerate(zip(y, out_offset)):                        # :204
+            y_cut_length = out_size + (y_lengths[i] - out_size).clamp(None, 0)            # :205
+            y_cut_lengths.append(y_cut_length)
+            cut_lower, cut_upper = out_offset_, out_offset_ + y_cut_length                # :207
+            y_cut[i, :, :y_cut_length] = y_[:, cut_lower:cut_upper]                       # :208
+            attn_cut[i, :, :y_cut_length] = attn[i, :, cut_lower:cut_upper]               # :209
+        y_cut_lengths = torch.LongTensor(y_cut_lengths)
+        y_cut_mask = sequence_mask(y_cut_lengths).unsqueeze(1).to(y_mask)                 # :211
+        attn, y, y_mask = attn_cut, y_cut, y_cut_mask.to(y.device)                        # :213-215
+    mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2))            # :217
+    mu_y = mu_y.transpose(1, 2)                                                           # :218
+    prior_loss = torch.sum(0.5 * ((y - mu_y) ** 2 + math.log(2 * math.pi)) * y_mask)      # :233
+    prior_loss = prior_loss / (torch.sum(y_mask) * n_feats)                               # :234
+    return dict(dur_loss=dur_loss, prior_loss=prior_loss, mu_y=mu_y, y=y, y_mask=y_mask, attn=attn_full,
+                attn_cut=attn, logw_=logw_, out_offset=out_offset)
