@@ -253,20 +253,24 @@ class AlignmentLosses:
 
 def alignment_losses(mu_x: torch.Tensor, logw: torch.Tensor, x_lengths, y: torch.Tensor, y_lengths, *,
                      out_size: Optional[int] = None, out_offset=None, dense_path: bool = False,
-                     impl: str = "auto", rng=random) -> AlignmentLosses:
+                     impl: str = "auto", rng=random, alignment: Optional[AlignmentResult] = None) -> AlignmentLosses:
     """Drop-in for the alignment block of FaceTTS.compute_loss, reference model/face_tts.py:161-218 + 233-234:
     masks -> log-prior -> MAS -> durations/duration loss -> random crop -> mu_y -> prior loss, with lengths
     instead of dense masks and the index form of the path instead of `attn`.
 
     mu_x [B,F,Tx], logw [B,1,Tx] (encoder outputs, may require grad), y [B,F,Ty]; x_lengths / y_lengths [B].
     out_size: crop window in frames (None: no crop).  out_offset: explicit [B] offsets; None draws them like the
-    reference (needs y_lengths on the host -- pass the CPU tensor the data loader produced to avoid a sync)."""
+    reference (needs y_lengths on the host -- pass the CPU tensor the data loader produced to avoid a sync).
+    alignment: a precomputed AlignmentResult (e.g. from maximum_path_from_lengths on a caller-supplied value
+    matrix); None runs the fused log-prior + MAS here."""
     _need_cuda(mu_x, "mu_x")
     _need_cuda(y, "y")
     B, F, Tx = mu_x.shape
     dev = mu_x.device
-    with torch.no_grad():                                              # face_tts.py:165, attn detached :174
-        res = log_prior_maximum_path(mu_x, y, x_lengths, y_lengths, dense_path=dense_path, impl=impl)
+    res = alignment
+    if res is None:
+        with torch.no_grad():                                          # face_tts.py:165, attn detached :174
+            res = log_prior_maximum_path(mu_x, y, x_lengths, y_lengths, dense_path=dense_path, impl=impl)
     dur = res.durations
     start = token_starts(dur)
     x_len = _lengths(x_lengths, B, dev, "x_lengths")

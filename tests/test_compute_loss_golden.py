@@ -1,0 +1,118 @@
+"""The alignment block of FaceTTS.compute_loss against fixtures the REFERENCE's real compute_loss produced
+(tests/golden/compute_loss_block.npz, made by tests/golden/make_compute_loss_golden.py from the unmodified
+reference model under import stubs; BASELINE configs[2] at fixture size).
+
+CPU (`not gpu`): the oracle's torch restatement (oracle.compute_loss_block) reproduces what the reference
+computed -- this is what pins the restatement the GPU tests in test_gpu_losses.py compare against.
+GPU: the CUDA path reproduces it through the public API:
+  * maximum_path(log_prior, attn_mask) on the reference's own tensors   -> attn, BIT-EXACT
+  * alignment_losses on that alignment: y/y_mask/mu_y handed to the decoder BIT-EXACT, dur_loss / prior_loss
+    within 2e-6 relative, gradients within 1e-5 of the largest magnitude
+  * the fully fused call (GPU log-prior instead of the reference's) agrees on >= 99.5 % of the frames
+    (a ~1e-7 relative log-prior difference may move a near-tie) and on both losses within 1e-3.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+CASES = ["cropped", "full"]
+LOSS_RTOL = 2e-6
+GRAD_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return np.load(os.path.join(ROOT, "tests", "golden", "compute_loss_block.npz"))
+
+
+def _case(fx, name):
+    d = {k.split("/", 1)[1]: fx[k] for k in fx.files if k.startswith(name + "/")}
+    shape = tuple(int(v) for v in d["attn_shape"])
+    d["attn"] = np.unpackbits(d["attn"], axis=-1)[..., :shape[-1]].astype(np.float32).reshape(shape)
+    d["out_size"] = None if int(d["out_size"]) < 0 else int(d["out_size"])
+    return d
+
+
+def _rel(a, b):
+    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_block_reproduces_the_reference_compute_loss(fx, name):
+    d = _case(fx, name)
+    t = {k: torch.from_numpy(np.asarray(d[k])) for k in ("mu_x", "logw", "x_mask", "y")}
+    mu = t["mu_x"].clone().requires_grad_(True)
+    lw = t["logw"].clone().requires_grad_(True)
+    off = torch.from_numpy(d["offsets"]).long() if d["out_size"] is not None else None
+    r = oracle.compute_loss_block(mu, lw, t["x_mask"], t["y"], torch.from_numpy(d["y_lengths"]).long(),
+                                  torch.from_numpy(d["x_lengths"]).long(), 128, out_size=d["out_size"], out_offset=off)
+    lp = oracle.log_prior_reference(t["mu_x"], t["y"])
+    np.testing.assert_allclose(lp.numpy(), d["log_prior"], rtol=1e-6, atol=1e-4)
+    assert np.array_equal(r["attn"].numpy(), d["attn"]), "restated wrapper + C oracle != reference attn"
+    assert np.array_equal(r["y"].numpy(), d["dec_y"])
+    assert np.array_equal(r["y_mask"].numpy(), d["dec_y_mask"])
+    np.testing.assert_allclose(r["mu_y"].detach().numpy(), d["dec_mu_y"], rtol=0, atol=0)
+    assert _rel(r["dur_loss"], d["dur_loss"]) < 1e-6 and _rel(r["prior_loss"], d["prior_loss"]) < 1e-6
+    g_mu, g_lw = torch.autograd.grad(r["dur_loss"] + r["prior_loss"], [mu, lw])
+    np.testing.assert_allclose(g_mu.numpy(), d["grad_mu_x"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(g_lw.numpy(), d["grad_logw"], rtol=1e-5, atol=1e-9)
+
+
+def test_reference_crop_offsets_are_reproduced_by_the_host_draw(fx):
+    """draw_crop_offsets consumes Python's `random` stream exactly like face_tts.py:186-191."""
+    import random
+
+    from face_gan_tts_b200 import losses
+
+    d = _case(fx, "cropped")
+    random.seed(int(d["seed"]))
+    assert losses.draw_crop_offsets(d["y_lengths"].tolist(), d["out_size"]) == d["offsets"].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_block_reproduces_the_reference_compute_loss(fx, name):
+    import face_gan_tts_b200 as fgt
+    from face_gan_tts_b200 import losses, monotonic_align
+
+    dev = "cuda:0"
+    d = _case(fx, name)
+    g = {k: torch.from_numpy(np.asarray(d[k])).to(dev) for k in ("mu_x", "logw", "x_mask", "y", "log_prior", "attn_mask")}
+    t_x, t_y = torch.from_numpy(d["x_lengths"]), torch.from_numpy(d["y_lengths"])
+
+    # 1. the drop-in call site, on the reference's own log_prior / attn_mask tensors (face_tts.py:173)
+    attn = monotonic_align.maximum_path(g["log_prior"], g["attn_mask"])
+    assert attn.dtype == torch.float32 and np.array_equal(attn.cpu().numpy(), d["attn"])
+
+    # 2. the consumers, on that alignment
+    ali = monotonic_align.maximum_path_from_lengths(g["log_prior"], t_x, t_y, dense_path=False)
+    mu = g["mu_x"].clone().requires_grad_(True)
+    lw = g["logw"].clone().requires_grad_(True)
+    off = d["offsets"].tolist() if d["out_size"] is not None else None
+    out = losses.alignment_losses(mu, lw, t_x, g["y"], t_y, out_size=d["out_size"], out_offset=off, alignment=ali)
+    T = d["dec_y"].shape[-1]                      # the reference's cut mask is only as wide as the longest cut
+    assert np.array_equal(out.y.cpu().numpy()[:, :, :T], d["dec_y"][:, :, :T])
+    Tm = d["dec_y_mask"].shape[-1]
+    assert np.array_equal(out.y_mask.cpu().numpy()[:, :, :Tm], d["dec_y_mask"]) and float(out.y_mask[:, :, Tm:].sum()) == 0
+    assert np.array_equal(out.mu_y.detach().cpu().numpy(), d["dec_mu_y"])
+    assert _rel(out.dur_loss, d["dur_loss"]) < LOSS_RTOL and _rel(out.prior_loss, d["prior_loss"]) < LOSS_RTOL
+    (out.dur_loss + out.prior_loss).backward()
+    for got, ref in ((mu.grad, d["grad_mu_x"]), (lw.grad, d["grad_logw"])):
+        assert np.abs(got.cpu().numpy() - ref).max() <= GRAD_RTOL * np.abs(ref).max()
+
+    # 3. fully fused (GPU log-prior): end-to-end agreement with the reference
+    fused = losses.alignment_losses(g["mu_x"], g["logw"], t_x, g["y"], t_y, out_size=d["out_size"], out_offset=off,
+                                    dense_path=True)
+    valid = torch.from_numpy(d["attn_mask"]).sum().item()
+    differ = float(np.abs(fused.alignment.path.cpu().numpy() - d["attn"]).sum()) / 2.0
+    assert differ / max(valid ** 0.5, 1) >= 0 and differ <= 0.005 * float(t_y.sum())
+    assert _rel(fused.dur_loss, d["dur_loss"]) < 1e-3 and _rel(fused.prior_loss, d["prior_loss"]) < 1e-3
+    lp = fgt.log_prior(g["mu_x"], g["y"])
+    m = g["attn_mask"] > 0
+    rel = ((lp - g["log_prior"]).abs() / g["log_prior"].abs())[m].max().item()
+    assert rel < 1e-4, rel                        # BASELINE north_star tolerance for the log-prior
