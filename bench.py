@@ -129,7 +129,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference (CPU) arm
-def reference_step_fn():
+def reference_step_fn(variant="asis"):
     """The reference's CPU implementation of the path: torch log-prior (face_tts.py:165-171, all torch
     threads) + its compiled core.pyx maximum_path_c as shipped (serial) through the wrapper's numpy steps."""
     import oracle
@@ -140,7 +140,7 @@ def reference_step_fn():
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         torch.set_num_threads(max(1, os.cpu_count() or 1))
-    core = oracle.reference_core("asis")
+    core = oracle.reference_core(variant)
     kind = "reference"
     if core is None:
         core, kind = oracle, "port"
@@ -299,7 +299,7 @@ def run_cuda(args):
     path_h = [torch.empty((B, TX, TY), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(dev)
 
-    def run_e2e(nsteps, dense_d2h):
+    def run_e2e(nsteps, dense_d2h, ragged=True):
         h2d_done = [torch.cuda.Event() for _ in range(nsteps)]
         res_done = [torch.cuda.Event() for _ in range(2)]
         checksum = 0
@@ -308,10 +308,14 @@ def run_cuda(args):
             d = sets[i % NSETS]
             mu_h, y_h, tx_h, ty_h = host_in[i % NH]
             with torch.cuda.stream(copy_stream):
-                d["mu"].copy_(mu_h, non_blocking=True)
-                d["y"].copy_(y_h, non_blocking=True)
-                d["tx"].copy_(tx_h, non_blocking=True)
-                d["ty"].copy_(ty_h, non_blocking=True)
+                if ragged:
+                    # only the valid [0,t_x) / [0,t_y) part of every row crosses PCIe (zero-copy pull kernel)
+                    fgt.upload_batch(mu_h, y_h, tx_h, ty_h, out=(d["mu"], d["y"], d["tx"], d["ty"]))
+                else:
+                    d["mu"].copy_(mu_h, non_blocking=True)
+                    d["y"].copy_(y_h, non_blocking=True)
+                    d["tx"].copy_(tx_h, non_blocking=True)
+                    d["ty"].copy_(ty_h, non_blocking=True)
                 h2d_done[i].record(copy_stream)
 
         enqueue_h2d(0)
@@ -332,11 +336,11 @@ def run_cuda(args):
         res_done[(nsteps - 1) & 1].synchronize()
         return checksum
 
-    def time_e2e(dense_d2h):
-        run_e2e(4, dense_d2h)
+    def time_e2e(dense_d2h, ragged=True):
+        run_e2e(4, dense_d2h, ragged)
         barrier()
         t0 = time.perf_counter()
-        run_e2e(K, dense_d2h)
+        run_e2e(K, dense_d2h, ragged)
         torch.cuda.synchronize(dev)
         sec = (time.perf_counter() - t0) / K
         if dist:
@@ -345,13 +349,22 @@ def run_cuda(args):
             sec = float(t.item())
         return sec
 
-    h2d = 4 * F * B * (TX + TY) + 8 * B
+    h2d_padded = 4 * F * B * (TX + TY) + 8 * B
+    # bytes the ragged upload actually reads over PCIe, counted from the host batches it copies (mean over the NH sets;
+    # 16-byte granularity along y rows)
+    h2d = int(sum(4 * F * int((t[2].long() + ((t[3].long() + 3) // 4) * 4).sum()) + 8 * B for t in host_in) / NH)
     sec_e2e = time_e2e(False)
+    sec_e2e_padded = time_e2e(False, ragged=False)
     sec_e2e_dense = time_e2e(True)
     e2e = {"value": world * CELLS / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e * 1e3,
            "result": "durations [B,Tx] + frame->token index [B,Ty] (dense path stays in HBM for mu_y)",
+           "h2d": "mas_b200_upload_batch: padded pinned host tensors in, only the valid rows' [0,t_x)/[0,t_y) cross "
+                  f"PCIe (padding zero-filled on the device); a plain copy of the padded tensors is {h2d_padded} bytes",
            "pipelining": "H2D of step i+1 on a copy stream under step i; host consumes result i-1 while step i runs"}
+    e2e_padded = {"value": world * CELLS / sec_e2e_padded, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
+                  "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e_padded * 1e3,
+                  "h2d": "cudaMemcpyAsync of the padded tensors (copy engine)"}
     e2e_dense = {"value": world * CELLS / sec_e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d,
                  "d2h_bytes_per_step": 4 * B * (TX + TY) + 4 * CELLS, "ms_per_step": sec_e2e_dense * 1e3}
 
@@ -404,10 +417,24 @@ def run_cuda(args):
             sec = time_cpu(cstep, 3, 1)
             cpu = {"value": CELLS / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + "; 3 steps",
                    "ms_per_step": sec * 1e3}
+            try:    # informational: the same core.pyx rebuilt with -fopenmp (its prange over the batch then uses every core)
+                ostep, okind, ocores, _ = reference_step_fn("omp")
+                if okind == "reference":
+                    osec = time_cpu(ostep, 3, 1)
+                    cpu["openmp_rebuild"] = {"value": CELLS / osec, "ms_per_step": osec * 1e3, "cores": ocores,
+                                             "note": "not how the reference ships (setup.py links no OpenMP)"}
+            except Exception:
+                pass
         except Exception as ex:  # the oracle is a reported baseline, never a dependency of the product
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
-        launches_per_step = 3      # log_prior + mas_forward + path_expand (no fused kernel selected)
+        # overlapped pipeline (B <= SMs/2, no profiler attached): tcgen05 log-prior kernel (which also expands the
+        # dense path) + MAS kernel; serial pipeline: log-prior, MAS, path_expand
+        overlapped = os.environ.get("MAS_B200_PIPELINE", "") != "serial" and 2 * B <= 148 and \
+            _lib.get_option("fused_impl") != 1
+        launches_per_step = 2 if overlapped else 3
+        roofline["pipeline"] = ("overlapped: log_prior_tc || mas_forward on two streams, flags through L2"
+                                if overlapped else "serial: log_prior -> mas_forward -> path_expand")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,7 +444,7 @@ def run_cuda(args):
                        "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 61} MB) larger than the 126 MB L2",
                        "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
                        else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense_path": e2e_dense,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_padded_copy": e2e_padded, "e2e_dense_path": e2e_dense,
             "gpu_launches": launches_per_step * K, "clocks": clocks,
         }
     if dist:

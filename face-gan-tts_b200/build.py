@@ -25,6 +25,7 @@ UNITS = [
     ("mas_forward_inst.cu", "mas_forward_r8", ["-DMASB200_INST_R=8"]),
     ("path_ops.cu", "path_ops", []),
     ("loss_ops.cu", "loss_ops", []),
+    ("upload.cu", "upload", []),
     ("log_prior_ffma.cu", "log_prior_ffma", []),
     ("log_prior_tc.cu", "log_prior_tc", []),
 ]

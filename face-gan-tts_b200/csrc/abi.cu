@@ -29,6 +29,7 @@ Opt g_opts[] = {
     {"lp_debug_ptr_lo", {0}},        // diagnostics only: [ctas][4] globaltimer stamps of the tcgen05 log-prior kernel
     {"lp_debug_ptr_hi", {0}},
     {"lp_impl", {0}},                // default log-prior implementation for MAS_B200_LP_AUTO
+    {"upload_ctas", {0}},            // CTAs of the zero-copy upload kernel (0 = one per SM)
     {"fused_impl", {0}},             // 0 auto, 1 force unfused pipeline, 2 force fused kernel
 };
 }  // namespace
@@ -284,6 +285,13 @@ int mas_b200_duration_loss(const float *logw_dev, const int *durations_dev, cons
                            float *loss_dev, float *logw_target_dev, float *grad_logw_dev, void *stream) {
     return launch_duration_loss(logw_dev, durations_dev, x_lengths_dev, B, Tx, loss_dev, logw_target_dev, grad_logw_dev,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_upload_batch(const float *mu_x_pinned, const float *y_pinned, const int *t_xs_pinned,
+                          const int *t_ys_pinned, int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev,
+                          int *t_x_dev, int *t_y_dev, void *stream) {
+    return launch_upload_batch(mu_x_pinned, y_pinned, t_xs_pinned, t_ys_pinned, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev,
+                               t_y_dev, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------- host-buffer drop-ins

@@ -1,0 +1,122 @@
+// upload.cu -- host -> device transfer of one padded batch that moves only the VALID part over PCIe.
+//
+// The call sites hand over mu_x [B,F,Tx] and y [B,F,Ty] padded to the batch maximum (reference
+// text_encoder.py:417 zeroes mu_x beyond t_x; lrs2_dataset.py:256,265 zero-pads y beyond t_y): with LRS2 lengths
+// ~35 % of those bytes are padding.  A plain cudaMemcpy of the padded tensors is PCIe-bound and ~4x longer than
+// the alignment itself, so the e2e path pulls the rows with SM loads straight from page-locked host memory
+// (UVA zero-copy), reads only [0,t_x) / [0,t_y) of every row, and writes zeros for the padding on the device --
+// the device tensors are exactly the padded tensors the reference contract describes.  PCIe-bound:
+// algorithmic bytes = 4*F*sum_b(t_x+t_y) + 8*B read over PCIe, 4*F*B*(Tx+Ty) written to HBM.
+#include <algorithm>
+
+#include "mas_common.cuh"
+#include "mas_host.h"
+
+namespace masb200 {
+
+namespace {
+
+constexpr int kRows = 4;          // feature rows per CTA: independent loads in flight per thread
+constexpr int kThreads = 256;
+
+// rows of one utterance: src/dst [F, T] with `valid` leading elements per row to copy, the rest zero-filled
+template <int VEC>
+__device__ __forceinline__ void pull_rows(const float *__restrict__ src, float *__restrict__ dst, int f0, int F, int T,
+                                          int valid) {
+    if (VEC == 4) {
+        const int nvec = T >> 2;
+        for (int i = threadIdx.x; i < nvec; i += kThreads) {
+            const int c = i << 2;
+            float4 v[kRows];
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) {
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f0 + k < F && c < valid)     // the only PCIe reads: 16 bytes, all rows issued before any store
+                    v[k] = __ldcs(reinterpret_cast<const float4 *>(src + (size_t)(f0 + k) * T + c));
+            }
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) {
+                if (f0 + k >= F) break;
+                if (c + 1 >= valid) v[k].y = 0.f;
+                if (c + 2 >= valid) v[k].z = 0.f;
+                if (c + 3 >= valid) v[k].w = 0.f;
+                *reinterpret_cast<float4 *>(dst + (size_t)(f0 + k) * T + c) = v[k];
+            }
+        }
+    } else {
+        for (int c = threadIdx.x; c < T; c += kThreads) {
+            float v[kRows];
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) v[k] = (f0 + k < F && c < valid) ? __ldcs(src + (size_t)(f0 + k) * T + c) : 0.f;
+#pragma unroll
+            for (int k = 0; k < kRows; ++k)
+                if (f0 + k < F) dst[(size_t)(f0 + k) * T + c] = v[k];
+        }
+    }
+}
+
+template <int VECX, int VECY>
+__global__ void __launch_bounds__(kThreads) upload_batch_kernel(const float *__restrict__ mu_h, const float *__restrict__ y_h,
+                                                                const int *__restrict__ tx_h, const int *__restrict__ ty_h,
+                                                                int B, int F, int Tx, int Ty, float *__restrict__ mu_d,
+                                                                float *__restrict__ y_d, int *__restrict__ tx_d,
+                                                                int *__restrict__ ty_d) {
+    // Persistent, one small CTA per SM: it only has to keep PCIe busy (a few hundred KB in flight), and it must
+    // leave the thread slots of every SM to the alignment kernels of the previous step running beside it.
+    const int groups = (F + kRows - 1) / kRows;
+    for (int item = blockIdx.x; item < B * groups; item += gridDim.x) {
+        const int b = item / groups, f0 = (item - b * groups) * kRows;
+        const int tx = tx_h[b], ty = ty_h[b];      // 8 bytes over PCIe per item
+        if (f0 == 0 && threadIdx.x == 0) { tx_d[b] = tx; ty_d[b] = ty; }
+        pull_rows<VECY>(y_h + (size_t)b * F * Ty, y_d + (size_t)b * F * Ty, f0, F, Ty, min(max(ty, 0), Ty));
+        pull_rows<VECX>(mu_h + (size_t)b * F * Tx, mu_d + (size_t)b * F * Tx, f0, F, Tx, min(max(tx, 0), Tx));
+    }
+}
+
+bool device_view(const void *host, const void **dev) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;   // pageable memory: not accessible
+    *dev = a.devicePointer;
+    return true;
+}
+
+bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const int *t_xs_pinned, const int *t_ys_pinned,
+                        int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev, int *t_x_dev, int *t_y_dev,
+                        cudaStream_t stream) {
+    if (!mu_x_pinned || !y_pinned || !t_xs_pinned || !t_ys_pinned || !mu_x_dev || !y_dev || !t_x_dev || !t_y_dev ||
+        B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0)
+        return MAS_B200_ERR_ARG;
+    DeviceInfo di;
+    const int rc = device_info(&di);
+    if (rc != MAS_B200_OK) return rc;
+    const void *mu_v, *y_v, *tx_v, *ty_v;
+    if (!device_view(mu_x_pinned, &mu_v) || !device_view(y_pinned, &y_v) || !device_view(t_xs_pinned, &tx_v) ||
+        !device_view(t_ys_pinned, &ty_v))
+        return MAS_B200_ERR_ARG;      // the host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)
+    const bool vx = (Tx % 4 == 0) && al16(mu_v) && al16(mu_x_dev);
+    const bool vy = (Ty % 4 == 0) && al16(y_v) && al16(y_dev);
+    const long long items = (long long)B * ((F + kRows - 1) / kRows);
+    const int ctas = option("upload_ctas");
+    dim3 grid((unsigned)std::min<long long>(items, ctas > 0 ? ctas : di.sm_count));
+    auto *mu = static_cast<const float *>(mu_v);
+    auto *yy = static_cast<const float *>(y_v);
+    auto *txp = static_cast<const int *>(tx_v);
+    auto *typ = static_cast<const int *>(ty_v);
+    if (vx && vy)
+        upload_batch_kernel<4, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+    else if (vy)
+        upload_batch_kernel<1, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+    else if (vx)
+        upload_batch_kernel<4, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+    else
+        upload_batch_kernel<1, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+    MASB200_CUDA_TRY(cudaGetLastError());
+    return MAS_B200_OK;
+}
+
+}  // namespace masb200

@@ -14,6 +14,7 @@ from .alignment import (  # noqa: F401
     generate_path,
     log_prior,
     log_prior_maximum_path,
+    upload_batch,
 )
 from .install import install, uninstall  # noqa: F401
 from .losses import (  # noqa: F401
@@ -28,6 +29,6 @@ from .losses import (  # noqa: F401
 
 __all__ = [
     "monotonic_align", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
-    "durations_to_logw", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
+    "durations_to_logw", "upload_batch", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
     "duration_loss", "gather_mu_y", "prior_loss", "sequence_mask",
 ]

@@ -50,6 +50,8 @@ SIGNATURES = {
                                              c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mas_b200_duration_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p]),
+    "mas_b200_upload_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_b200_maximum_path_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float]),
     "mas_b200_log_prior_maximum_path_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                                      c_int, c_float, c_void_p, c_void_p, c_void_p]),

@@ -194,6 +194,35 @@ def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     return path if mask.dtype == torch.float32 else path.to(mask.dtype)
 
 
+def upload_batch(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *,
+                 device=None, out=None):
+    """Host -> device transfer of one padded batch that moves only its valid part over PCIe
+    (mas_b200_upload_batch): mu_x [B,F,Tx], y [B,F,Ty] float32 and int32 lengths [B], all in PINNED host
+    memory.  Returns (mu_x, y, t_x, t_y) on the device (`out` = the same 4-tuple to reuse buffers), padding
+    zero-filled.  Asynchronous on the current stream: do not touch the host tensors until it has completed."""
+    for t, name in ((mu_x, "mu_x"), (y, "y"), (x_lengths, "x_lengths"), (y_lengths, "y_lengths")):
+        if t.is_cuda or not t.is_pinned() or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous tensor in pinned host memory")
+    if mu_x.dtype != torch.float32 or y.dtype != torch.float32 or x_lengths.dtype != torch.int32 or \
+            y_lengths.dtype != torch.int32:
+        raise ValueError("mu_x / y must be float32 and the lengths int32")
+    B, F, Tx = mu_x.shape
+    Ty = y.shape[2]
+    if y.shape[:2] != (B, F) or x_lengths.shape != (B,) or y_lengths.shape != (B,):
+        raise ValueError("mu_x [B,F,Tx], y [B,F,Ty] and lengths [B] must agree")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        if out is None:
+            out = (torch.empty((B, F, Tx), dtype=torch.float32, device=dev),
+                   torch.empty((B, F, Ty), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
+        rc = _lib.lib().mas_b200_upload_batch(mu_x.data_ptr(), y.data_ptr(), x_lengths.data_ptr(), y_lengths.data_ptr(),
+                                              B, F, Tx, Ty, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                              out[3].data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "mas_b200_upload_batch")
+    return out
+
+
 def durations_to_logw(durations: torch.Tensor, x_mask: torch.Tensor) -> torch.Tensor:
     """logw_ = log(1e-8 + sum_t attn) * x_mask  (reference model/face_tts.py:176) straight from the
     integer durations the backtrack emits -- no dense re-read.  x_mask [B,1,Tx] -> [B,1,Tx]."""

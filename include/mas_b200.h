@@ -227,6 +227,21 @@ int mas_b200_duration_loss(const float *logw_dev, const int *durations_dev, cons
                            void *stream);
 
 /*
+ * Host -> device transfer of one padded batch that moves only its VALID part over PCIe.
+ * Replaces: the `.to(self.device)` copies of FaceTTS.relocate_input (model/face_tts.py:85-89, call :146) for
+ * the tensors of this path, when they start in host memory (the e2e measurement; in training mu_x is already
+ * on the device).  mu_x [B,F,Tx] / y [B,F,Ty] are padded to the batch maximum (text_encoder.py:417,
+ * lrs2_dataset.py:256,265); the kernel reads [0,t_x) / [0,t_y) of every row straight from PAGE-LOCKED host
+ * memory (cudaHostAlloc / cudaHostRegister / torch pin_memory; anything else -> MAS_B200_ERR_ARG) and writes
+ * the zero padding on the device, so the device tensors equal a plain copy of correctly padded inputs.
+ * Also copies the lengths.  Asynchronous on `stream`; the host buffers must stay untouched until it completes.
+ */
+int mas_b200_upload_batch(const float *mu_x_pinned, const float *y_pinned,
+                          const int *t_xs_pinned, const int *t_ys_pinned,
+                          int B, int F, int Tx, int Ty,
+                          float *mu_x_dev, float *y_dev, int *t_x_dev, int *t_y_dev, void *stream);
+
+/*
  * HOST-buffer drop-in with the exact argument meaning of the Cython
  * maximum_path_c (model/monotonic_align/core.pyx:40): `paths` int32 [B,Tx,Ty]
  * (overwritten; need not be pre-zeroed), `values` float32 [B,Tx,Ty] (NOT

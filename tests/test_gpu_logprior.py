@@ -183,3 +183,36 @@ def test_overlapped_pipeline_rejects_bad_items_without_hanging():
     assert res.status.tolist() == [0, 1, 0, 0]
     assert int(res.path[1].sum()) == 0 and int(res.durations[1].sum()) == 0
     assert torch.equal(res.path[0].sum(-1).int(), res.durations[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# ragged zero-copy upload (mas_b200_upload_batch): the e2e path's host -> device transfer
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,F,Tx,Ty", [(32, 80, 190, 1000), (5, 128, 64, 256), (3, 7, 33, 101), (2, 80, 1, 4)])
+def test_upload_batch_equals_a_plain_copy_of_padded_inputs(B, F, Tx, Ty):
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, Tx, Ty, seed=77, tx_lo=1, ty_lo=max(1, Ty // 3))
+    # garbage in the padding of the HOST buffers: the device tensors must still be zero-padded
+    g = torch.Generator().manual_seed(1)
+    junk_x = torch.randn(B, F, Tx, generator=g) * (torch.arange(Tx)[None, None] >= t_x[:, None, None])
+    junk_y = torch.randn(B, F, Ty, generator=g) * (torch.arange(Ty)[None, None] >= t_y[:, None, None])
+    host = [(mu_x + junk_x).pin_memory(), (y + junk_y).pin_memory(), t_x.pin_memory(), t_y.pin_memory()]
+    out = fgt.upload_batch(*host)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0].cpu(), mu_x) and torch.equal(out[1].cpu(), y)
+    assert torch.equal(out[2].cpu(), t_x) and torch.equal(out[3].cpu(), t_y)
+    # reuse of the output buffers + the alignment computed from them equals the one from plain copies
+    out2 = fgt.upload_batch(*host, out=out)
+    a = fgt.log_prior_maximum_path(out2[0], out2[1], out2[2], out2[3], dense_path=False)
+    b = fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, dense_path=False)
+    assert torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token)
+
+
+def test_upload_batch_rejects_pageable_memory():
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(2, 80, 21, 64, seed=3, tx_lo=5, ty_lo=30)
+    with pytest.raises(ValueError):
+        fgt.upload_batch(mu_x, y, t_x, t_y)
+    L = fgt._lib.lib()
+    d = [t.to(DEV) for t in (mu_x, y, t_x, t_y)]
+    rc = L.mas_b200_upload_batch(mu_x.data_ptr(), y.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), 2, 80, 21, 64,
+                                 d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), None)
+    assert rc == fgt._lib.ERR_ARG
