@@ -29,6 +29,8 @@ Opt g_opts[] = {
     {"lp_debug_ptr_lo", {0}},        // diagnostics only: [ctas][4] globaltimer stamps of the tcgen05 log-prior kernel
     {"lp_debug_ptr_hi", {0}},
     {"lp_impl", {0}},                // default log-prior implementation for MAS_B200_LP_AUTO
+    {"upload_impl", {0}},            // 0/1 SM zero-copy pull kernel, 2 copy engine (one 2-D copy per utterance and tensor)
+    {"upload_l2_256b", {0}},         // 1: zero-copy loads carry the L2::256B fetch hint
     {"upload_ctas", {0}},            // CTAs of the zero-copy upload kernel (0 = one per SM)
     {"fused_impl", {0}},             // 0 auto, 1 force unfused pipeline, 2 force fused kernel
 };
@@ -191,7 +193,7 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
     const int fi = option("fused_impl");
     const bool tc_ok = (impl == MAS_B200_LP_AUTO || impl == MAS_B200_LP_TCGEN05) && option("lp_impl") != MAS_B200_LP_FFMA &&
                        log_prior_tc_supported(mu_x_dev, y_dev, value, B, F, Tx, Ty);
-    if (tc_ok && fi != 1 && 2 * B <= di.sm_count && (fi == 2 || kernels_may_overlap())) {
+    if (tc_ok && fi != 1 && B + log_prior_tc_min_ctas(B, F, Tx) <= di.sm_count && (fi == 2 || kernels_may_overlap())) {
         AuxStream *aux = aux_stream();
         if (aux != nullptr) {
             const int ngroups = (Ty + 63) / 64;
@@ -214,7 +216,8 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
             L.path = path_dev; L.path_dtype = path_dtype;
             L.durations = durations_dev; L.frame_token = frame_token_dev; L.status = status_dev;
             L.workspace = workspace_dev; L.workspace_bytes = mas_ws; L.stream = s;
-            L.gate = flags; L.gate_pitch = ngroups; L.done = want_path ? done : nullptr;
+            L.gate = flags; L.gate_pitch = ngroups; L.gate_need = log_prior_tc_flag_target(F, Tx);
+            L.done = want_path ? done : nullptr;
             L.dry_run = 1;
             rc = launch_mas(L);
             if (rc != MAS_B200_OK) return rc;
@@ -237,7 +240,14 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
 
 int mas_b200_generate_path(const int *durations_dev, const int *t_x_dev, const int *t_y_dev, int B, int Tx, int Ty,
                            void *path_dev, int path_dtype, void *stream) {
-    return launch_generate_path(durations_dev, t_x_dev, t_y_dev, B, Tx, Ty, path_dev, path_dtype,
+    if (path_dtype == MAS_B200_PATH_NONE) return MAS_B200_ERR_ARG;
+    return launch_generate_path(durations_dev, 0, t_x_dev, t_y_dev, B, Tx, Ty, path_dev, path_dtype, nullptr,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_generate_path_f32(const float *durations_dev, const int *t_x_dev, const int *t_y_dev, int B, int Tx, int Ty,
+                               void *path_dev, int path_dtype, int *frame_token_dev, void *stream) {
+    return launch_generate_path(durations_dev, 1, t_x_dev, t_y_dev, B, Tx, Ty, path_dev, path_dtype, frame_token_dev,
                                 static_cast<cudaStream_t>(stream));
 }
 

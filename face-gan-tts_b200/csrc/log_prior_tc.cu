@@ -17,7 +17,7 @@ float log_prior_const(int F);   // log_prior_ffma.cu
 namespace {
 
 constexpr int kTcThreads = 160;
-constexpr int kMaxF = 96;             // 4F (A hi/lo, two M-tiles) + 128 (D) <= 512 columns
+constexpr int kMaxF = 96;             // 4F (A hi/lo, two M-tiles) + 128 (D) <= 512 columns; beyond: split-M (2F + 64)
 
 struct LpTcParams {
     const float *mu;     // [B,F,Tx]
@@ -29,18 +29,23 @@ struct LpTcParams {
     int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
     PathJob job;         // optional: expand the dense path of utterance b once the MAS kernel reports it done
     long long *dbg;      // diagnostics: [ctas][4] globaltimer stamps
-    int *flags;          // optional [B][flag_pitch]: set to 1 when a 64-frame group of an utterance is in memory
-    int flag_pitch;
+    int *flags;          // optional [B][flag_pitch]: counts the M-tile CTAs that have a 64-frame group of an utterance
+    int flag_pitch;      //   in memory (1 when a CTA holds both M-tiles; split-M: ready at ceil(Tx/128))
 };
 
-template <int KS>
+// SPLITM: one CTA per (utterance, group run, M-tile) -- blockIdx.z is the M-tile; see lp_tc_frontend.cuh.
+template <int KS, bool SPLITM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap) {
     constexpr int F = 8 * KS;
+    constexpr int MTMAX = SPLITM ? 1 : 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     LpFront S;
     S.carve(smem_raw, F);
-    float *mu_s = reinterpret_cast<float *>(smem_raw + ((LpFrontSmem::total(F) + 127) / 128) * 128);   // [F][Tx] staging
+    // [F][Tx] staging of mu_x.  Split-M (F = 128: 128 KB of operand buffers) parks it in the hi/lo operand buffers,
+    // which nothing writes before every aux thread has left the prologue.
+    float *mu_s = SPLITM ? reinterpret_cast<float *>(S.hi)
+                         : reinterpret_cast<float *>(smem_raw + ((LpFrontSmem::total(F) + 127) / 128) * 128);
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
@@ -50,7 +55,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     const int g0 = P.strided ? (int)blockIdx.x : (int)blockIdx.x * P.groups_per_cta;
     const int ng = P.strided ? (P.ngroups - g0 + gs - 1) / gs : min(P.groups_per_cta, P.ngroups - g0);   // groups of this CTA
     if (ng <= 0) return;
-    const int MT = (P.Tx + 127) >> 7;                                         // M-tiles of 128 text positions
+    const int MT = SPLITM ? 1 : (P.Tx + 127) >> 7;                           // M-tiles of 128 text positions in this CTA
+    const int mt0 = SPLITM ? (int)blockIdx.z : 0;
 
     long long *dbg = P.dbg ? P.dbg + ((size_t)b * gridDim.x + blockIdx.x) * 4 : nullptr;
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[0] = t; }
@@ -62,10 +68,11 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     const uint32_t tmem = __shfl_sync(kFullMask, *S.tmem_slot, 0);
 
     if (warp == 4) {
-        lp_mma_warp<KS>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng, MT, tmem);
+        lp_mma_warp<KS, MTMAX>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng, MT, tmem);
     } else {
         float musq[2];
-        lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [](int mt, int m) { return mt * 128 + m; }, musq);
+        lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [mt0](int mt, int m) { return (mt0 + mt) * 128 + m; }, musq);
+        if (SPLITM) lp_aux_bar();          // mu_s aliases the operand buffers the first split is about to fill
         float *outb = P.out + (size_t)b * P.Tx * P.Ty;
         for (int g = 0; g <= ng; ++g) {
             if (g < ng) lp_aux_split<KS>(S, g, tid, warp, lane);
@@ -75,10 +82,10 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                 const int gidx = g0 + gg * gs;
                 const int t0 = gidx * kLpGroup;
                 uint32_t d0[2][32], d1[2][32];
-                lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1);
+                lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1, MTMAX);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int x = mt * 128 + tid;
+                for (int mt = 0; mt < MTMAX; ++mt) {
+                    const int x = (mt0 + mt) * 128 + tid;
                     if (mt < MT && x < P.Tx) {
                         float *dst = outb + (size_t)x * P.Ty + t0;
 #pragma unroll
@@ -101,7 +108,10 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                     // publish the group to the MAS kernel running next to this one (device-scope release)
                     __threadfence();
                     lp_aux_bar();
-                    if (tid == 0) gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
+                    if (tid == 0) {
+                        if (SPLITM) gflag_add_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
+                        else gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
+                    }
                 }
             }
         }
@@ -116,8 +126,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     // table -- the last utterance to finish is written by all SMs of the kernel at once.  32 done-flags are
     // polled per load (one lane each), so a sweep costs one L2 round trip.
     if (P.job.path != nullptr) {
-        const int total_warps = (int)(gridDim.x * gridDim.y) * (kTcThreads / 32);
-        const int gw = (int)(blockIdx.y * gridDim.x + blockIdx.x) * (kTcThreads / 32) + warp;
+        const int total_warps = (int)(gridDim.x * gridDim.y * gridDim.z) * (kTcThreads / 32);
+        const int gw = (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (kTcThreads / 32) + warp;
         if (gw < P.Tx) {
             uint32_t proc[4] = {0u, 0u, 0u, 0u};
             int remaining = P.B;
@@ -184,11 +194,16 @@ int make_y_tensor_map(const float *y, int B, int F, int Ty, CUtensorMap *out) {
 
 // shapes the tensor-core kernel takes; everything else goes to the FFMA kernel
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty) {
-    if (!(F == 64 || F == 80 || F == 96) || Tx > 256 || Ty % 4 != 0 || B > 65535) return false;
+    if (!(F == 64 || F == 80 || F == 96 || F == 128) || Tx > 256 || Ty % 4 != 0 || B > 65535) return false;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(mu_x) & 15))
         return false;
     return true;
 }
+
+// CTAs the kernel needs co-resident at least (one per utterance and M-tile) and the count a `flags` entry reaches
+// when a group is complete -- what the overlapped pipeline (abi.cu) sizes itself with.
+int log_prior_tc_min_ctas(int B, int F, int Tx) { return F > kMaxF ? B * ((Tx + 127) / 128) : B; }
+int log_prior_tc_flag_target(int F, int Tx) { return F > kMaxF ? (Tx + 127) / 128 : 1; }
 
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
                         cudaStream_t stream, int *flags, int flag_pitch, int max_ctas, const PathJob *job) {
@@ -211,32 +226,35 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
     }
     if (job) P.job = *job;
+    const bool splitm = F > kMaxF;
+    const int mtiles = splitm ? (Tx + 127) / 128 : 1;          // grid.z
     const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;
-    int chunks = cta_budget / B;                                // one wave of CTAs (one CTA per SM: TMEM + smem)
+    int chunks = cta_budget / (B * mtiles);                                // one wave of CTAs (one CTA per SM: TMEM + smem)
     chunks = chunks < 1 ? 1 : (chunks > P.ngroups ? P.ngroups : chunks);
     P.groups_per_cta = (P.ngroups + chunks - 1) / chunks;
     chunks = (P.ngroups + P.groups_per_cta - 1) / P.groups_per_cta;
     P.chunks = chunks;
     P.strided = flags != nullptr ? 1 : 0;
-    size_t smem = ((LpFrontSmem::total(F) + 127) / 128) * 128 + (size_t)F * Tx * 4 + 1024;
+    size_t smem = ((LpFrontSmem::total(F) + 127) / 128) * 128 + (splitm ? 0 : (size_t)F * Tx * 4) + 1024;
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;   // > half an SM: one CTA per SM (each allocates all of TMEM)
 
     void (*kern)(const LpTcParams, const CUtensorMap) = nullptr;
     switch (F) {
-        case 64: kern = log_prior_tc_kernel<8>; break;
-        case 80: kern = log_prior_tc_kernel<10>; break;
-        case 96: kern = log_prior_tc_kernel<12>; break;
+        case 64: kern = log_prior_tc_kernel<8, false>; break;
+        case 80: kern = log_prior_tc_kernel<10, false>; break;
+        case 96: kern = log_prior_tc_kernel<12, false>; break;
+        case 128: kern = log_prior_tc_kernel<16, true>; break;
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
-    static std::atomic<int> configured[16][3];
+    static std::atomic<int> configured[16][4];
     int dev = 0;
     MASB200_CUDA_TRY(cudaGetDevice(&dev));
-    const int ki = F == 64 ? 0 : (F == 80 ? 1 : 2);
+    const int ki = F == 64 ? 0 : (F == 80 ? 1 : (F == 96 ? 2 : 3));
     if (dev < 0 || dev >= 16 || !configured[dev][ki].load(std::memory_order_acquire)) {
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         if (dev >= 0 && dev < 16) configured[dev][ki].store(1, std::memory_order_release);
     }
-    kern<<<dim3(chunks, B), kTcThreads, smem, stream>>>(P, ymap);
+    kern<<<dim3(chunks, B, mtiles), kTcThreads, smem, stream>>>(P, ymap);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

@@ -7,7 +7,7 @@
 // accumulation in TMEM): ~22 mantissa bits per operand, fp32-class accuracy (3.8e-7 max relative error
 // measured), far inside the 1e-4 bar.  ysq / musq are fp32 FMAs on the CUDA cores.
 //
-// Per CTA (one utterance, Tx <= 256, F = 8*KS <= 96):
+// Per CTA (one utterance, Tx <= 256, F = 8*KS <= 96; or -- split-M, F <= 128 -- one 128-row M-tile of it):
 //   A  (M = text positions)  mu_x rows: one cp.async.bulk of the utterance's [F][Tx] block into shared
 //                            memory, split hi/lo in registers and parked in TENSOR MEMORY for the whole CTA
 //                            (tcgen05.st; lane = text position, column = mel bin) -- the operand costs no
@@ -21,6 +21,9 @@
 // the K loop is fully unrolled (KS is a template argument) and only the instruction itself is predicated
 // on elect.sync; N = 64 keeps the instruction count at 6*KS per 64 frames.
 // TMEM map (columns): [0,4F) A hi/lo of M-tile 0 then 1; [4F, 4F+128) D of M-tile 0 then 1.
+// Split-M (n_feats = 128, the reference default, needs 4F = 512 columns for A alone): a CTA holds ONE M-tile,
+// A in [0,2F), D in [2F, 2F+64); the CTAs of the two M-tiles of an utterance run on different SMs and each
+// splits the y groups itself.
 #pragma once
 
 #include "tc_common.cuh"
@@ -69,7 +72,8 @@ struct LpFront {
 };
 
 __device__ __forceinline__ uint32_t lp_col_a(int F, int mt, int lo) { return (uint32_t)((mt * 2 + lo) * F); }
-__device__ __forceinline__ uint32_t lp_col_d(int F, int mt) { return (uint32_t)(4 * F + mt * kLpGroup); }
+// mtmax = M-tiles one CTA holds: 2 (Tx <= 256 in one CTA, F <= 96) or 1 (split-M: one CTA per M-tile, F <= 128)
+__device__ __forceinline__ uint32_t lp_col_d(int F, int mt, int mtmax = 2) { return (uint32_t)(2 * mtmax * F + mt * kLpGroup); }
 
 __device__ __forceinline__ void lp_aux_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -98,7 +102,7 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
 // ---------------------------------------------------------------------------------------------------
 // MMA / TMA warp: all 32 lanes run this (warp-uniform); ng groups of 64 frames: frames t_begin + k*t_stride.
 // ---------------------------------------------------------------------------------------------------
-template <int KS>
+template <int KS, int MTMAX = 2>
 __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap *ymap, const float *mu_b, float *mu_stage,
                                             int Tx, int b, int t_begin, int t_stride, int ng, int MT, uint32_t tmem) {
     constexpr int F = 8 * KS;
@@ -128,7 +132,7 @@ __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap 
         const uint32_t bh = smem_u32(S.hi) + (uint32_t)p * LpFrontSmem::op_bytes(F);
         const uint32_t bl = smem_u32(S.lo) + (uint32_t)p * LpFrontSmem::op_bytes(F);
         for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t dcol = tmem + lp_col_d(F, mt);
+            const uint32_t dcol = tmem + lp_col_d(F, mt, MTMAX);
             const uint32_t ah = tmem + lp_col_a(F, mt, 0), al = tmem + lp_col_a(F, mt, 1);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
@@ -218,15 +222,15 @@ __device__ __forceinline__ void lp_aux_split(const LpFront &S, int g, int tid, i
 
 // drain D of group g into registers (both M-tiles, 64 columns each) and hand the accumulator back.
 __device__ __forceinline__ void lp_aux_drain(const LpFront &S, int F, int g, int warp, int MT, uint32_t tmem,
-                                             uint32_t (&d0)[2][32], uint32_t (&d1)[2][32]) {
+                                             uint32_t (&d0)[2][32], uint32_t (&d1)[2][32], int mtmax = 2) {
     const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
     mbar_wait(S.bar_dfull, (uint32_t)g & 1u);
     tc_fence_after();
-    tmem_ld32(tmem + lane_base + lp_col_d(F, 0), d0[0]);
-    tmem_ld32(tmem + lane_base + lp_col_d(F, 0) + 32, d0[1]);
+    tmem_ld32(tmem + lane_base + lp_col_d(F, 0, mtmax), d0[0]);
+    tmem_ld32(tmem + lane_base + lp_col_d(F, 0, mtmax) + 32, d0[1]);
     if (MT > 1) {
-        tmem_ld32(tmem + lane_base + lp_col_d(F, 1), d1[0]);
-        tmem_ld32(tmem + lane_base + lp_col_d(F, 1) + 32, d1[1]);
+        tmem_ld32(tmem + lane_base + lp_col_d(F, 1, mtmax), d1[0]);
+        tmem_ld32(tmem + lane_base + lp_col_d(F, 1, mtmax) + 32, d1[1]);
     }
     tmem_wait_ld();
     tc_fence_before();

@@ -152,6 +152,9 @@ __device__ __forceinline__ void flag_release_if(int *flag, int v, uint32_t pred)
 __device__ __forceinline__ void gflag_release(int *flag, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
 }
+__device__ __forceinline__ void gflag_add_release(int *flag, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
 __device__ __forceinline__ int gflag_acquire(const int *flag) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");

@@ -79,6 +79,7 @@ struct MasParams {
     int *done;               // optional [B]: set to 1 (device-scope release) once the [start,dur] table of item b is final
     const int *gate;         // optional [B][gate_pitch]: group g of utterance b may be read once gate != 0
     int gate_pitch;          //   (written by the log-prior kernel running concurrently), 64 frames per group
+    int gate_need;           // value a gate entry reaches when its group is complete (1, or the M-tile CTA count)
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
@@ -556,7 +557,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                     while (true) {
                         const int g = g0 + lane;
                         const int f = (g < P.gate_pitch) ? gflag_acquire(gf + g) : 0;
-                        const unsigned ready = __ballot_sync(kFullMask, f != 0);
+                        const unsigned ready = __ballot_sync(kFullMask, f >= P.gate_need);
                         if (ready & 1u) { gate_known = g0 + __ffs((int)~ready) - 1; break; }    // consecutive ready groups
                         __nanosleep(64);
                         ++gate_spins;

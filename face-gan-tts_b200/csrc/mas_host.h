@@ -58,6 +58,7 @@ struct MasLaunch {
     cudaStream_t stream;
     const int *gate;    // optional device flags [B][gate_pitch] (see MasParams::gate); null normally
     int gate_pitch;
+    int gate_need;      // value a gate entry holds when its group is complete (0/1: one writer; split-M log-prior: 2)
     int dry_run;        // 1: validate arguments / plan only, launch nothing
     int *done;          // optional device flags [B]: when set, the dense path is NOT written here; the kernel
                         // watching `done` expands it from the [start,dur] table (see PathJob)
@@ -77,8 +78,8 @@ int launch_mas(const MasLaunch &L);
 int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, void *path, int path_dtype,
                        cudaStream_t stream);
 int launch_lengths_from_mask(const float *mask, int B, int Tx, int Ty, int *t_x, int *t_y, cudaStream_t stream);
-int launch_generate_path(const int *durations, const int *t_x, const int *t_y, int B, int Tx, int Ty, void *path,
-                         int path_dtype, cudaStream_t stream);
+int launch_generate_path(const void *durations, int dur_is_float, const int *t_x, const int *t_y, int B, int Tx, int Ty,
+                         void *path, int path_dtype, int *frame_token, cudaStream_t stream);
 // loss_ops.cu: consumers of the alignment in index form
 int launch_sequence_mask(const int *lengths, int B, int T, float *mask, cudaStream_t stream);
 int launch_crop_frames(const float *y, const int *frame_token, const int *y_lengths, const int *offsets, int B, int F,
@@ -107,6 +108,8 @@ int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int T
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
                         cudaStream_t stream, int *flags = nullptr, int flag_pitch = 0, int max_ctas = 0,
                         const PathJob *job = nullptr);
+int log_prior_tc_min_ctas(int B, int F, int Tx);
+int log_prior_tc_flag_target(int F, int Tx);
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty);
 
 }  // namespace masb200

@@ -50,10 +50,15 @@ __global__ void __launch_bounds__(256) lengths_from_mask_kernel(const float *__r
 }
 
 // One CTA per utterance: inclusive scan of the durations in shared memory, then the rows.
-template <typename T>
-__global__ void __launch_bounds__(256) generate_path_kernel(const int *__restrict__ durations,
+// D = int: integer durations.  D = float: the reference's float durations (w_ceil * length_scale,
+// model/face_tts.py:118-119): cumsum in index order with a double accumulator rounded to fp32 per element (what
+// torch.cumsum does on the CPU; its CUDA scan associates differently, within an fp32 rounding), and since the
+// reference tests `t < cum` on integer t (sequence_mask, model/utils.py:10), token x owns [ceil(cum[x-1]), ceil(cum[x])).
+template <typename T, typename D>
+__global__ void __launch_bounds__(256) generate_path_kernel(const D *__restrict__ durations,
                                                             const int *__restrict__ t_x, const int *__restrict__ t_y,
-                                                            int Tx, int Ty, T *__restrict__ path) {
+                                                            int Tx, int Ty, T *__restrict__ path,
+                                                            int *__restrict__ frame_token) {
     extern __shared__ int sm[];
     int *start_s = sm;          // [Tx]
     int *dur_s = sm + Tx;       // [Tx]
@@ -61,18 +66,33 @@ __global__ void __launch_bounds__(256) generate_path_kernel(const int *__restric
     const int tx = min(max(t_x[b], 0), Tx), ty = min(max(t_y[b], 0), Ty);
     if (threadIdx.x == 0) {
         // Tx is a few hundred: a serial scan costs less than the dense write that follows
-        long long cum = 0;
+        double acc = 0.0;
+        long long e_prev = 0;
         for (int x = 0; x < Tx; ++x) {
-            const long long d = max(durations[(size_t)b * Tx + x], 0);
-            const long long s = cum < ty ? cum : ty;
-            cum += d;
-            const long long e = cum < ty ? cum : ty;           // sequence_mask(cum, t_y) then * mask
+            acc += (double)durations[(size_t)b * Tx + x];
+            const D cum = (D)acc;
+            long long e;
+            if (sizeof(D) == sizeof(float) && !(cum == cum)) e = 0;                 // NaN: `t < nan` is false
+            else if ((double)cum >= (double)ty) e = ty;
+            else if ((double)cum <= 0.0) e = 0;
+            else e = (long long)ceil((double)cum);                                  // sequence_mask(cum, t_y)
+            // path = mask(cum[x]) - mask(cum[x-1]): ones on [e_prev, e); a negative duration would give -1s in
+            // the reference, which no caller produces (durations are ceil(exp(.)) >= 0) -- clamped to empty here
+            const long long s = e_prev < e ? e_prev : e;
             start_s[x] = (int)s;
-            dur_s[x] = (x < tx) ? (int)(e - s) : 0;
+            dur_s[x] = (x < tx) ? (int)(e - s) : 0;                                 // * mask
+            e_prev = e > e_prev ? e : e_prev;
         }
     }
     __syncthreads();
-    write_path_rows<T>(path + (size_t)b * Tx * Ty, start_s, dur_s, Tx, Ty, threadIdx.x, blockDim.x);
+    if (path != nullptr) write_path_rows<T>(path + (size_t)b * Tx * Ty, start_s, dur_s, Tx, Ty, threadIdx.x, blockDim.x);
+    if (frame_token != nullptr) {
+        int *ft = frame_token + (size_t)b * Ty;
+        for (int t = threadIdx.x; t < Ty; t += blockDim.x) ft[t] = -1;
+        __syncthreads();
+        for (int x = threadIdx.x; x < Tx; x += blockDim.x)
+            for (int t = start_s[x], e = start_s[x] + dur_s[x]; t < e; ++t) ft[t] = x;
+    }
 }
 
 }  // namespace
@@ -98,17 +118,26 @@ int launch_lengths_from_mask(const float *mask, int B, int Tx, int Ty, int *t_x,
     return MAS_B200_OK;
 }
 
-int launch_generate_path(const int *durations, const int *t_x, const int *t_y, int B, int Tx, int Ty, void *path,
-                         int path_dtype, cudaStream_t stream) {
-    if (!durations || !t_x || !t_y || !path || B <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+int launch_generate_path(const void *durations, int dur_is_float, const int *t_x, const int *t_y, int B, int Tx, int Ty,
+                         void *path, int path_dtype, int *frame_token, cudaStream_t stream) {
+    if (!durations || !t_x || !t_y || B <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    if (path_dtype != MAS_B200_PATH_NONE && path_dtype != MAS_B200_PATH_F32 && path_dtype != MAS_B200_PATH_I32)
+        return MAS_B200_ERR_ARG;
+    if (path_dtype != MAS_B200_PATH_NONE && !path) return MAS_B200_ERR_ARG;
+    if (path_dtype == MAS_B200_PATH_NONE && !frame_token) return MAS_B200_ERR_ARG;
     const size_t smem = sizeof(int) * 2 * (size_t)Tx;
     if (smem > 48 * 1024) return MAS_B200_ERR_UNSUPPORTED;
-    if (path_dtype == MAS_B200_PATH_F32)
-        generate_path_kernel<float><<<B, 256, smem, stream>>>(durations, t_x, t_y, Tx, Ty, static_cast<float *>(path));
-    else if (path_dtype == MAS_B200_PATH_I32)
-        generate_path_kernel<int><<<B, 256, smem, stream>>>(durations, t_x, t_y, Tx, Ty, static_cast<int *>(path));
-    else
-        return MAS_B200_ERR_ARG;
+    float *pf = path_dtype == MAS_B200_PATH_F32 ? static_cast<float *>(path) : nullptr;
+    int *pi = path_dtype == MAS_B200_PATH_I32 ? static_cast<int *>(path) : nullptr;
+    if (dur_is_float) {
+        auto *d = static_cast<const float *>(durations);
+        if (pi) generate_path_kernel<int, float><<<B, 256, smem, stream>>>(d, t_x, t_y, Tx, Ty, pi, frame_token);
+        else generate_path_kernel<float, float><<<B, 256, smem, stream>>>(d, t_x, t_y, Tx, Ty, pf, frame_token);
+    } else {
+        auto *d = static_cast<const int *>(durations);
+        if (pi) generate_path_kernel<int, int><<<B, 256, smem, stream>>>(d, t_x, t_y, Tx, Ty, pi, frame_token);
+        else generate_path_kernel<float, int><<<B, 256, smem, stream>>>(d, t_x, t_y, Tx, Ty, pf, frame_token);
+    }
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

@@ -20,9 +20,19 @@ constexpr int kRows = 4;          // feature rows per CTA: independent loads in 
 constexpr int kThreads = 256;
 
 // rows of one utterance: src/dst [F, T] with `valid` leading elements per row to copy, the rest zero-filled
+// 16-byte load from mapped host memory; hint = 1 asks L2 for 256-byte fetches (fewer, larger PCIe read requests)
+__device__ __forceinline__ float4 ld_host16(const float4 *p, int hint) {
+    float4 v;
+    if (hint)
+        asm volatile("ld.global.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else
+        asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 template <int VEC>
 __device__ __forceinline__ void pull_rows(const float *__restrict__ src, float *__restrict__ dst, int f0, int F, int T,
-                                          int valid) {
+                                          int valid, int hint) {
     if (VEC == 4) {
         const int nvec = T >> 2;
         for (int i = threadIdx.x; i < nvec; i += kThreads) {
@@ -32,7 +42,7 @@ __device__ __forceinline__ void pull_rows(const float *__restrict__ src, float *
             for (int k = 0; k < kRows; ++k) {
                 v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (f0 + k < F && c < valid)     // the only PCIe reads: 16 bytes, all rows issued before any store
-                    v[k] = __ldcs(reinterpret_cast<const float4 *>(src + (size_t)(f0 + k) * T + c));
+                    v[k] = ld_host16(reinterpret_cast<const float4 *>(src + (size_t)(f0 + k) * T + c), hint);
             }
 #pragma unroll
             for (int k = 0; k < kRows; ++k) {
@@ -60,7 +70,7 @@ __global__ void __launch_bounds__(kThreads) upload_batch_kernel(const float *__r
                                                                 const int *__restrict__ tx_h, const int *__restrict__ ty_h,
                                                                 int B, int F, int Tx, int Ty, float *__restrict__ mu_d,
                                                                 float *__restrict__ y_d, int *__restrict__ tx_d,
-                                                                int *__restrict__ ty_d) {
+                                                                int *__restrict__ ty_d, int hint) {
     // Persistent, one small CTA per SM: it only has to keep PCIe busy (a few hundred KB in flight), and it must
     // leave the thread slots of every SM to the alignment kernels of the previous step running beside it.
     const int groups = (F + kRows - 1) / kRows;
@@ -68,8 +78,21 @@ __global__ void __launch_bounds__(kThreads) upload_batch_kernel(const float *__r
         const int b = item / groups, f0 = (item - b * groups) * kRows;
         const int tx = tx_h[b], ty = ty_h[b];      // 8 bytes over PCIe per item
         if (f0 == 0 && threadIdx.x == 0) { tx_d[b] = tx; ty_d[b] = ty; }
-        pull_rows<VECY>(y_h + (size_t)b * F * Ty, y_d + (size_t)b * F * Ty, f0, F, Ty, min(max(ty, 0), Ty));
-        pull_rows<VECX>(mu_h + (size_t)b * F * Tx, mu_d + (size_t)b * F * Tx, f0, F, Tx, min(max(tx, 0), Tx));
+        pull_rows<VECY>(y_h + (size_t)b * F * Ty, y_d + (size_t)b * F * Ty, f0, F, Ty, min(max(ty, 0), Ty), hint);
+        pull_rows<VECX>(mu_h + (size_t)b * F * Tx, mu_d + (size_t)b * F * Tx, f0, F, Tx, min(max(tx, 0), Tx), hint);
+    }
+}
+
+// zero-fill of the padding only: elements [valid, T) of every row (copy-engine variant; lengths from the mapped host arrays)
+__global__ void __launch_bounds__(kThreads) zero_padding_kernel(const int *__restrict__ tx_h, const int *__restrict__ ty_h,
+                                                                int B, int F, int Tx, int Ty, float *__restrict__ mu_d,
+                                                                float *__restrict__ y_d) {
+    for (int row = blockIdx.x; row < B * F; row += gridDim.x) {
+        const int b = row / F;
+        const int tx = min(max(tx_h[b], 0), Tx), ty = min(max(ty_h[b], 0), Ty);
+        float *yr = y_d + (size_t)row * Ty, *mr = mu_d + (size_t)row * Tx;
+        for (int t = ty + threadIdx.x; t < Ty; t += kThreads) yr[t] = 0.f;
+        for (int t = tx + threadIdx.x; t < Tx; t += kThreads) mr[t] = 0.f;
     }
 }
 
@@ -98,6 +121,26 @@ int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const i
     if (!device_view(mu_x_pinned, &mu_v) || !device_view(y_pinned, &y_v) || !device_view(t_xs_pinned, &tx_v) ||
         !device_view(t_ys_pinned, &ty_v))
         return MAS_B200_ERR_ARG;      // the host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)
+    if (option("upload_impl") == 2) {
+        // Copy-engine variant: one pitched 2-D copy per utterance and tensor (F rows of t_y / t_x valid floats), the
+        // padding zero-filled by a small kernel.  DMA reads move ~50 GB/s over PCIe gen5 where SM-issued zero-copy
+        // loads reach ~40 GB/s, at the price of 2B+2 driver calls per batch on the host.
+        zero_padding_kernel<<<std::min(B * F, 4 * di.sm_count), kThreads, 0, stream>>>(
+            static_cast<const int *>(tx_v), static_cast<const int *>(ty_v), B, F, Tx, Ty, mu_x_dev, y_dev);
+        MASB200_CUDA_TRY(cudaGetLastError());
+        for (int b = 0; b < B; ++b) {
+            const size_t tx = (size_t)std::min(std::max(t_xs_pinned[b], 0), Tx), ty = (size_t)std::min(std::max(t_ys_pinned[b], 0), Ty);
+            if (ty)
+                MASB200_CUDA_TRY(cudaMemcpy2DAsync(y_dev + (size_t)b * F * Ty, sizeof(float) * Ty, y_pinned + (size_t)b * F * Ty,
+                                                   sizeof(float) * Ty, sizeof(float) * ty, (size_t)F, cudaMemcpyHostToDevice, stream));
+            if (tx)
+                MASB200_CUDA_TRY(cudaMemcpy2DAsync(mu_x_dev + (size_t)b * F * Tx, sizeof(float) * Tx, mu_x_pinned + (size_t)b * F * Tx,
+                                                   sizeof(float) * Tx, sizeof(float) * tx, (size_t)F, cudaMemcpyHostToDevice, stream));
+        }
+        MASB200_CUDA_TRY(cudaMemcpyAsync(t_x_dev, t_xs_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+        MASB200_CUDA_TRY(cudaMemcpyAsync(t_y_dev, t_ys_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+        return MAS_B200_OK;
+    }
     const bool vx = (Tx % 4 == 0) && al16(mu_v) && al16(mu_x_dev);
     const bool vy = (Ty % 4 == 0) && al16(y_v) && al16(y_dev);
     const long long items = (long long)B * ((F + kRows - 1) / kRows);
@@ -107,14 +150,26 @@ int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const i
     auto *yy = static_cast<const float *>(y_v);
     auto *txp = static_cast<const int *>(tx_v);
     auto *typ = static_cast<const int *>(ty_v);
+    // The alignment kernels of the previous step run beside this one and need (almost) all of an SM's shared
+    // memory; an SM only changes its L1/shared split when idle, so this kernel asks for the same split -- otherwise
+    // its persistent CTAs would keep every SM in the small-shared configuration and the two would serialise.
+    static const bool carveout_set = [] {
+        cudaFuncSetAttribute(upload_batch_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(upload_batch_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(upload_batch_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(upload_batch_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return true;
+    }();
+    (void)carveout_set;
+    const int hint = option("upload_l2_256b");
     if (vx && vy)
-        upload_batch_kernel<4, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+        upload_batch_kernel<4, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
     else if (vy)
-        upload_batch_kernel<1, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+        upload_batch_kernel<1, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
     else if (vx)
-        upload_batch_kernel<4, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+        upload_batch_kernel<4, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
     else
-        upload_batch_kernel<1, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+        upload_batch_kernel<1, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

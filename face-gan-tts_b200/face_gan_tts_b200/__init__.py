@@ -11,6 +11,7 @@ from .alignment import (  # noqa: F401
     AlignmentResult,
     align,
     durations_to_logw,
+    expand_durations,
     generate_path,
     log_prior,
     log_prior_maximum_path,
@@ -29,6 +30,6 @@ from .losses import (  # noqa: F401
 
 __all__ = [
     "monotonic_align", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
-    "durations_to_logw", "upload_batch", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
+    "durations_to_logw", "expand_durations", "upload_batch", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
     "duration_loss", "gather_mu_y", "prior_loss", "sequence_mask",
 ]

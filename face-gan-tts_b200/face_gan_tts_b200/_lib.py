@@ -37,6 +37,8 @@ SIGNATURES = {
                                                 c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_size_t, c_int, c_void_p]),
     "mas_b200_generate_path": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mas_b200_generate_path_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                           c_void_p]),
     "mas_b200_sequence_mask": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mas_b200_crop_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -177,21 +177,54 @@ def log_prior_maximum_path(mu_x: torch.Tensor, y: torch.Tensor, x_lengths, y_len
     return AlignmentResult(path, dur, ft, status)
 
 
-def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+def generate_path(duration: torch.Tensor, mask: torch.Tensor, *, return_index: bool = False):
     """Drop-in for reference model/utils.py:27-40 generate_path(duration, mask):
-    duration [B,Tx] (integer-valued), mask [B,Tx,Ty] prefix mask -> path [B,Tx,Ty] in mask.dtype."""
+    duration [B,Tx] (float as at the call site face_tts.py:126, or integer), mask [B,Tx,Ty] prefix mask
+    -> path [B,Tx,Ty] in mask.dtype.  `return_index=True` also returns frame_token [B,Ty] int32."""
     _need_cuda(duration, "duration")
     _need_cuda(mask, "mask")
     B, Tx, Ty = mask.shape
     dev = mask.device
     t_x, t_y = lengths_from_mask(mask)
     with torch.cuda.device(dev):
-        d = duration.detach().to(torch.int32).contiguous()
         path = torch.empty((B, Tx, Ty), dtype=torch.float32, device=dev)
-        rc = _lib.lib().mas_b200_generate_path(d.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), B, Tx, Ty,
-                                               path.data_ptr(), _lib.PATH_F32, _stream_ptr(dev))
+        ft = torch.empty((B, Ty), dtype=torch.int32, device=dev) if return_index else None
+        if duration.dtype.is_floating_point:
+            d = duration.detach().to(torch.float32).contiguous()
+            rc = _lib.lib().mas_b200_generate_path_f32(d.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), B, Tx, Ty,
+                                                       path.data_ptr(), _lib.PATH_F32,
+                                                       ft.data_ptr() if ft is not None else None, _stream_ptr(dev))
+        else:
+            d = duration.detach().to(torch.int32).contiguous()
+            rc = _lib.lib().mas_b200_generate_path(d.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), B, Tx, Ty,
+                                                   path.data_ptr(), _lib.PATH_F32, _stream_ptr(dev))
+            if rc == 0 and ft is not None:
+                rc = _lib.lib().mas_b200_generate_path_f32(d.to(torch.float32).data_ptr(), t_x.data_ptr(), t_y.data_ptr(),
+                                                           B, Tx, Ty, None, _lib.PATH_NONE, ft.data_ptr(), _stream_ptr(dev))
         _lib.check(rc, "mas_b200_generate_path")
-    return path if mask.dtype == torch.float32 else path.to(mask.dtype)
+    path = path if mask.dtype == torch.float32 else path.to(mask.dtype)
+    return (path, ft) if return_index else path
+
+
+def expand_durations(mu_x: torch.Tensor, duration: torch.Tensor, x_lengths, y_lengths, Ty: int):
+    """The inference-side expansion of reference model/face_tts.py:124-129 without the dense path:
+    float durations [B,Tx] -> (mu_y [B,F,Ty], frame_token [B,Ty]); mu_y[:,:,t] = mu_x[:,:,token of frame t]."""
+    _need_cuda(mu_x, "mu_x")
+    B, F, Tx = mu_x.shape
+    dev = mu_x.device
+    with torch.cuda.device(dev):
+        t_x = _lengths(x_lengths, B, dev, "x_lengths")
+        t_y = _lengths(y_lengths, B, dev, "y_lengths")
+        d = duration.detach().reshape(B, Tx).to(torch.float32).contiguous()
+        mx = mu_x.detach().to(torch.float32).contiguous()
+        ft = torch.empty((B, Ty), dtype=torch.int32, device=dev)
+        mu_y = torch.empty((B, F, Ty), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        _lib.check(L.mas_b200_generate_path_f32(d.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), B, Tx, Ty, None,
+                                                _lib.PATH_NONE, ft.data_ptr(), _stream_ptr(dev)), "mas_b200_generate_path_f32")
+        _lib.check(L.mas_b200_gather_mu_y(mx.data_ptr(), ft.data_ptr(), B, F, Tx, Ty, mu_y.data_ptr(), _stream_ptr(dev)),
+                   "mas_b200_gather_mu_y")
+    return mu_y, ft
 
 
 def upload_batch(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *,

@@ -148,6 +148,16 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,
  */
 int mas_b200_generate_path(const int *durations_dev, const int *t_x_dev, const int *t_y_dev,
                            int B, int Tx, int Ty, void *path_dev, int path_dtype, void *stream);
+/*
+ * Same with the reference's FLOAT durations (w_ceil * length_scale, model/face_tts.py:118-119,126): the
+ * cumulative sum is taken in fp32 in index order, and `t < cum` on integer t (model/utils.py:10) makes token x
+ * own the frames [ceil(cum[x-1]), ceil(cum[x])).  Optionally also (or only: path_dtype MAS_B200_PATH_NONE,
+ * path_dev NULL) emits the index form frame_token [B,Ty] (-1 where no token), from which
+ * mas_b200_gather_mu_y builds the mu_y of model/face_tts.py:128-129 without the dense path.
+ */
+int mas_b200_generate_path_f32(const float *durations_dev, const int *t_x_dev, const int *t_y_dev,
+                               int B, int Tx, int Ty, void *path_dev, int path_dtype,
+                               int *frame_token_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * Consumers of the alignment inside FaceTTS.compute_loss (SURVEY.md section 8

@@ -39,7 +39,7 @@ def _case(fx, name):
 
 
 def _rel(a, b):
-    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+    return abs(float(a.detach() if hasattr(a, "detach") else a) - float(b)) / max(abs(float(b)), 1e-30)
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -21,7 +21,7 @@ def rel_err(a, b):
     return ((a.double() - b.double()).abs() / b.double().abs().clamp_min(1e-30)).max().item()
 
 
-IMPLS = ["ffma", "auto"]       # "auto" = tcgen05/TMEM kernel where it covers the shape (F in {64,80,96}, Tx <= 256), else FFMA
+IMPLS = ["ffma", "auto"]       # "auto" = tcgen05/TMEM kernel where it covers the shape (F in {64,80,96,128}, Tx <= 256), else FFMA
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -133,26 +133,28 @@ def test_tcgen05_kernel_is_the_one_running_and_matches_ffma():
     accuracy), unsupported ones raise.  Against the FFMA kernel the two agree far inside the 1e-4 bar."""
     from face_gan_tts_b200 import _lib
 
-    for (B, F, Tx, Ty) in [(3, 80, 190, 1000), (2, 64, 129, 136), (2, 96, 256, 420), (5, 80, 37, 68)]:
+    # F = 128 (the reference default n_feats) runs the split-M form: one CTA per 128-row M-tile
+    for (B, F, Tx, Ty) in [(3, 80, 190, 1000), (2, 64, 129, 136), (2, 96, 256, 420), (5, 80, 37, 68),
+                           (3, 128, 190, 1000), (2, 128, 256, 420), (4, 128, 61, 200), (2, 128, 128, 132), (1, 128, 129, 132)]:
         mu_x, y, _, _ = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=7, tx_lo=max(1, Tx // 3), ty_lo=max(Tx // 3, Ty // 3))
         mu_d, y_d = mu_x.to(DEV), y.to(DEV)
         tc = fgt.log_prior(mu_d, y_d, impl="tcgen05")
         ff = fgt.log_prior(mu_d, y_d, impl="ffma")
         ref64 = oracle.log_prior_direct(mu_d, y_d)
         assert rel_err(tc, ref64) < 2e-6 and rel_err(tc, ff) < 2e-6
-    mu_x, y, _, _ = synthetic.lrs2_batch(B=2, F=128, Tx=190, Ty=1000, seed=7)
+    mu_x, y, _, _ = synthetic.lrs2_batch(B=2, F=72, Tx=190, Ty=1000, seed=7)
     with pytest.raises(_lib.MasB200Error):
-        fgt.log_prior(mu_x.to(DEV), y.to(DEV), impl="tcgen05")          # F = 128: 4F + 128 TMEM columns do not fit
+        fgt.log_prior(mu_x.to(DEV), y.to(DEV), impl="tcgen05")          # n_feats not instantiated: raises, no fallback
 
 
-@pytest.mark.parametrize("B", [3, 32, 80])
-def test_overlapped_pipeline_equals_serial_pipeline(B):
+@pytest.mark.parametrize("B,F", [(3, 80), (32, 80), (80, 80), (3, 128), (32, 128), (49, 128), (50, 128)])
+def test_overlapped_pipeline_equals_serial_pipeline(B, F):
     """mas_b200_log_prior_maximum_path: the overlapped log-prior || MAS pipeline (device flags, dense path written
     by the log-prior CTAs; taken for 2*B <= SM count) and the serial one (fused_impl=1; also what B=80 gets) must
     produce identical outputs -- same kernels, same arithmetic, only the scheduling differs."""
     from face_gan_tts_b200 import _lib
 
-    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=80, Tx=190, Ty=1000, seed=11)
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=190, Ty=1000, seed=11)      # F = 128: split-M, counting flags
     mu_d, y_d = mu_x.to(DEV), y.to(DEV)
     outs = []
     for mode in (0, 1):
@@ -188,8 +190,15 @@ def test_overlapped_pipeline_rejects_bad_items_without_hanging():
 # ---------------------------------------------------------------------------------------------
 # ragged zero-copy upload (mas_b200_upload_batch): the e2e path's host -> device transfer
 # ---------------------------------------------------------------------------------------------
+@pytest.fixture(params=[1, 2], ids=["sm_zero_copy_pull", "copy_engine_2d"])
+def upload_impl(request):
+    prev = fgt._lib.set_option("upload_impl", request.param)
+    yield request.param
+    fgt._lib.set_option("upload_impl", prev)
+
+
 @pytest.mark.parametrize("B,F,Tx,Ty", [(32, 80, 190, 1000), (5, 128, 64, 256), (3, 7, 33, 101), (2, 80, 1, 4)])
-def test_upload_batch_equals_a_plain_copy_of_padded_inputs(B, F, Tx, Ty):
+def test_upload_batch_equals_a_plain_copy_of_padded_inputs(B, F, Tx, Ty, upload_impl):
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, Tx, Ty, seed=77, tx_lo=1, ty_lo=max(1, Ty // 3))
     # garbage in the padding of the HOST buffers: the device tensors must still be zero-padded
     g = torch.Generator().manual_seed(1)

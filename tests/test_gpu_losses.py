@@ -50,7 +50,7 @@ def _gpu_path(mu_x, y, t_x, t_y):
 
 
 def _rel(a, b):
-    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+    return abs(float(a.detach() if hasattr(a, "detach") else a) - float(b)) / max(abs(float(b)), 1e-30)
 
 
 def test_sequence_mask_bit_exact():

@@ -261,6 +261,36 @@ def test_generate_path_matches_reference_expression():
     assert out.dtype == mask.dtype and torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("length_scale", [1.0, 1.1, 0.77])
+def test_inference_expansion_matches_reference_forward(length_scale):
+    """reference model/face_tts.py:118-129 (w_ceil * length_scale -> y_lengths -> generate_path -> mu_y), with the
+    reference's generate_path / sequence_mask restated by the oracle on the CPU (sequential fp32 cumsum)."""
+    g = torch.Generator().manual_seed(11)
+    B, F, Tx = 5, 80, 37
+    t_x = torch.tensor([37, 12, 1, 30, 25])
+    x_mask = (torch.arange(Tx)[None, :] < t_x[:, None]).float().unsqueeze(1)
+    logw = torch.randn(B, 1, Tx, generator=g) * 0.8 + 0.7
+    mu_x = torch.randn(B, F, Tx, generator=g) * x_mask
+    w_ceil = torch.ceil(torch.exp(logw) * x_mask) * length_scale                       # :118-119
+    y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()                    # :120
+    Ty = int(y_lengths.max())
+    Ty += (-Ty) % 4                                                                      # fix_len_compatibility :122
+    y_mask = oracle.sequence_mask(y_lengths, Ty).unsqueeze(1).to(x_mask.dtype)          # :124
+    attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)                               # :125
+    ref_attn = oracle.generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1))             # :126
+    ref_mu_y = torch.matmul(ref_attn.transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)   # :128-129
+    path, ft = fgt.generate_path(w_ceil.squeeze(1).to(DEV), attn_mask.squeeze(1).to(DEV), return_index=True)
+    assert torch.equal(path.cpu(), ref_attn)
+    mu_y, ft2 = fgt.expand_durations(mu_x.to(DEV), w_ceil.to(DEV), t_x, y_lengths, Ty)
+    assert torch.equal(ft, ft2) and torch.equal(mu_y.cpu(), ref_mu_y)
+    onehot = torch.zeros(B, Tx, Ty)
+    for b in range(B):
+        for t in range(Ty):
+            if ft[b, t] >= 0:
+                onehot[b, ft[b, t], t] = 1
+    assert torch.equal(onehot, ref_attn)
+
+
 def test_durations_to_logw_matches_dense_expression(kats):
     value, t_x, t_y = cases.CASES["lrs2_shape"]()
     res = run_align(value, t_x, t_y, path_dtype=torch.float32)
