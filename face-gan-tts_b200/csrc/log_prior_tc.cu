@@ -42,10 +42,13 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     LpFront S;
     S.carve(smem_raw, F);
-    // [F][Tx] staging of mu_x.  Split-M (F = 128: 128 KB of operand buffers) parks it in the hi/lo operand buffers,
+    // [F][Tx] staging of mu_x: parked in the hi/lo operand buffers (4 * F * 64 * 4 bytes >= F * Tx * 4 for Tx <= 256),
     // which nothing writes before every aux thread has left the prologue.
-    float *mu_s = SPLITM ? reinterpret_cast<float *>(S.hi)
-                         : reinterpret_cast<float *>(smem_raw + ((LpFrontSmem::total(F) + 127) / 128) * 128);
+    float *mu_s = reinterpret_cast<float *>(S.hi);
+    // epilogue staging: per (M-tile, 32-frame half) a [128 rows][32 frames] fp32 box, 16-byte chunks XOR-swizzled by
+    // row & 7 -- written row-per-thread (what tcgen05.ld hands out) and read back row-per-quarter-warp, both
+    // conflict-free, so that every global store instruction covers whole 128-byte row segments.
+    unsigned char *stage = smem_raw + ((LpFrontSmem::total(F) + 127) / 128) * 128;
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
@@ -72,7 +75,7 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     } else {
         float musq[2];
         lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [mt0](int mt, int m) { return (mt0 + mt) * 128 + m; }, musq);
-        if (SPLITM) lp_aux_bar();          // mu_s aliases the operand buffers the first split is about to fill
+        lp_aux_bar();                      // mu_s aliases the operand buffers the first split is about to fill
         float *outb = P.out + (size_t)b * P.Tx * P.Ty;
         for (int g = 0; g <= ng; ++g) {
             if (g < ng) lp_aux_split<KS>(S, g, tid, warp, lane);
@@ -83,13 +86,14 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                 const int t0 = gidx * kLpGroup;
                 uint32_t d0[2][32], d1[2][32];
                 lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1, MTMAX);
+                lp_aux_bar();                                   // every warp is done reading the previous group's boxes
 #pragma unroll
                 for (int mt = 0; mt < MTMAX; ++mt) {
                     const int x = (mt0 + mt) * 128 + tid;
                     if (mt < MT && x < P.Tx) {
-                        float *dst = outb + (size_t)x * P.Ty + t0;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
+                            unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384 + (size_t)tid * 128;
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
                                 const float4 yq = *reinterpret_cast<const float4 *>(S.ysq + p * 64 + 32 * h + 4 * c);
@@ -99,7 +103,30 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                                 o.y = ((yq.y + __uint_as_float(r[1])) + musq[mt]) + P.cst;
                                 o.z = ((yq.z + __uint_as_float(r[2])) + musq[mt]) + P.cst;
                                 o.w = ((yq.w + __uint_as_float(r[3])) + musq[mt]) + P.cst;
-                                if (t0 + 32 * h + 4 * c + 3 < P.Ty) __stcs(reinterpret_cast<float4 *>(dst + 32 * h + 4 * c), o);   // Ty % 4 == 0
+                                *reinterpret_cast<float4 *>(box + ((c ^ (tid & 7)) << 4)) = o;
+                            }
+                        }
+                    }
+                }
+                lp_aux_bar();
+                {
+                    const int c16 = lane & 7, rsub = lane >> 3;
+#pragma unroll
+                    for (int mt = 0; mt < MTMAX; ++mt) {
+                        if (mt >= MT) break;
+                        const int xb = (mt0 + mt) * 128;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384;
+                            const int t = t0 + 32 * h + 4 * c16;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = (i * 4 + warp) * 4 + rsub;
+                                const int x = xb + r;
+                                if (x < P.Tx && t + 3 < P.Ty) {                       // Ty % 4 == 0
+                                    const float4 o = *reinterpret_cast<const float4 *>(box + r * 128 + ((c16 ^ (r & 7)) << 4));
+                                    __stcs(reinterpret_cast<float4 *>(outb + (size_t)x * P.Ty + t), o);
+                                }
                             }
                         }
                     }
@@ -235,7 +262,7 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     chunks = (P.ngroups + P.groups_per_cta - 1) / P.groups_per_cta;
     P.chunks = chunks;
     P.strided = flags != nullptr ? 1 : 0;
-    size_t smem = ((LpFrontSmem::total(F) + 127) / 128) * 128 + (splitm ? 0 : (size_t)F * Tx * 4) + 1024;
+    size_t smem = ((LpFrontSmem::total(F) + 127) / 128) * 128 + (size_t)(splitm ? 1 : 2) * 32768 + 1024;
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;   // > half an SM: one CTA per SM (each allocates all of TMEM)
 
     void (*kern)(const LpTcParams, const CUtensorMap) = nullptr;

@@ -108,9 +108,8 @@ def test_cuda_block_reproduces_the_reference_compute_loss(fx, name):
     # 3. fully fused (GPU log-prior): end-to-end agreement with the reference
     fused = losses.alignment_losses(g["mu_x"], g["logw"], t_x, g["y"], t_y, out_size=d["out_size"], out_offset=off,
                                     dense_path=True)
-    valid = torch.from_numpy(d["attn_mask"]).sum().item()
-    differ = float(np.abs(fused.alignment.path.cpu().numpy() - d["attn"]).sum()) / 2.0
-    assert differ / max(valid ** 0.5, 1) >= 0 and differ <= 0.005 * float(t_y.sum())
+    differ = float(np.abs(fused.alignment.path.cpu().numpy() - d["attn"]).sum()) / 2.0      # frames on another token
+    assert differ <= 0.005 * float(t_y.sum())
     assert _rel(fused.dur_loss, d["dur_loss"]) < 1e-3 and _rel(fused.prior_loss, d["prior_loss"]) < 1e-3
     lp = fgt.log_prior(g["mu_x"], g["y"])
     m = g["attn_mask"] > 0
