@@ -28,6 +28,7 @@ Opt g_opts[] = {
     {"mas_debug_ptr_hi", {0}},
     {"lp_debug_ptr_lo", {0}},        // diagnostics only: [ctas][4] globaltimer stamps of the tcgen05 log-prior kernel
     {"lp_debug_ptr_hi", {0}},
+    {"lp_debug_skip", {0}},          // diagnostics only: phases of the tcgen05 log-prior kernel to skip (results invalid)
     {"lp_impl", {0}},                // default log-prior implementation for MAS_B200_LP_AUTO
     {"upload_impl", {0}},            // 0/1 SM zero-copy pull kernel, 2 copy engine (one 2-D copy per utterance and tensor)
     {"upload_l2_256b", {0}},         // 1: zero-copy loads carry the L2::256B fetch hint

@@ -1,6 +1,6 @@
 // log_prior_tc.cu -- Grad-TTS log-prior on the 5th-generation tensor cores (tcgen05 + TMEM), unfused:
 // the front end of lp_tc_frontend.cuh with an epilogue that streams [B,Tx,Ty] to HBM.
-// One CTA = one utterance x a run of 64-frame groups; warps 0-3 aux/epilogue, warp 4 TMA + MMA issue.
+// One CTA = one utterance x a run of 64-frame groups; warps 0-3 epilogue, warps 4-7 operand split, warp 8 TMA + MMA issue.
 #include <atomic>
 #include <cstring>
 
@@ -16,7 +16,7 @@ float log_prior_const(int F);   // log_prior_ffma.cu
 
 namespace {
 
-constexpr int kTcThreads = 160;
+constexpr int kTcThreads = 288;        // warps 0-3 epilogue, 4-7 split, 8 TMA + MMA issue
 constexpr int kMaxF = 96;             // 4F (A hi/lo, two M-tiles) + 128 (D) <= 512 columns; beyond: split-M (2F + 64)
 
 struct LpTcParams {
@@ -28,8 +28,9 @@ struct LpTcParams {
     int chunks;          // CTAs per utterance
     int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
     PathJob job;         // optional: expand the dense path of utterance b once the MAS kernel reports it done
-    long long *dbg;      // diagnostics: [ctas][4] globaltimer stamps
+    long long *dbg;      // diagnostics: [ctas][32] globaltimer stamps / wait-cycle accumulators
     int *flags;          // optional [B][flag_pitch]: counts the M-tile CTAs that have a 64-frame group of an utterance
+    int skip;            // diagnostics (option lp_debug_skip): 1 no global stores, 2 no MMA issue, 4 no split math, 8 no staging
     int flag_pitch;      //   in memory (1 when a CTA holds both M-tiles; split-M: ready at ceil(Tx/128))
 };
 
@@ -61,7 +62,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     const int MT = SPLITM ? 1 : (P.Tx + 127) >> 7;                           // M-tiles of 128 text positions in this CTA
     const int mt0 = SPLITM ? (int)blockIdx.z : 0;
 
-    long long *dbg = P.dbg ? P.dbg + ((size_t)b * gridDim.x + blockIdx.x) * 4 : nullptr;
+    long long *dbg = P.dbg ? P.dbg + ((size_t)(blockIdx.z * gridDim.y + b) * gridDim.x + blockIdx.x) * 32 : nullptr;
+    S.prof = dbg;
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[0] = t; }
     if (tid == 0) { S.init_barriers(); mbar_fence_init(); }
     if (warp == 0) { __syncwarp(); tmem_alloc(S.tmem_slot, kLpTmemCols); tmem_relinquish(); }
@@ -70,27 +72,37 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(kFullMask, *S.tmem_slot, 0);
 
-    if (warp == 4) {
-        lp_mma_warp<KS, MTMAX>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng, MT, tmem);
+    if (warp == 8) {
+        lp_mma_warp<KS, MTMAX>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng,
+                               (P.skip & 2) ? 0 : MT, tmem);
+    } else if (warp >= 4) {
+        // ---- split warps: raw y group -> hi/lo K-major operands + ysq.  mu_s aliases the operand buffers, which
+        // may be filled once every epilogue thread has left the prologue (bar_aready).
+        mbar_wait(S.bar_aready, 0);
+        const long long cs0 = clock64();
+        for (int g = 0; g < ng; ++g) lp_aux_split<KS>(S, g, tid - 128, warp - 4, lane, (P.skip & 4) != 0);
+        if (dbg && tid == 128) dbg[9] = clock64() - cs0;
     } else {
         float musq[2];
         lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [mt0](int mt, int m) { return (mt0 + mt) * 128 + m; }, musq);
-        lp_aux_bar();                      // mu_s aliases the operand buffers the first split is about to fill
         float *outb = P.out + (size_t)b * P.Tx * P.Ty;
-        for (int g = 0; g <= ng; ++g) {
-            if (g < ng) lp_aux_split<KS>(S, g, tid, warp, lane);
-            if (g >= 1) {
+        if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[4] = t; }
+        if (dbg && tid == 0) dbg[3] = clock64();
+        for (int g = 1; g <= ng; ++g) {
+            {
                 // ---- epilogue of group g-1: thread = text position, 64 consecutive frames per M-tile
-                const int gg = g - 1, p = gg & 1;
+                const int gg = g - 1, p = gg & 3;
                 const int gidx = g0 + gg * gs;
                 const int t0 = gidx * kLpGroup;
                 uint32_t d0[2][32], d1[2][32];
+                long long cseg = clock64();
                 lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1, MTMAX);
-                lp_aux_bar();                                   // every warp is done reading the previous group's boxes
+                if (dbg && tid == 0) { const long long c = clock64(); dbg[16] += c - cseg; cseg = c; }
+                lp_epi_bar();                                   // every warp is done reading the previous group's boxes
 #pragma unroll
                 for (int mt = 0; mt < MTMAX; ++mt) {
                     const int x = (mt0 + mt) * 128 + tid;
-                    if (mt < MT && x < P.Tx) {
+                    if (mt < MT && x < P.Tx && !(P.skip & 8)) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384 + (size_t)tid * 128;
@@ -108,7 +120,9 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                         }
                     }
                 }
-                lp_aux_bar();
+                if (dbg && tid == 0) { const long long c = clock64(); dbg[17] += c - cseg; cseg = c; }
+                lp_epi_bar();
+                if (dbg && tid == 0) { const long long c = clock64(); dbg[18] += c - cseg; cseg = c; }
                 {
                     const int c16 = lane & 7, rsub = lane >> 3;
 #pragma unroll
@@ -123,7 +137,7 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                             for (int i = 0; i < 8; ++i) {
                                 const int r = (i * 4 + warp) * 4 + rsub;
                                 const int x = xb + r;
-                                if (x < P.Tx && t + 3 < P.Ty) {                       // Ty % 4 == 0
+                                if (x < P.Tx && t + 3 < P.Ty && !(P.skip & 1)) {      // Ty % 4 == 0
                                     const float4 o = *reinterpret_cast<const float4 *>(box + r * 128 + ((c16 ^ (r & 7)) << 4));
                                     __stcs(reinterpret_cast<float4 *>(outb + (size_t)x * P.Ty + t), o);
                                 }
@@ -131,18 +145,21 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                         }
                     }
                 }
+                if (dbg && tid == 0) { const long long c = clock64(); dbg[19] += c - cseg; cseg = c; }
                 if (P.flags != nullptr) {
                     // publish the group to the MAS kernel running next to this one (device-scope release)
                     __threadfence();
-                    lp_aux_bar();
+                    lp_epi_bar();
                     if (tid == 0) {
                         if (SPLITM) gflag_add_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
                         else gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
                     }
+                    if (dbg && tid == 0) { const long long c = clock64(); dbg[20] += c - cseg; cseg = c; }
                 }
             }
         }
     }
+    if (dbg && tid == 0) dbg[6] = clock64() - dbg[3];
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kLpTmemCols);
@@ -153,8 +170,11 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     // table -- the last utterance to finish is written by all SMs of the kernel at once.  32 done-flags are
     // polled per load (one lane each), so a sweep costs one L2 round trip.
     if (P.job.path != nullptr) {
-        const int total_warps = (int)(gridDim.x * gridDim.y * gridDim.z) * (kTcThreads / 32);
-        const int gw = (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (kTcThreads / 32) + warp;
+        // rows are dealt CTA-major (warp w of CTA c takes row w*nctas + c, ...): a text of 190 rows keeps two warps
+        // of EVERY CTA busy instead of all warps of the first few
+        const int nctas = (int)(gridDim.x * gridDim.y * gridDim.z);
+        const int total_warps = nctas * (kTcThreads / 32);
+        const int gw = warp * nctas + (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
         if (gw < P.Tx) {
             uint32_t proc[4] = {0u, 0u, 0u, 0u};
             int remaining = P.B;
@@ -253,6 +273,7 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
     }
     if (job) P.job = *job;
+    P.skip = option("lp_debug_skip");
     const bool splitm = F > kMaxF;
     const int mtiles = splitm ? (Tx + 127) / 128 : 1;          // grid.z
     const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;

@@ -36,23 +36,25 @@ constexpr int kLpTmemCols = 512;
 
 struct LpFrontSmem {
     // byte offsets from a 1024-aligned base; F = 8*KS
+    __host__ __device__ static constexpr int nraw(int F) { return F <= 96 ? 2 : 1; }      // raw y-group buffers
     __host__ __device__ static constexpr uint32_t raw_bytes(int F) { return (uint32_t)F * kLpGroup * 4u; }
     __host__ __device__ static constexpr uint32_t op_bytes(int F) { return (uint32_t)F * kLpGroup * 4u; }
-    __host__ __device__ static constexpr uint32_t off_raw() { return 0; }
-    __host__ __device__ static constexpr uint32_t off_hi(int F) { return raw_bytes(F); }                    // [2]
+    __host__ __device__ static constexpr uint32_t off_raw() { return 0; }                                   // [nraw]
+    __host__ __device__ static constexpr uint32_t off_hi(int F) { return (uint32_t)nraw(F) * raw_bytes(F); }   // [2]
     __host__ __device__ static constexpr uint32_t off_lo(int F) { return off_hi(F) + 2 * op_bytes(F); }     // [2]
     __host__ __device__ static constexpr uint32_t off_part(int F) { return off_lo(F) + 2 * op_bytes(F); }   // [2][2][64] f32
-    __host__ __device__ static constexpr uint32_t off_ysq(int F) { return off_part(F) + 2 * 2 * 64 * 4; }   // [2][64] f32
-    __host__ __device__ static constexpr uint32_t off_bars(int F) { return off_ysq(F) + 2 * 64 * 4; }       // 8 mbarriers
-    __host__ __device__ static constexpr uint32_t off_tmem(int F) { return off_bars(F) + 8 * 8; }
+    __host__ __device__ static constexpr uint32_t off_ysq(int F) { return off_part(F) + 2 * 2 * 64 * 4; }   // [4][64] f32 ring
+    __host__ __device__ static constexpr uint32_t off_bars(int F) { return off_ysq(F) + 4 * 64 * 4; }       // 12 mbarriers
+    __host__ __device__ static constexpr uint32_t off_tmem(int F) { return off_bars(F) + 12 * 8; }
     __host__ __device__ static constexpr uint32_t total(int F) { return off_tmem(F) + 16; }
 };
 
 struct LpFront {
     unsigned char *raw, *hi, *lo;
     float *part, *ysq;
-    uint64_t *bar_raw, *bar_split /*[2]*/, *bar_dfull, *bar_dempty, *bar_aready, *bar_mu;
+    uint64_t *bar_raw /*[2]*/, *bar_split /*[2]*/, *bar_dfull, *bar_dempty, *bar_aready, *bar_mu, *bar_bfree /*[2]*/;
     uint32_t *tmem_slot;
+    long long *prof = nullptr;     // diagnostics: per-CTA wait-cycle accumulators (see scripts/timeline.py), normally null
     __device__ __forceinline__ void carve(unsigned char *base, int F) {
         raw = base + LpFrontSmem::off_raw();
         hi = base + LpFrontSmem::off_hi(F);
@@ -60,14 +62,16 @@ struct LpFront {
         part = reinterpret_cast<float *>(base + LpFrontSmem::off_part(F));
         ysq = reinterpret_cast<float *>(base + LpFrontSmem::off_ysq(F));
         uint64_t *b = reinterpret_cast<uint64_t *>(base + LpFrontSmem::off_bars(F));
-        bar_raw = b; bar_split = b + 1; bar_dfull = b + 3; bar_dempty = b + 4; bar_aready = b + 5; bar_mu = b + 6;
+        bar_raw = b; bar_split = b + 2; bar_dfull = b + 4; bar_dempty = b + 5; bar_aready = b + 6; bar_mu = b + 7;
+        bar_bfree = b + 8;
         tmem_slot = reinterpret_cast<uint32_t *>(base + LpFrontSmem::off_tmem(F));
     }
     __device__ __forceinline__ void init_barriers() {       // one thread
-        mbar_init(bar_raw, 1);
+        mbar_init(&bar_raw[0], 1); mbar_init(&bar_raw[1], 1);
         mbar_init(&bar_split[0], kLpAux); mbar_init(&bar_split[1], kLpAux);
         mbar_init(bar_dfull, 1); mbar_init(bar_dempty, kLpAux);
         mbar_init(bar_aready, kLpAux); mbar_init(bar_mu, 1);
+        mbar_init(&bar_bfree[0], 1); mbar_init(&bar_bfree[1], 1);
     }
 };
 
@@ -75,7 +79,9 @@ __device__ __forceinline__ uint32_t lp_col_a(int F, int mt, int lo) { return (ui
 // mtmax = M-tiles one CTA holds: 2 (Tx <= 256 in one CTA, F <= 96) or 1 (split-M: one CTA per M-tile, F <= 128)
 __device__ __forceinline__ uint32_t lp_col_d(int F, int mt, int mtmax = 2) { return (uint32_t)(2 * mtmax * F + mt * kLpGroup); }
 
+// named barriers of the two 128-thread groups: 1 = split warps, 2 = epilogue warps
 __device__ __forceinline__ void lp_aux_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void lp_epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 // elect-predicated MMA (the whole warp executes this; one lane issues)
 __device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -108,26 +114,36 @@ __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap 
     constexpr int F = 8 * KS;
     constexpr uint32_t kSbo = (uint32_t)F * 32u;                 // 8 frames x F mel bins x 4 B per row group
     const uint32_t idesc = umma_idesc_tf32_ts(128, kLpGroup);
+    constexpr int NRAW = LpFrontSmem::nraw(F);
     if (elect_one()) {
         // the utterance's whole mu_x block [F][Tx] in one bulk copy (16-byte aligned since F % 4 == 0)
         const uint32_t mu_bytes = (uint32_t)F * (uint32_t)Tx * 4u;
         mbar_arrive_expect_tx(S.bar_mu, mu_bytes);
         tma_bulk_load_1d(mu_stage, mu_b, mu_bytes, S.bar_mu);
-        mbar_arrive_expect_tx(S.bar_raw, LpFrontSmem::raw_bytes(F));
-        tma_load_3d(S.raw, ymap, t_begin, 0, b, S.bar_raw);
+        for (int q = 0; q < NRAW && q < ng; ++q) {
+            mbar_arrive_expect_tx(&S.bar_raw[q], LpFrontSmem::raw_bytes(F));
+            tma_load_3d(S.raw + (size_t)q * LpFrontSmem::raw_bytes(F), ymap, t_begin + q * t_stride, 0, b, &S.bar_raw[q]);
+        }
     }
     __syncwarp();
+    long long w_split = 0, w_dempty = 0, c_start = clock64();
     mbar_wait_warp(S.bar_aready, 0);
+    const long long c_loop = clock64();
     for (int g = 0; g < ng; ++g) {
         const int p = g & 1;
+        long long c0 = clock64();
         mbar_wait_warp(&S.bar_split[p], (uint32_t)(g >> 1) & 1u);
-        // every aux thread is done with the raw buffer: fetch the next group into it
-        if (g + 1 < ng && elect_one()) {
-            mbar_arrive_expect_tx(S.bar_raw, LpFrontSmem::raw_bytes(F));
-            tma_load_3d(S.raw, ymap, t_begin + (g + 1) * t_stride, 0, b, S.bar_raw);
+        w_split += clock64() - c0;
+        // every split thread is done with raw buffer g % NRAW: fetch group g + NRAW into it
+        if (g + NRAW < ng && elect_one()) {
+            const int q = g % NRAW;
+            mbar_arrive_expect_tx(&S.bar_raw[q], LpFrontSmem::raw_bytes(F));
+            tma_load_3d(S.raw + (size_t)q * LpFrontSmem::raw_bytes(F), ymap, t_begin + (g + NRAW) * t_stride, 0, b, &S.bar_raw[q]);
         }
         __syncwarp();
+        c0 = clock64();
         if (g >= 1) mbar_wait_warp(S.bar_dempty, (uint32_t)(g - 1) & 1u);
+        w_dempty += clock64() - c0;
         tc_fence_after();
         const uint32_t bh = smem_u32(S.hi) + (uint32_t)p * LpFrontSmem::op_bytes(F);
         const uint32_t bl = smem_u32(S.lo) + (uint32_t)p * LpFrontSmem::op_bytes(F);
@@ -143,13 +159,19 @@ __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap 
                 umma_tf32_ts_elect(dcol, al + 8u * ks, dh, idesc, 1u);                    // lo * hi
             }
         }
-        umma_commit_elect(S.bar_dfull);
+        umma_commit_elect(S.bar_dfull);           // D of group g complete -> epilogue warps
+        umma_commit_elect(&S.bar_bfree[p]);       // ... and operand buffer p may be refilled -> split warps
         __syncwarp();
+    }
+    if (S.prof && elect_one()) {
+        S.prof[10] = w_split; S.prof[11] = w_dempty; S.prof[12] = clock64() - c_loop; S.prof[13] = c_loop - c_start;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// aux warps (threads 0..127; warp w owns TMEM lanes 32w..32w+31)
+// epilogue warps (threads 0..127; warp w owns TMEM lanes 32w..32w+31) and split warps (a second group of 128
+// threads, passed in as tid 0..127 / warp 0..3).  The two groups run concurrently: split(g+1) overlaps
+// MMA(g) and epilogue(g-1); hand-offs are mbarriers only (raw -> split -> MMA -> epilogue, bfree: MMA -> split).
 // ---------------------------------------------------------------------------------------------------
 // A prologue: row_of(mt, m) gives the text position parked in lane m of M-tile mt (any permutation).
 template <int KS, class RowOf>
@@ -189,18 +211,23 @@ __device__ __forceinline__ void lp_aux_prologue(const LpFront &S, const float *m
 // thread = (frame n = 32*(warp&1) + lane, mel-bin chunk kc = warp>>1, +2, ...): 4 conflict-free LDS.32 down a
 // column of the raw tile, one STS.128 per operand into core matrix (n/8, kc), row n%8.
 template <int KS>
-__device__ __forceinline__ void lp_aux_split(const LpFront &S, int g, int tid, int warp, int lane) {
+__device__ __forceinline__ void lp_aux_split(const LpFront &S, int g, int tid, int warp, int lane, bool skip_math = false) {
     constexpr int F = 8 * KS;
     constexpr uint32_t kSbo = (uint32_t)F * 32u;
+    constexpr int NRAW = LpFrontSmem::nraw(F);
     const int p = g & 1;
-    mbar_wait(S.bar_raw, (uint32_t)g & 1u);
-    const float *raw = reinterpret_cast<const float *>(S.raw);
+    long long c0 = clock64();
+    if (g >= 2) mbar_wait(&S.bar_bfree[p], (uint32_t)((g >> 1) - 1) & 1u);      // MMA(g-2) has read operand buffer p
+    long long c1 = clock64();
+    mbar_wait(&S.bar_raw[g % NRAW], (uint32_t)(g / NRAW) & 1u);
+    if (S.prof && tid == 0) { S.prof[8] += c1 - c0; S.prof[7] += clock64() - c1; }
+    const float *raw = reinterpret_cast<const float *>(S.raw + (size_t)(g % NRAW) * LpFrontSmem::raw_bytes(F));
     unsigned char *hb = S.hi + (size_t)p * LpFrontSmem::op_bytes(F), *lb = S.lo + (size_t)p * LpFrontSmem::op_bytes(F);
     const int n = 32 * (warp & 1) + lane;
     const uint32_t row_off = (uint32_t)(n >> 3) * kSbo + (uint32_t)(n & 7) * 16u;
     float q = 0.f;
 #pragma unroll
-    for (int kc = (warp >> 1); kc < 2 * KS; kc += 2) {
+    for (int kc = (warp >> 1); kc < (skip_math ? 0 : 2 * KS); kc += 2) {
         float v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = raw[(4 * kc + k) * kLpGroup + n];
@@ -216,7 +243,7 @@ __device__ __forceinline__ void lp_aux_split(const LpFront &S, int g, int tid, i
     pd[(warp >> 1) * 64 + n] = q;
     fence_proxy_async_smem();              // hi/lo stores -> visible to the tensor core's smem reads
     lp_aux_bar();
-    if (tid < 64) S.ysq[p * 64 + tid] = pd[tid] + pd[64 + tid];
+    if (tid < 64) S.ysq[(g & 3) * 64 + tid] = pd[tid] + pd[64 + tid];      // ring of 4: epilogue(g-3) is long done
     mbar_arrive(&S.bar_split[p]);          // also: the raw buffer may be refilled
 }
 
@@ -224,7 +251,9 @@ __device__ __forceinline__ void lp_aux_split(const LpFront &S, int g, int tid, i
 __device__ __forceinline__ void lp_aux_drain(const LpFront &S, int F, int g, int warp, int MT, uint32_t tmem,
                                              uint32_t (&d0)[2][32], uint32_t (&d1)[2][32], int mtmax = 2) {
     const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    const long long c0 = clock64();
     mbar_wait(S.bar_dfull, (uint32_t)g & 1u);
+    if (S.prof && threadIdx.x == 0) S.prof[5] += clock64() - c0;
     tc_fence_after();
     tmem_ld32(tmem + lane_base + lp_col_d(F, 0, mtmax), d0[0]);
     tmem_ld32(tmem + lane_base + lp_col_d(F, 0, mtmax) + 32, d0[1]);

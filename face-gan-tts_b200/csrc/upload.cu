@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(kThreads) upload_batch_kernel(const float *__r
         const int tx = tx_h[b], ty = ty_h[b];      // 8 bytes over PCIe per item
         if (f0 == 0 && threadIdx.x == 0) { tx_d[b] = tx; ty_d[b] = ty; }
         pull_rows<VECY>(y_h + (size_t)b * F * Ty, y_d + (size_t)b * F * Ty, f0, F, Ty, min(max(ty, 0), Ty), hint);
-        pull_rows<VECX>(mu_h + (size_t)b * F * Tx, mu_d + (size_t)b * F * Tx, f0, F, Tx, min(max(tx, 0), Tx), hint);
+        if (mu_h != nullptr)
+            pull_rows<VECX>(mu_h + (size_t)b * F * Tx, mu_d + (size_t)b * F * Tx, f0, F, Tx, min(max(tx, 0), Tx), hint);
     }
 }
 
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(kThreads) zero_padding_kernel(const int *__res
         const int tx = min(max(tx_h[b], 0), Tx), ty = min(max(ty_h[b], 0), Ty);
         float *yr = y_d + (size_t)row * Ty, *mr = mu_d + (size_t)row * Tx;
         for (int t = ty + threadIdx.x; t < Ty; t += kThreads) yr[t] = 0.f;
-        for (int t = tx + threadIdx.x; t < Tx; t += kThreads) mr[t] = 0.f;
+        if (mu_d != nullptr)
+            for (int t = tx + threadIdx.x; t < Tx; t += kThreads) mr[t] = 0.f;
     }
 }
 
@@ -111,14 +113,15 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const int *t_xs_pinned, const int *t_ys_pinned,
                         int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev, int *t_x_dev, int *t_y_dev,
                         cudaStream_t stream) {
-    if (!mu_x_pinned || !y_pinned || !t_xs_pinned || !t_ys_pinned || !mu_x_dev || !y_dev || !t_x_dev || !t_y_dev ||
+    if (!y_pinned || !t_xs_pinned || !t_ys_pinned || !y_dev || !t_x_dev || !t_y_dev || (mu_x_pinned && !mu_x_dev) ||
         B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0)
         return MAS_B200_ERR_ARG;
+    const bool with_mu = mu_x_pinned != nullptr;     // NULL: the caller moves mu_x itself (e.g. on the copy engine, in parallel)
     DeviceInfo di;
     const int rc = device_info(&di);
     if (rc != MAS_B200_OK) return rc;
-    const void *mu_v, *y_v, *tx_v, *ty_v;
-    if (!device_view(mu_x_pinned, &mu_v) || !device_view(y_pinned, &y_v) || !device_view(t_xs_pinned, &tx_v) ||
+    const void *mu_v = nullptr, *y_v, *tx_v, *ty_v;
+    if ((with_mu && !device_view(mu_x_pinned, &mu_v)) || !device_view(y_pinned, &y_v) || !device_view(t_xs_pinned, &tx_v) ||
         !device_view(t_ys_pinned, &ty_v))
         return MAS_B200_ERR_ARG;      // the host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)
     if (option("upload_impl") == 2) {
@@ -126,10 +129,10 @@ int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const i
         // padding zero-filled by a small kernel.  DMA reads move ~50 GB/s over PCIe gen5 where SM-issued zero-copy
         // loads reach ~40 GB/s, at the price of 2B+2 driver calls per batch on the host.
         zero_padding_kernel<<<std::min(B * F, 4 * di.sm_count), kThreads, 0, stream>>>(
-            static_cast<const int *>(tx_v), static_cast<const int *>(ty_v), B, F, Tx, Ty, mu_x_dev, y_dev);
+            static_cast<const int *>(tx_v), static_cast<const int *>(ty_v), B, F, Tx, Ty, with_mu ? mu_x_dev : nullptr, y_dev);
         MASB200_CUDA_TRY(cudaGetLastError());
         for (int b = 0; b < B; ++b) {
-            const size_t tx = (size_t)std::min(std::max(t_xs_pinned[b], 0), Tx), ty = (size_t)std::min(std::max(t_ys_pinned[b], 0), Ty);
+            const size_t tx = with_mu ? (size_t)std::min(std::max(t_xs_pinned[b], 0), Tx) : 0, ty = (size_t)std::min(std::max(t_ys_pinned[b], 0), Ty);
             if (ty)
                 MASB200_CUDA_TRY(cudaMemcpy2DAsync(y_dev + (size_t)b * F * Ty, sizeof(float) * Ty, y_pinned + (size_t)b * F * Ty,
                                                    sizeof(float) * Ty, sizeof(float) * ty, (size_t)F, cudaMemcpyHostToDevice, stream));
@@ -141,7 +144,7 @@ int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const i
         MASB200_CUDA_TRY(cudaMemcpyAsync(t_y_dev, t_ys_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
         return MAS_B200_OK;
     }
-    const bool vx = (Tx % 4 == 0) && al16(mu_v) && al16(mu_x_dev);
+    const bool vx = with_mu && (Tx % 4 == 0) && al16(mu_v) && al16(mu_x_dev);
     const bool vy = (Ty % 4 == 0) && al16(y_v) && al16(y_dev);
     const long long items = (long long)B * ((F + kRows - 1) / kRows);
     const int ctas = option("upload_ctas");

@@ -245,6 +245,9 @@ int mas_b200_duration_loss(const float *logw_dev, const int *durations_dev, cons
  * memory (cudaHostAlloc / cudaHostRegister / torch pin_memory; anything else -> MAS_B200_ERR_ARG) and writes
  * the zero padding on the device, so the device tensors equal a plain copy of correctly padded inputs.
  * Also copies the lengths.  Asynchronous on `stream`; the host buffers must stay untouched until it completes.
+ * mu_x_pinned may be NULL (mu_x_dev is then untouched): SM-issued zero-copy reads and the copy engine are
+ * separate requesters on the PCIe link, so a caller can move the small mu_x with cudaMemcpyAsync on another
+ * stream while this kernel pulls y.
  */
 int mas_b200_upload_batch(const float *mu_x_pinned, const float *y_pinned,
                           const int *t_xs_pinned, const int *t_ys_pinned,

@@ -19,7 +19,7 @@ def call():
     assert rc == 0, rc
 for _ in range(5): call()
 torch.cuda.synchronize()
-dm = torch.zeros((B, 16), dtype=torch.int64, device=dev); dl = torch.zeros((B * 8, 4), dtype=torch.int64, device=dev)
+dm = torch.zeros((B, 16), dtype=torch.int64, device=dev); dl = torch.zeros((B * 8, 32), dtype=torch.int64, device=dev)
 def setp(name, t):
     p = t.data_ptr(); lo, hi = p & 0xFFFFFFFF, p >> 32
     _lib.set_option(name + "_lo", lo - (1 << 32) if lo >= (1 << 31) else lo); _lib.set_option(name + "_hi", hi)
@@ -34,7 +34,11 @@ t0 = min(int(lp[:, 0].min()), int(dm[:, 12].min()))
 print(f"event time {e0.elapsed_time(e1)*1e3:.1f} us; {lp.shape[0]} LP CTAs")
 print("LP  start  min/max us:", (int(lp[:, 0].min()) - t0) / 1e3, (int(lp[:, 0].max()) - t0) / 1e3)
 print("LP  gemm end min/max :", (int(lp[:, 1].min()) - t0) / 1e3, (int(lp[:, 1].max()) - t0) / 1e3)
-pass
+print("LP  prologue end min/max:", (int(lp[:, 4].min()) - t0) / 1e3, (int(lp[:, 4].max()) - t0) / 1e3)
+import numpy as np
+m = lp[:, 5:14].double().mean(0).tolist()
+print("LP mean cycles/CTA: E drain-wait %.0f, E loop %.0f | S raw-wait %.0f, S bfree-wait %.0f, S loop %.0f | M split-wait %.0f, M dempty-wait %.0f, M loop %.0f, M aready-wait %.0f" % tuple(m))
+print("LP E segments mean cycles/CTA: drain(incl wait) %.0f, bar+stage %.0f, bar %.0f, write-out %.0f, fence+flag %.0f" % tuple(lp[:, 16:21].double().mean(0).tolist()))
 print("LP  path end min/max :", (int(lp[:, 2].min()) - t0) / 1e3, (int(lp[:, 2].max()) - t0) / 1e3)
 print("MAS start  min/max   :", (int(dm[:, 12].min()) - t0) / 1e3, (int(dm[:, 12].max()) - t0) / 1e3)
 print("MAS end    min/max   :", (int(dm[:, 13].min()) - t0) / 1e3, (int(dm[:, 13].max()) - t0) / 1e3)

@@ -23,7 +23,7 @@ def ev_time(fn, reps=50):
     return a.elapsed_time(b) / reps * 1e-3
 
 _lib.set_option("upload_impl", 2)
-s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out))
+s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out, mu_on_copy_engine=False))
 print(f"ragged upload, copy engine 2-D per utterance: {s*1e6:7.1f} us  {sum(valid)/3/s/1e9:6.1f} GB/s over PCIe ({sum(valid)/3/1e6:.2f} MB valid)")
 t0 = time.perf_counter()
 for i in range(200): fgt.upload_batch(*host[i % 3], out=out)
@@ -34,9 +34,12 @@ for hint in (1, 0):
   _lib.set_option("upload_l2_256b", hint); print("L2::256B hint", hint)
   for ctas in (74, 148, 592):
     _lib.set_option("upload_ctas", ctas)
-    s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out))
+    s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out, mu_on_copy_engine=False))
     print(f"  ragged upload ctas={ctas:5d}: {s*1e6:7.1f} us  {sum(valid)/3/s/1e9:6.1f} GB/s over PCIe ({sum(valid)/3/1e6:.2f} MB valid)")
 _lib.set_option("upload_ctas", 0)
+for m in (True, False):
+    s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out, mu_on_copy_engine=m))
+    print(f"ragged upload, mu_on_copy_engine={m}: {s*1e6:7.1f} us")
 def padded(i):
     h = host[i % 3]
     for d, s in zip(out, h): d.copy_(s, non_blocking=True)

@@ -205,12 +205,15 @@ def test_upload_batch_equals_a_plain_copy_of_padded_inputs(B, F, Tx, Ty, upload_
     junk_x = torch.randn(B, F, Tx, generator=g) * (torch.arange(Tx)[None, None] >= t_x[:, None, None])
     junk_y = torch.randn(B, F, Ty, generator=g) * (torch.arange(Ty)[None, None] >= t_y[:, None, None])
     host = [(mu_x + junk_x).pin_memory(), (y + junk_y).pin_memory(), t_x.pin_memory(), t_y.pin_memory()]
-    out = fgt.upload_batch(*host)
+    out = fgt.upload_batch(*host, mu_on_copy_engine=False)
     torch.cuda.synchronize()
     assert torch.equal(out[0].cpu(), mu_x) and torch.equal(out[1].cpu(), y)
     assert torch.equal(out[2].cpu(), t_x) and torch.equal(out[3].cpu(), t_y)
-    # reuse of the output buffers + the alignment computed from them equals the one from plain copies
-    out2 = fgt.upload_batch(*host, out=out)
+    # reuse of the output buffers (mu_x through the copy engine: a plain copy, host padding included) + the
+    # alignment computed from them equals the one from plain copies
+    out2 = fgt.upload_batch(*host, out=out, mu_on_copy_engine=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out2[1].cpu(), y) and torch.equal(out2[0].cpu(), host[0])
     a = fgt.log_prior_maximum_path(out2[0], out2[1], out2[2], out2[3], dense_path=False)
     b = fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, dense_path=False)
     assert torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token)
