@@ -1,6 +1,7 @@
 // log_prior_tc.cu -- Grad-TTS log-prior on the 5th-generation tensor cores (tcgen05 + TMEM), unfused:
 // the front end of lp_tc_frontend.cuh with an epilogue that streams [B,Tx,Ty] to HBM.
-// One CTA = one utterance x a run of 64-frame groups; warps 0-3 epilogue, warps 4-7 operand split, warp 8 TMA + MMA issue.
+// One CTA = one utterance x a run of 64-frame groups; warps 0-3 epilogue, warps 4-7 operand split, warp 8 TMA loads + MMA issue,
+// warps 9-10 (even / odd groups) TMA stores of the finished tiles + publication to a concurrent MAS kernel.
 #include <atomic>
 #include <cstring>
 
@@ -16,7 +17,7 @@ float log_prior_const(int F);   // log_prior_ffma.cu
 
 namespace {
 
-constexpr int kTcThreads = 288;        // warps 0-3 epilogue, 4-7 split, 8 TMA + MMA issue
+constexpr int kTcThreads = 352;        // warps 0-3 epilogue, 4-7 split, 8 TMA loads + MMA issue, 9-10 TMA stores + publication
 constexpr int kMaxF = 96;             // 4F (A hi/lo, two M-tiles) + 128 (D) <= 512 columns; beyond: split-M (2F + 64)
 
 struct LpTcParams {
@@ -37,7 +38,7 @@ struct LpTcParams {
 // SPLITM: one CTA per (utterance, group run, M-tile) -- blockIdx.z is the M-tile; see lp_tc_frontend.cuh.
 template <int KS, bool SPLITM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap) {
+log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap omap) {
     constexpr int F = 8 * KS;
     constexpr int MTMAX = SPLITM ? 1 : 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -46,10 +47,10 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     // [F][Tx] staging of mu_x: parked in the hi/lo operand buffers (4 * F * 64 * 4 bytes >= F * Tx * 4 for Tx <= 256),
     // which nothing writes before every aux thread has left the prologue.
     float *mu_s = reinterpret_cast<float *>(S.hi);
-    // epilogue staging: per (M-tile, 32-frame half) a [128 rows][32 frames] fp32 box, 16-byte chunks XOR-swizzled by
-    // row & 7 -- written row-per-thread (what tcgen05.ld hands out) and read back row-per-quarter-warp, both
-    // conflict-free, so that every global store instruction covers whole 128-byte row segments.
-    unsigned char *stage = smem_raw + ((LpFrontSmem::total(F) + 127) / 128) * 128;
+    // epilogue staging: per (M-tile, 32-frame half) a [128 rows][32 frames] fp32 box in the 128-byte-swizzle layout
+    // (16-byte chunk ^= row & 7): written row-per-thread (what tcgen05.ld hands out) without bank conflicts and
+    // stored by TMA (tensor map over out[B][Tx][Ty], box {32,128,1}), which also clips rows >= Tx and frames >= Ty.
+    unsigned char *stage = smem_raw + ((LpFrontSmem::total(F) + 1023) / 1024) * 1024;
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
@@ -75,89 +76,84 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     if (warp == 8) {
         lp_mma_warp<KS, MTMAX>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng,
                                (P.skip & 2) ? 0 : MT, tmem);
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ---- split warps: raw y group -> hi/lo K-major operands + ysq.  mu_s aliases the operand buffers, which
         // may be filled once every epilogue thread has left the prologue (bar_aready).
         mbar_wait(S.bar_aready, 0);
         const long long cs0 = clock64();
         for (int g = 0; g < ng; ++g) lp_aux_split<KS>(S, g, tid - 128, warp - 4, lane, (P.skip & 4) != 0);
         if (dbg && tid == 128) dbg[9] = clock64() - cs0;
+    } else if (warp >= 9) {
+        // ---- store / publication warps: warp 9 takes the even groups, warp 10 the odd ones, so that waiting for the
+        // completion of one group's bulk stores (before its flag may be released) never delays the next group's
+        // stores.  One elected lane per step, warp-uniform control flow.
+        for (int gg = warp - 9; gg < ng; gg += 2) {
+            const int gidx = g0 + gg * gs;
+            const int t0 = gidx * kLpGroup;
+            mbar_wait_warp(&S.bar_staged[gg & 1], (uint32_t)(gg >> 1) & 1u);
+            if (elect_one()) {
+                if (!(P.skip & 1)) {
+                    for (int mt = 0; mt < MT; ++mt)
+                        for (int h = 0; h < 2; ++h)
+                            tma_store_3d(&omap, stage + (size_t)(mt * 2 + h) * 16384, t0 + 32 * h, (mt0 + mt) * 128, b);
+                }
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(S.bar_stfree);                       // the staging boxes may be refilled
+                if (P.flags != nullptr) {
+                    // publish the group to the MAS kernel running next to this one: bulk stores complete ->
+                    // async-proxy / generic-proxy fence -> device-scope release
+                    tma_store_wait_all();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    if (SPLITM) gflag_add_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
+                    else gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
     } else {
         float musq[2];
         lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [mt0](int mt, int m) { return (mt0 + mt) * 128 + m; }, musq);
-        float *outb = P.out + (size_t)b * P.Tx * P.Ty;
         if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[4] = t; }
         if (dbg && tid == 0) dbg[3] = clock64();
-        for (int g = 1; g <= ng; ++g) {
-            {
-                // ---- epilogue of group g-1: thread = text position, 64 consecutive frames per M-tile
-                const int gg = g - 1, p = gg & 3;
-                const int gidx = g0 + gg * gs;
-                const int t0 = gidx * kLpGroup;
-                uint32_t d0[2][32], d1[2][32];
-                long long cseg = clock64();
-                lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1, MTMAX);
-                if (dbg && tid == 0) { const long long c = clock64(); dbg[16] += c - cseg; cseg = c; }
-                lp_epi_bar();                                   // every warp is done reading the previous group's boxes
+        long long w_stfree = 0;
+        for (int gg = 0; gg < ng; ++gg) {
+            // ---- epilogue of group gg: thread = text position, 64 consecutive frames per M-tile
+            const int p = gg & 3;
+            uint32_t d0[2][32], d1[2][32];
+            lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1, MTMAX);
+            if (gg >= 1) {                                       // the store warp has read the previous group's boxes
+                const long long c0 = clock64();
+                mbar_wait(S.bar_stfree, (uint32_t)(gg - 1) & 1u);
+                w_stfree += clock64() - c0;
+            }
 #pragma unroll
-                for (int mt = 0; mt < MTMAX; ++mt) {
-                    const int x = (mt0 + mt) * 128 + tid;
-                    if (mt < MT && x < P.Tx && !(P.skip & 8)) {
+            for (int mt = 0; mt < MTMAX; ++mt) {
+                const int x = (mt0 + mt) * 128 + tid;
+                if (mt < MT && x < P.Tx && !(P.skip & 8)) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384 + (size_t)tid * 128;
+                    for (int h = 0; h < 2; ++h) {
+                        unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384 + (size_t)tid * 128;
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 yq = *reinterpret_cast<const float4 *>(S.ysq + p * 64 + 32 * h + 4 * c);
-                                const uint32_t *r = (mt == 0) ? &d0[h][4 * c] : &d1[h][4 * c];
-                                float4 o;
-                                o.x = ((yq.x + __uint_as_float(r[0])) + musq[mt]) + P.cst;
-                                o.y = ((yq.y + __uint_as_float(r[1])) + musq[mt]) + P.cst;
-                                o.z = ((yq.z + __uint_as_float(r[2])) + musq[mt]) + P.cst;
-                                o.w = ((yq.w + __uint_as_float(r[3])) + musq[mt]) + P.cst;
-                                *reinterpret_cast<float4 *>(box + ((c ^ (tid & 7)) << 4)) = o;
-                            }
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 yq = *reinterpret_cast<const float4 *>(S.ysq + p * 64 + 32 * h + 4 * c);
+                            const uint32_t *r = (mt == 0) ? &d0[h][4 * c] : &d1[h][4 * c];
+                            float4 o;
+                            o.x = ((yq.x + __uint_as_float(r[0])) + musq[mt]) + P.cst;
+                            o.y = ((yq.y + __uint_as_float(r[1])) + musq[mt]) + P.cst;
+                            o.z = ((yq.z + __uint_as_float(r[2])) + musq[mt]) + P.cst;
+                            o.w = ((yq.w + __uint_as_float(r[3])) + musq[mt]) + P.cst;
+                            *reinterpret_cast<float4 *>(box + ((c ^ (tid & 7)) << 4)) = o;
                         }
                     }
-                }
-                if (dbg && tid == 0) { const long long c = clock64(); dbg[17] += c - cseg; cseg = c; }
-                lp_epi_bar();
-                if (dbg && tid == 0) { const long long c = clock64(); dbg[18] += c - cseg; cseg = c; }
-                {
-                    const int c16 = lane & 7, rsub = lane >> 3;
-#pragma unroll
-                    for (int mt = 0; mt < MTMAX; ++mt) {
-                        if (mt >= MT) break;
-                        const int xb = (mt0 + mt) * 128;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384;
-                            const int t = t0 + 32 * h + 4 * c16;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = (i * 4 + warp) * 4 + rsub;
-                                const int x = xb + r;
-                                if (x < P.Tx && t + 3 < P.Ty && !(P.skip & 1)) {      // Ty % 4 == 0
-                                    const float4 o = *reinterpret_cast<const float4 *>(box + r * 128 + ((c16 ^ (r & 7)) << 4));
-                                    __stcs(reinterpret_cast<float4 *>(outb + (size_t)x * P.Ty + t), o);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (dbg && tid == 0) { const long long c = clock64(); dbg[19] += c - cseg; cseg = c; }
-                if (P.flags != nullptr) {
-                    // publish the group to the MAS kernel running next to this one (device-scope release)
-                    __threadfence();
-                    lp_epi_bar();
-                    if (tid == 0) {
-                        if (SPLITM) gflag_add_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
-                        else gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
-                    }
-                    if (dbg && tid == 0) { const long long c = clock64(); dbg[20] += c - cseg; cseg = c; }
                 }
             }
+            fence_proxy_async_smem();                            // staging stores -> visible to the TMA store
+            mbar_arrive(&S.bar_staged[gg & 1]);
         }
+        if (dbg && tid == 0) dbg[14] = w_stfree;
     }
     if (dbg && tid == 0) dbg[6] = clock64() - dbg[3];
     tc_fence_before();
@@ -239,6 +235,19 @@ int make_y_tensor_map(const float *y, int B, int F, int Ty, CUtensorMap *out) {
     return r == CUDA_SUCCESS ? MAS_B200_OK : MAS_B200_ERR_ARG;
 }
 
+// 3-D map over out[b, x, t] for the epilogue's TMA stores: box {32 frames, 128 rows, 1}, 128-byte swizzle.
+static int make_out_tensor_map(float *out, int B, int Tx, int Ty, CUtensorMap *map) {
+    auto enc = encoder();
+    if (!enc) return MAS_B200_ERR_CUDA;
+    cuuint64_t gdim[3] = {(cuuint64_t)Ty, (cuuint64_t)Tx, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)Ty * 4, (cuuint64_t)Tx * Ty * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MAS_B200_OK : MAS_B200_ERR_ARG;
+}
+
 // shapes the tensor-core kernel takes; everything else goes to the FFMA kernel
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty) {
     if (!(F == 64 || F == 80 || F == 96 || F == 128) || Tx > 256 || Ty % 4 != 0 || B > 65535) return false;
@@ -264,6 +273,11 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     rc = make_y_tensor_map(y, B, F, Ty, &ymap);
     if (rc != MAS_B200_OK) return rc;
 
+    CUtensorMap omap;
+    std::memset(&omap, 0, sizeof(omap));
+    rc = make_out_tensor_map(out, B, Tx, Ty, &omap);
+    if (rc != MAS_B200_OK) return rc;
+
     LpTcParams P{};
     P.mu = mu_x; P.out = out; P.B = B; P.Tx = Tx; P.Ty = Ty; P.cst = log_prior_const(F);
     P.ngroups = (Ty + kLpGroup - 1) / kLpGroup;
@@ -283,10 +297,10 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     chunks = (P.ngroups + P.groups_per_cta - 1) / P.groups_per_cta;
     P.chunks = chunks;
     P.strided = flags != nullptr ? 1 : 0;
-    size_t smem = ((LpFrontSmem::total(F) + 127) / 128) * 128 + (size_t)(splitm ? 1 : 2) * 32768 + 1024;
+    size_t smem = ((LpFrontSmem::total(F) + 1023) / 1024) * 1024 + (size_t)(splitm ? 1 : 2) * 32768 + 1024;
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;   // > half an SM: one CTA per SM (each allocates all of TMEM)
 
-    void (*kern)(const LpTcParams, const CUtensorMap) = nullptr;
+    void (*kern)(const LpTcParams, const CUtensorMap, const CUtensorMap) = nullptr;
     switch (F) {
         case 64: kern = log_prior_tc_kernel<8, false>; break;
         case 80: kern = log_prior_tc_kernel<10, false>; break;
@@ -302,7 +316,7 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         if (dev >= 0 && dev < 16) configured[dev][ki].store(1, std::memory_order_release);
     }
-    kern<<<dim3(chunks, B, mtiles), kTcThreads, smem, stream>>>(P, ymap);
+    kern<<<dim3(chunks, B, mtiles), kTcThreads, smem, stream>>>(P, ymap, omap);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

@@ -44,15 +44,16 @@ struct LpFrontSmem {
     __host__ __device__ static constexpr uint32_t off_lo(int F) { return off_hi(F) + 2 * op_bytes(F); }     // [2]
     __host__ __device__ static constexpr uint32_t off_part(int F) { return off_lo(F) + 2 * op_bytes(F); }   // [2][2][64] f32
     __host__ __device__ static constexpr uint32_t off_ysq(int F) { return off_part(F) + 2 * 2 * 64 * 4; }   // [4][64] f32 ring
-    __host__ __device__ static constexpr uint32_t off_bars(int F) { return off_ysq(F) + 4 * 64 * 4; }       // 12 mbarriers
-    __host__ __device__ static constexpr uint32_t off_tmem(int F) { return off_bars(F) + 12 * 8; }
+    __host__ __device__ static constexpr uint32_t off_bars(int F) { return off_ysq(F) + 4 * 64 * 4; }       // 16 mbarrier slots
+    __host__ __device__ static constexpr uint32_t off_tmem(int F) { return off_bars(F) + 16 * 8; }
     __host__ __device__ static constexpr uint32_t total(int F) { return off_tmem(F) + 16; }
 };
 
 struct LpFront {
     unsigned char *raw, *hi, *lo;
     float *part, *ysq;
-    uint64_t *bar_raw /*[2]*/, *bar_split /*[2]*/, *bar_dfull, *bar_dempty, *bar_aready, *bar_mu, *bar_bfree /*[2]*/;
+    uint64_t *bar_raw /*[2]*/, *bar_split /*[2]*/, *bar_dfull, *bar_dempty, *bar_aready, *bar_mu, *bar_bfree /*[2]*/,
+        *bar_staged /*[2]*/, *bar_stfree;
     uint32_t *tmem_slot;
     long long *prof = nullptr;     // diagnostics: per-CTA wait-cycle accumulators (see scripts/timeline.py), normally null
     __device__ __forceinline__ void carve(unsigned char *base, int F) {
@@ -63,7 +64,7 @@ struct LpFront {
         ysq = reinterpret_cast<float *>(base + LpFrontSmem::off_ysq(F));
         uint64_t *b = reinterpret_cast<uint64_t *>(base + LpFrontSmem::off_bars(F));
         bar_raw = b; bar_split = b + 2; bar_dfull = b + 4; bar_dempty = b + 5; bar_aready = b + 6; bar_mu = b + 7;
-        bar_bfree = b + 8;
+        bar_bfree = b + 8; bar_staged = b + 10; bar_stfree = b + 12;
         tmem_slot = reinterpret_cast<uint32_t *>(base + LpFrontSmem::off_tmem(F));
     }
     __device__ __forceinline__ void init_barriers() {       // one thread
@@ -72,6 +73,7 @@ struct LpFront {
         mbar_init(bar_dfull, 1); mbar_init(bar_dempty, kLpAux);
         mbar_init(bar_aready, kLpAux); mbar_init(bar_mu, 1);
         mbar_init(&bar_bfree[0], 1); mbar_init(&bar_bfree[1], 1);
+        mbar_init(&bar_staged[0], kLpAux); mbar_init(&bar_staged[1], kLpAux); mbar_init(bar_stfree, 1);
     }
 };
 

@@ -123,6 +123,18 @@ __device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *t
         : "memory");
 }
 
+// shared -> global tensor-map store (bulk async-group completion).  SASS: UTMASTG.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tmap, const void *src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed groups have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed groups are complete (their global writes are performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP): src/dst 16-byte aligned, bytes % 16 == 0
 __device__ __forceinline__ void tma_bulk_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -38,7 +38,7 @@ print("LP  prologue end min/max:", (int(lp[:, 4].min()) - t0) / 1e3, (int(lp[:, 
 import numpy as np
 m = lp[:, 5:14].double().mean(0).tolist()
 print("LP mean cycles/CTA: E drain-wait %.0f, E loop %.0f | S raw-wait %.0f, S bfree-wait %.0f, S loop %.0f | M split-wait %.0f, M dempty-wait %.0f, M loop %.0f, M aready-wait %.0f" % tuple(m))
-print("LP E segments mean cycles/CTA: drain(incl wait) %.0f, bar+stage %.0f, bar %.0f, write-out %.0f, fence+flag %.0f" % tuple(lp[:, 16:21].double().mean(0).tolist()))
+print("LP E staging-free wait mean cycles/CTA: %.0f" % lp[:, 14].double().mean().item())
 print("LP  path end min/max :", (int(lp[:, 2].min()) - t0) / 1e3, (int(lp[:, 2].max()) - t0) / 1e3)
 print("MAS start  min/max   :", (int(dm[:, 12].min()) - t0) / 1e3, (int(dm[:, 12].max()) - t0) / 1e3)
 print("MAS end    min/max   :", (int(dm[:, 13].min()) - t0) / 1e3, (int(dm[:, 13].max()) - t0) / 1e3)
