@@ -44,13 +44,16 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     LpFront S;
     S.carve(smem_raw, F);
-    // [F][Tx] staging of mu_x: parked in the hi/lo operand buffers (4 * F * 64 * 4 bytes >= F * Tx * 4 for Tx <= 256),
-    // which nothing writes before every aux thread has left the prologue.
-    float *mu_s = reinterpret_cast<float *>(S.hi);
     // epilogue staging: per (M-tile, 32-frame half) a [128 rows][32 frames] fp32 box in the 128-byte-swizzle layout
     // (16-byte chunk ^= row & 7): written row-per-thread (what tcgen05.ld hands out) without bank conflicts and
     // stored by TMA (tensor map over out[B][Tx][Ty], box {32,128,1}), which also clips rows >= Tx and frames >= Ty.
     unsigned char *stage = smem_raw + ((LpFrontSmem::total(F) + 1023) / 1024) * 1024;
+    // [F][Tx] staging of mu_x for the prologue: in the epilogue boxes when it fits there (first written after the
+    // prologue, by the same threads) -- then the split warps start on the first y groups while the prologue runs --
+    // else in the hi/lo operand buffers (4 * F * 64 * 4 bytes >= F * Tx * 4 for Tx <= 256), which the split warps
+    // may only fill once every epilogue thread has left the prologue (bar_aready).
+    const bool mu_in_stage = (size_t)F * P.Tx * 4 <= (size_t)MTMAX * 32768;
+    float *mu_s = reinterpret_cast<float *>(mu_in_stage ? stage : S.hi);
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
@@ -77,9 +80,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
         lp_mma_warp<KS, MTMAX>(S, &ymap, P.mu + (size_t)b * F * P.Tx, mu_s, P.Tx, b, g0 * kLpGroup, gs * kLpGroup, ng,
                                (P.skip & 2) ? 0 : MT, tmem);
     } else if (warp >= 4 && warp < 8) {
-        // ---- split warps: raw y group -> hi/lo K-major operands + ysq.  mu_s aliases the operand buffers, which
-        // may be filled once every epilogue thread has left the prologue (bar_aready).
-        mbar_wait(S.bar_aready, 0);
+        // ---- split warps: raw y group -> hi/lo K-major operands + ysq
+        if (!mu_in_stage) mbar_wait(S.bar_aready, 0);
         const long long cs0 = clock64();
         for (int g = 0; g < ng; ++g) lp_aux_split<KS>(S, g, tid - 128, warp - 4, lane, (P.skip & 4) != 0);
         if (dbg && tid == 128) dbg[9] = clock64() - cs0;
@@ -90,16 +92,21 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
         for (int gg = warp - 9; gg < ng; gg += 2) {
             const int gidx = g0 + gg * gs;
             const int t0 = gidx * kLpGroup;
-            mbar_wait_warp(&S.bar_staged[gg & 1], (uint32_t)(gg >> 1) & 1u);
-            if (elect_one()) {
-                if (!(P.skip & 1)) {
-                    for (int mt = 0; mt < MT; ++mt)
+            for (int mt = 0; mt < MT; ++mt) {
+                // M-tile by M-tile: the boxes of tile 0 are on their way while the epilogue warps still stage tile 1
+                mbar_wait_warp(&S.bar_staged[(gg & 1) * 2 + mt], (uint32_t)(gg >> 1) & 1u);
+                if (elect_one()) {
+                    if (!(P.skip & 1)) {
                         for (int h = 0; h < 2; ++h)
                             tma_store_3d(&omap, stage + (size_t)(mt * 2 + h) * 16384, t0 + 32 * h, (mt0 + mt) * 128, b);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read();
+                    mbar_arrive(&S.bar_stfree[mt]);              // the boxes of this M-tile may be refilled
                 }
-                tma_store_commit();
-                tma_store_wait_read();
-                mbar_arrive(S.bar_stfree);                       // the staging boxes may be refilled
+                __syncwarp();
+            }
+            if (elect_one()) {
                 if (P.flags != nullptr) {
                     // publish the group to the MAS kernel running next to this one: bulk stores complete ->
                     // async-proxy / generic-proxy fence -> device-scope release
@@ -124,15 +131,16 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
             const int p = gg & 3;
             uint32_t d0[2][32], d1[2][32];
             lp_aux_drain(S, F, gg, warp, MT, tmem, d0, d1, MTMAX);
-            if (gg >= 1) {                                       // the store warp has read the previous group's boxes
-                const long long c0 = clock64();
-                mbar_wait(S.bar_stfree, (uint32_t)(gg - 1) & 1u);
-                w_stfree += clock64() - c0;
-            }
 #pragma unroll
             for (int mt = 0; mt < MTMAX; ++mt) {
+                if (mt >= MT) break;
+                if (gg >= 1) {                                   // the store warp has read this tile's previous boxes
+                    const long long c0 = clock64();
+                    mbar_wait(&S.bar_stfree[mt], (uint32_t)(gg - 1) & 1u);
+                    w_stfree += clock64() - c0;
+                }
                 const int x = (mt0 + mt) * 128 + tid;
-                if (mt < MT && x < P.Tx && !(P.skip & 8)) {
+                if (x < P.Tx && !(P.skip & 8)) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         unsigned char *box = stage + (size_t)(mt * 2 + h) * 16384 + (size_t)tid * 128;
@@ -149,9 +157,9 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                         }
                     }
                 }
+                fence_proxy_async_smem();                        // staging stores -> visible to the TMA store
+                mbar_arrive(&S.bar_staged[(gg & 1) * 2 + mt]);
             }
-            fence_proxy_async_smem();                            // staging stores -> visible to the TMA store
-            mbar_arrive(&S.bar_staged[gg & 1]);
         }
         if (dbg && tid == 0) dbg[14] = w_stfree;
     }

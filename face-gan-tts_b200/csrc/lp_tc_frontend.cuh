@@ -53,7 +53,7 @@ struct LpFront {
     unsigned char *raw, *hi, *lo;
     float *part, *ysq;
     uint64_t *bar_raw /*[2]*/, *bar_split /*[2]*/, *bar_dfull, *bar_dempty, *bar_aready, *bar_mu, *bar_bfree /*[2]*/,
-        *bar_staged /*[2]*/, *bar_stfree;
+        *bar_staged /*[2 parities][2 M-tiles]*/, *bar_stfree /*[2 M-tiles]*/;
     uint32_t *tmem_slot;
     long long *prof = nullptr;     // diagnostics: per-CTA wait-cycle accumulators (see scripts/timeline.py), normally null
     __device__ __forceinline__ void carve(unsigned char *base, int F) {
@@ -64,7 +64,7 @@ struct LpFront {
         ysq = reinterpret_cast<float *>(base + LpFrontSmem::off_ysq(F));
         uint64_t *b = reinterpret_cast<uint64_t *>(base + LpFrontSmem::off_bars(F));
         bar_raw = b; bar_split = b + 2; bar_dfull = b + 4; bar_dempty = b + 5; bar_aready = b + 6; bar_mu = b + 7;
-        bar_bfree = b + 8; bar_staged = b + 10; bar_stfree = b + 12;
+        bar_bfree = b + 8; bar_staged = b + 10; bar_stfree = b + 14;
         tmem_slot = reinterpret_cast<uint32_t *>(base + LpFrontSmem::off_tmem(F));
     }
     __device__ __forceinline__ void init_barriers() {       // one thread
@@ -73,7 +73,8 @@ struct LpFront {
         mbar_init(bar_dfull, 1); mbar_init(bar_dempty, kLpAux);
         mbar_init(bar_aready, kLpAux); mbar_init(bar_mu, 1);
         mbar_init(&bar_bfree[0], 1); mbar_init(&bar_bfree[1], 1);
-        mbar_init(&bar_staged[0], kLpAux); mbar_init(&bar_staged[1], kLpAux); mbar_init(bar_stfree, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_staged[i], kLpAux);
+        mbar_init(&bar_stfree[0], 1); mbar_init(&bar_stfree[1], 1);
     }
 };
 
