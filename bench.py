@@ -189,6 +189,58 @@ def run_reference(args):
     }))
 
 
+def time_compute_loss_block(dev, out_size=128):
+    """ms per forward+backward of the alignment block at the bench shape: this library vs the reference's way."""
+    import random
+
+    import oracle
+    from face_gan_tts_b200 import losses, synthetic
+
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, TX, TY, seed=1234)
+    g = torch.Generator().manual_seed(7)
+    x_mask = (torch.arange(TX)[None, :] < t_x[:, None]).float().unsqueeze(1)
+    logw = torch.randn(B, 1, TX, generator=g) * x_mask
+    mu_d, y_d, lw_d, xm_d = mu_x.to(dev), y.to(dev), logw.to(dev), x_mask.to(dev)
+    off = losses.draw_crop_offsets(t_y.tolist(), out_size, random.Random(5))
+
+    def ours():
+        mu = mu_d.detach().requires_grad_(True)
+        lw = lw_d.detach().requires_grad_(True)
+        o = losses.alignment_losses(mu, lw, t_x, y_d, t_y, out_size=out_size, out_offset=off)
+        (o.dur_loss + o.prior_loss + o.mu_y.sum()).backward()
+        return o.prior_loss.detach()
+
+    core = oracle.reference_core("asis")
+    ty_l, tx_l = t_y.long().to(dev), t_x.long().to(dev)
+    off_t = torch.as_tensor(off).long()
+
+    def ref():
+        mu = mu_d.detach().requires_grad_(True)
+        lw = lw_d.detach().requires_grad_(True)
+        r = oracle.compute_loss_block(mu, lw, xm_d, y_d, ty_l, tx_l, F, out_size=out_size, out_offset=off_t,
+                                      maximum_path_fn=lambda v, m: oracle.maximum_path(v, m, core=core))
+        (r["dur_loss"] + r["prior_loss"] + r["mu_y"].sum()).backward()
+        return r["prior_loss"].detach()
+
+    def wall(fn, n):
+        fn(); torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            v = fn()
+        float(v)                                   # the loss is read back, as a training step logs it
+        return (time.perf_counter() - t0) / n * 1e3
+
+    ms_ours = wall(ours, 50)
+    out = {"shape": f"B={B} F={F} Tx={TX} Ty={TY} out_size={out_size}", "this_library_ms": ms_ours,
+           "what": "masks -> log-prior -> MAS -> duration loss -> crop -> mu_y -> prior loss, forward + backward"}
+    if core is not None:
+        ms_ref = wall(ref, 3)
+        out.update({"reference_formulation_ms": ms_ref, "speedup": ms_ref / ms_ours})
+        a, b_ = float(ours()), float(ref())
+        out["prior_loss_rel_diff"] = abs(a - b_) / abs(b_)
+    return out
+
+
 # ----------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
     import face_gan_tts_b200 as fgt
@@ -236,12 +288,14 @@ def run_cuda(args):
     gathered = [torch.empty((world * B, TX), dtype=torch.int32, device=dev) for _ in range(2)] if dist else None
     comm_stream = torch.cuda.Stream(dev) if dist else None
 
+    step_done = [torch.cuda.Event() for _ in range(4)] if dist else None
+
     def step(i):
         d = sets[i % NSETS]
         fused(d, wss[i % NSETS])
         if dist:
             # loss-bookkeeping collective: durations of every rank, asynchronous on a side stream
-            ev = torch.cuda.Event()
+            ev = step_done[i % 4]
             ev.record(stream)
             comm_stream.wait_event(ev)
             with torch.cuda.stream(comm_stream):
@@ -261,8 +315,10 @@ def run_cuda(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
+    host_t0 = time.perf_counter()
     for i in range(K):
         step(W + i)
+    host_enqueue_us = (time.perf_counter() - host_t0) / K * 1e6      # host time to enqueue one step (no sync inside)
     if dist:
         stream.wait_stream(comm_stream)      # all gathers complete inside the timed region
     e1.record(stream)
@@ -428,6 +484,17 @@ def run_cuda(args):
         except Exception as ex:  # the oracle is a reported baseline, never a dependency of the product
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
+        # ---- configs[2] at the bench shape: the whole alignment block of compute_loss (face_tts.py:159-218,233-234),
+        # forward + backward w.r.t. mu_x / logw.  "reference" = the reference's formulation on the SAME GPU tensors
+        # (torch log-prior GEMMs on the device, its maximum_path wrapper bouncing value/mask to the host for the
+        # compiled core.pyx and back, dense attn consumers) -- what a training step pays today.
+        block = None
+        if world == 1:
+            try:
+                block = time_compute_loss_block(dev)
+            except Exception as ex:
+                block = {"error": repr(ex)[:200]}
+
         # overlapped pipeline (B <= SMs/2, no profiler attached): tcgen05 log-prior kernel (which also expands the
         # dense path) + MAS kernel; serial pipeline: log-prior, MAS, path_expand
         overlapped = os.environ.get("MAS_B200_PIPELINE", "") != "serial" and 2 * B <= 148 and \
@@ -444,8 +511,8 @@ def run_cuda(args):
                        "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 61} MB) larger than the 126 MB L2",
                        "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
                        else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_padded_copy": e2e_padded, "e2e_dense_path": e2e_dense,
-            "gpu_launches": launches_per_step * K, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "compute_loss_block": block, "e2e": e2e, "e2e_padded_copy": e2e_padded, "e2e_dense_path": e2e_dense,
+            "gpu_launches": launches_per_step * K, "host_enqueue_us_per_step": host_enqueue_us, "clocks": clocks,
         }
     if dist:
         dist.barrier()

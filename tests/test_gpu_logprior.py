@@ -174,6 +174,33 @@ def test_overlapped_pipeline_equals_serial_pipeline(B, F):
     assert int(a.status.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("F", [80, 128])
+def test_overlapped_pipeline_soak(F):
+    """300 back-to-back overlapped calls over rotating inputs and workspaces, no host sync in between: every result
+    must equal the serial pipeline's.  Guards the cross-kernel protocol (bulk-store completion -> proxy fence ->
+    release flag -> acquire -> TMA load; flag reset by the next call's memset; done flags -> path writers)."""
+    from face_gan_tts_b200 import _lib
+
+    B, nset = 32, 3
+    sets = []
+    for k in range(nset):
+        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=190, Ty=1000, seed=100 + k)
+        sets.append((mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV)))
+    prev = _lib.set_option("fused_impl", 1)
+    try:
+        want = [fgt.log_prior_maximum_path(*s_, path_dtype=torch.float32) for s_ in sets]
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("fused_impl", prev)
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    for i in range(300):
+        r = fgt.log_prior_maximum_path(*sets[i % nset], path_dtype=torch.float32)
+        w = want[i % nset]
+        bad += (r.durations != w.durations).sum() + (r.frame_token != w.frame_token).sum() + (r.path != w.path).sum()
+    torch.cuda.synchronize()
+    assert int(bad) == 0
+
+
 def test_overlapped_pipeline_rejects_bad_items_without_hanging():
     """t_x > t_y is undefined in the reference (core.pyx:34); here the item is rejected, its outputs are zero, and the
     producer/consumer flag protocol of the overlapped pipeline still terminates."""
