@@ -207,6 +207,21 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
                 job.dur = mas_dur_table(workspace_dev, B, Tx, Ty, durations_dev);
                 job.done = done; job.path = path_dev; job.path_dtype = path_dtype;
             }
+            if (fi == 3) {
+                // diagnostics only: log-prior first (serial), then the GATED MAS kernel with every flag already set --
+                // isolates the cost of the gating code path from the cost of waiting for the producer
+                rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, s);
+                if (rc != MAS_B200_OK) return rc;
+                MASB200_CUDA_TRY(cudaMemsetAsync(flags, 1, sizeof(int) * ((size_t)B * ngroups + B), s));
+                MasLaunch G{};
+                G.value = value; G.stride_b = (long long)Tx * Ty; G.stride_x = Ty;
+                G.t_x = t_x_dev; G.t_y = t_y_dev; G.B = B; G.Tx = Tx; G.Ty = Ty; G.neg = max_neg_val;
+                G.path = path_dev; G.path_dtype = path_dtype;
+                G.durations = durations_dev; G.frame_token = frame_token_dev; G.status = status_dev;
+                G.workspace = workspace_dev; G.workspace_bytes = mas_ws; G.stream = s;
+                G.gate = flags; G.gate_pitch = ngroups; G.gate_need = 1;
+                return launch_mas(G);
+            }
             MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)B * ngroups + B), s));
             MASB200_CUDA_TRY(cudaEventRecord(aux->fork, s));
             MASB200_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));

@@ -540,7 +540,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             // ============================ producer warp ============================
             int stage = 0;
             uint32_t phase = 0;
-            long long gate_spins = 0;
+            long long gate_spins = 0, gate_cycles = 0, gate_first = 0;
             int gate_known = 0;                                // groups [0, gate_known) are known to be in memory
             int jt_next = 0;                                   // next tile whose transfer table (upper groups) is owed
             const int *flag_last = hprog + (w_act - 1);
@@ -563,6 +563,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                         ++gate_spins;
                         if (clock64() - c0 > (1ll << 31)) __trap();
                     }
+                    { const long long dc = clock64() - c0; gate_cycles += dc; if (j == 0) gate_first = dc; }
                     asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> the TMA reads below
                     __syncwarp();
                 }
@@ -615,7 +616,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 }
             }
             if (lane == 0) bt_state[3] = jt_next;      // the rest is shared by all warps once the DP is done
-            if (dbg && lane == 0) { dbg[10] = gate_spins; dbg[11] = jt_next; dbg[15] = clock64(); }
+            if (dbg && lane == 0) { dbg[10] = gate_spins; dbg[11] = jt_next; dbg[15] = clock64(); dbg[9] = gate_cycles; dbg[8] = gate_first; }
         } else if (SMEM_BITS && warp == W + 1) {
             // ========================== backtrack helper warp ==========================
             // trails the LAST active DP warp (its progress flag implies every earlier warp is past the tile too)

@@ -46,7 +46,7 @@ print("MAS gate spins       :", dm[:8, 10].tolist())
 i = int(torch.argmax(dm[:, 13]))
 s_ = dm[i].tolist()
 print(f"slowest MAS CTA b={i} t_x={s_[7] >> 32} t_y={s_[7] & 0xffffffff}: dp_done {s_[2]-s_[0]} all_warps {s_[4]-s_[0]} backtrack {s_[5]-s_[4]} tail {s_[6]-s_[5]} total {s_[6]-s_[0]} cycles; spins {s_[10]}")
-print(f"  helper done {s_[14]-s_[0]}  producer done {s_[15]-s_[0]}")
+print(f"  helper done {s_[14]-s_[0]}  producer done {s_[15]-s_[0]}; gate wait cycles total {s_[9]} (first group {s_[8]})")
 # same batch through the serial pipeline (MAS ungated)
 _lib.set_option("fused_impl", 1)
 for _ in range(3): call()
@@ -56,3 +56,12 @@ _lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0); 
 s2 = dm2.cpu()[i].tolist()
 print(f"ungated    b={i}: dp_done {s2[2]-s2[0]} all_warps {s2[4]-s2[0]} backtrack {s2[5]-s2[4]} tail {s2[6]-s2[5]} total {s2[6]-s2[0]}; helper done {s2[14]-s2[0]} producer done {s2[15]-s2[0]}")
 
+
+# gated MAS with every flag preset (log-prior run before it): cost of the gating code path alone
+_lib.set_option("fused_impl", 3)
+for _ in range(3): call()
+dm3 = torch.zeros((B, 16), dtype=torch.int64, device=dev)
+setp("mas_debug_ptr", dm3); call(); torch.cuda.synchronize()
+_lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0); _lib.set_option("fused_impl", 0)
+s3 = dm3.cpu()[i].tolist()
+print(f"gated, flags preset b={i}: dp_done {s3[2]-s3[0]} all_warps {s3[4]-s3[0]} backtrack {s3[5]-s3[4]} tail {s3[6]-s3[5]} total {s3[6]-s3[0]}; spins {s3[10]} producer done {s3[15]-s3[0]}")
