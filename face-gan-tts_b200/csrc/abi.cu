@@ -239,8 +239,11 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
             if (rc != MAS_B200_OK) return rc;
             L.dry_run = 0;
             // producer first (the block scheduler must place its CTAs before the consumer's start spinning)
-            rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, aux->stream, flags, ngroups, di.sm_count - B,
+            // The log-prior kernel is on the critical path (the search cannot start before its first group), so it
+            // stays on the caller's stream right behind the memset; the MAS kernel takes the cross-stream hop.
+            rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, s, flags, ngroups, di.sm_count - B,
                                      want_path ? &job : nullptr);
+            L.stream = aux->stream;
             if (rc == MAS_B200_OK) rc = launch_mas(L);
             MASB200_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
             // join even on error so the aux stream never runs ahead of the caller's stream
