@@ -409,19 +409,22 @@ def run_cuda(args):
     # bytes the ragged upload actually reads over PCIe, counted from the host batches it copies (mean over the NH sets;
     # 16-byte granularity along y rows)
     h2d = int(sum(4 * F * int((t[2].long() + ((t[3].long() + 3) // 4) * 4).sum()) + 8 * B for t in host_in) / NH)
-    sec_e2e = time_e2e(False)
-    sec_e2e_padded = time_e2e(False, ragged=False)
-    sec_e2e_dense = time_e2e(True)
-    e2e = {"value": world * CELLS / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+    # The headline e2e moves the padded tensors with the copy engine (50.6 GB/s, within 1 % run to run).  The ragged
+    # zero-copy upload moves a third fewer bytes but SM-issued PCIe reads reach only 36-41 GB/s and vary box to box
+    # (228-260 us per step measured), so it is reported beside it, not instead of it.
+    sec_e2e = time_e2e(False, ragged=False)
+    sec_e2e_ragged = time_e2e(False, ragged=True)
+    sec_e2e_dense = time_e2e(True, ragged=False)
+    e2e = {"value": world * CELLS / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
            "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e * 1e3,
            "result": "durations [B,Tx] + frame->token index [B,Ty] (dense path stays in HBM for mu_y)",
-           "h2d": "mas_b200_upload_batch: padded pinned host tensors in, only the valid rows' [0,t_x)/[0,t_y) cross "
-                  f"PCIe (padding zero-filled on the device); a plain copy of the padded tensors is {h2d_padded} bytes",
+           "h2d": "cudaMemcpyAsync of the padded pinned tensors (copy engine)",
            "pipelining": "H2D of step i+1 on a copy stream under step i; host consumes result i-1 while step i runs"}
-    e2e_padded = {"value": world * CELLS / sec_e2e_padded, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
-                  "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e_padded * 1e3,
-                  "h2d": "cudaMemcpyAsync of the padded tensors (copy engine)"}
-    e2e_dense = {"value": world * CELLS / sec_e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d,
+    e2e_ragged = {"value": world * CELLS / sec_e2e_ragged, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e_ragged * 1e3,
+                  "h2d": "mas_b200_upload_batch: only the valid rows' [0,t_x)/[0,t_y) cross PCIe (zero-copy pull kernel, "
+                         "padding zero-filled on the device)"}
+    e2e_dense = {"value": world * CELLS / sec_e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
                  "d2h_bytes_per_step": 4 * B * (TX + TY) + 4 * CELLS, "ms_per_step": sec_e2e_dense * 1e3}
 
     out = None
@@ -511,7 +514,7 @@ def run_cuda(args):
                        "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 61} MB) larger than the 126 MB L2",
                        "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
                        else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "compute_loss_block": block, "e2e": e2e, "e2e_padded_copy": e2e_padded, "e2e_dense_path": e2e_dense,
+            "roofline": roofline, "cpu_baseline": cpu, "compute_loss_block": block, "e2e": e2e, "e2e_ragged_upload": e2e_ragged, "e2e_dense_path": e2e_dense,
             "gpu_launches": launches_per_step * K, "host_enqueue_us_per_step": host_enqueue_us, "clocks": clocks,
         }
     if dist:

@@ -52,8 +52,9 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     // prologue, by the same threads) -- then the split warps start on the first y groups while the prologue runs --
     // else in the hi/lo operand buffers (4 * F * 64 * 4 bytes >= F * Tx * 4 for Tx <= 256), which the split warps
     // may only fill once every epilogue thread has left the prologue (bar_aready).
-    const bool mu_in_stage = (size_t)F * P.Tx * 4 <= (size_t)MTMAX * 32768;
-    float *mu_s = reinterpret_cast<float *>(mu_in_stage ? stage : S.hi);
+    // The split-M form stages nothing: its prologue reads the CTA's 128 columns of mu_x from global memory.
+    const bool mu_in_stage = SPLITM || (size_t)F * P.Tx * 4 <= (size_t)MTMAX * 32768;
+    float *mu_s = SPLITM ? nullptr : reinterpret_cast<float *>(mu_in_stage ? stage : S.hi);
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
@@ -122,7 +123,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
         __syncwarp();
     } else {
         float musq[2];
-        lp_aux_prologue<KS>(S, mu_s, P.Tx, MT, tmem, tid, warp, [mt0](int mt, int m) { return (mt0 + mt) * 128 + m; }, musq);
+        lp_aux_prologue<KS, SPLITM>(S, SPLITM ? P.mu + (size_t)b * F * P.Tx : mu_s, P.Tx, MT, tmem, tid, warp,
+                                    [mt0](int mt, int m) { return (mt0 + mt) * 128 + m; }, musq);
         if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[4] = t; }
         if (dbg && tid == 0) dbg[3] = clock64();
         long long w_stfree = 0;
@@ -258,7 +260,7 @@ static int make_out_tensor_map(float *out, int B, int Tx, int Ty, CUtensorMap *m
 
 // shapes the tensor-core kernel takes; everything else goes to the FFMA kernel
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty) {
-    if (!(F == 64 || F == 80 || F == 96 || F == 128) || Tx > 256 || Ty % 4 != 0 || B > 65535) return false;
+    if (!(F == 64 || F == 80 || F == 96 || F == 128) || Tx > 128 * 65535 || Ty % 4 != 0 || B > 65535) return false;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(mu_x) & 15))
         return false;
     return true;
@@ -266,8 +268,11 @@ bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out,
 
 // CTAs the kernel needs co-resident at least (one per utterance and M-tile) and the count a `flags` entry reaches
 // when a group is complete -- what the overlapped pipeline (abi.cu) sizes itself with.
-int log_prior_tc_min_ctas(int B, int F, int Tx) { return F > kMaxF ? B * ((Tx + 127) / 128) : B; }
-int log_prior_tc_flag_target(int F, int Tx) { return F > kMaxF ? (Tx + 127) / 128 : 1; }
+// split-M (one CTA per 128-row M-tile): n_feats = 128, whose A operand alone fills TMEM, and texts longer than the
+// two M-tiles one CTA holds
+static bool lp_split_m(int F, int Tx) { return F > kMaxF || Tx > 256; }
+int log_prior_tc_min_ctas(int B, int F, int Tx) { return lp_split_m(F, Tx) ? B * ((Tx + 127) / 128) : B; }
+int log_prior_tc_flag_target(int F, int Tx) { return lp_split_m(F, Tx) ? (Tx + 127) / 128 : 1; }
 
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
                         cudaStream_t stream, int *flags, int flag_pitch, int max_ctas, const PathJob *job) {
@@ -296,7 +301,7 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     }
     if (job) P.job = *job;
     P.skip = option("lp_debug_skip");
-    const bool splitm = F > kMaxF;
+    const bool splitm = lp_split_m(F, Tx);
     const int mtiles = splitm ? (Tx + 127) / 128 : 1;          // grid.z
     const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;
     int chunks = cta_budget / (B * mtiles);                                // one wave of CTAs (one CTA per SM: TMEM + smem)
@@ -310,16 +315,16 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
 
     void (*kern)(const LpTcParams, const CUtensorMap, const CUtensorMap) = nullptr;
     switch (F) {
-        case 64: kern = log_prior_tc_kernel<8, false>; break;
-        case 80: kern = log_prior_tc_kernel<10, false>; break;
-        case 96: kern = log_prior_tc_kernel<12, false>; break;
+        case 64: kern = splitm ? log_prior_tc_kernel<8, true> : log_prior_tc_kernel<8, false>; break;
+        case 80: kern = splitm ? log_prior_tc_kernel<10, true> : log_prior_tc_kernel<10, false>; break;
+        case 96: kern = splitm ? log_prior_tc_kernel<12, true> : log_prior_tc_kernel<12, false>; break;
         case 128: kern = log_prior_tc_kernel<16, true>; break;
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
-    static std::atomic<int> configured[16][4];
+    static std::atomic<int> configured[16][8];
     int dev = 0;
     MASB200_CUDA_TRY(cudaGetDevice(&dev));
-    const int ki = F == 64 ? 0 : (F == 80 ? 1 : (F == 96 ? 2 : 3));
+    const int ki = (F == 64 ? 0 : (F == 80 ? 1 : (F == 96 ? 2 : 3))) + (splitm ? 4 : 0);
     if (dev < 0 || dev >= 16 || !configured[dev][ki].load(std::memory_order_acquire)) {
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         if (dev >= 0 && dev < 16) configured[dev][ki].store(1, std::memory_order_release);

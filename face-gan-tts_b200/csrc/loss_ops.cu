@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(kThreads) prior_loss_finish_kernel(const doubl
 
 // grad_mu_x[b,f,x] = sum over the frames token x owns of grad_mu_y[b,f,t].  A token's frames are contiguous
 // ([start, start+dur), shifted by the crop window when there is one): a segmented sum in a fixed order.
+// One WARP per token (lanes stride the token's frames, so a 200-frame silence token costs 7 coalesced passes instead
+// of one thread looping 200 times), kF feature rows per warp, xor-shuffle tree at the end: the order of the
+// additions is fixed by (lane, tree), hence deterministic.
 // kPrior: instead of reading grad_mu_y, the summand is the prior-loss derivative  -(y - mu_x[x]) * g / denom.
+constexpr int kSegWarps = kThreads / 32;      // tokens per CTA
 template <bool kPrior>
 __global__ void __launch_bounds__(kThreads) segment_sum_kernel(const float *__restrict__ g, const float *__restrict__ mu_x,
                                                                const int *__restrict__ start, const int *__restrict__ dur,
@@ -119,8 +123,9 @@ __global__ void __launch_bounds__(kThreads) segment_sum_kernel(const float *__re
                                                                const float *__restrict__ gscale, int B, int F, int Tx,
                                                                int Ty, float *__restrict__ gx) {
     const int b = blockIdx.z, f0 = blockIdx.y * kF;
-    const int x = blockIdx.x * kThreads + threadIdx.x;
-    if (x >= Tx) return;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+    if (x >= Tx) return;                                   // warp-uniform
     const int o = off ? off[b] : 0;
     const int hi = len ? min(max(len[b], 0), Ty) : Ty;
     const int s0 = start[(size_t)b * Tx + x] - o;
@@ -129,24 +134,34 @@ __global__ void __launch_bounds__(kThreads) segment_sum_kernel(const float *__re
     const float *gb = g + ((size_t)b * F + f0) * Ty;
     float scale = 1.f;
     if (kPrior) {
-        double l = 0.0;      // B additions per thread: cheaper than a third kernel for B of a few hundred
-        for (int i = 0; i < B; ++i) l += (double)min(max(len ? len[i] : Ty, 0), Ty);
+        double l = 0.0;      // sum of the (clamped) lengths: B/32 additions per lane + a shuffle tree
+        for (int i = lane; i < B; i += 32) l += (double)min(max(len ? len[i] : Ty, 0), Ty);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(kFullMask, l, d);
         scale = -gscale[0] / (float)(l * (double)F);
     }
     float acc[kF], m[kF];
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
         acc[k] = 0.f;
-        m[k] = (kPrior && f0 + k < F) ? mu_x[((size_t)b * F + f0 + k) * Tx + x] : 0.f;
+        m[k] = (kPrior && f0 + k < F) ? __ldg(mu_x + ((size_t)b * F + f0 + k) * Tx + x) : 0.f;
     }
-    for (int t = s; t < e; ++t) {
+    for (int t = s + lane; t < e; t += 32) {
 #pragma unroll
         for (int k = 0; k < kF; ++k)
             if (f0 + k < F) acc[k] += __ldg(gb + (size_t)k * Ty + t) - m[k];
     }
 #pragma unroll
-    for (int k = 0; k < kF; ++k)
-        if (f0 + k < F) gx[((size_t)b * F + f0 + k) * Tx + x] = acc[k] * scale;
+    for (int k = 0; k < kF; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(kFullMask, acc[k], d);
+    }
+    if (lane < kF && f0 + lane < F) {
+        float v = acc[0];
+#pragma unroll
+        for (int k = 1; k < kF; ++k) v = (lane == k) ? acc[k] : v;
+        gx[((size_t)b * F + f0 + lane) * Tx + x] = v * scale;
+    }
 }
 
 // One CTA: loss = sum_{b,x} (logw - logw_)^2 / sum_b x_len,  logw_ = log(1e-8 + dur) * (x < x_len).
@@ -238,7 +253,7 @@ int launch_gather_mu_y_bwd(const float *grad_mu_y, const int *start, const int *
                            const int *lengths, int B, int F, int Tx, int Ty, float *grad_mu_x, cudaStream_t stream) {
     if (!grad_mu_y || !start || !dur || !grad_mu_x || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!grid_ok(B, F)) return MAS_B200_ERR_UNSUPPORTED;
-    dim3 grid((Tx + kThreads - 1) / kThreads, (F + kF - 1) / kF, B);
+    dim3 grid((Tx + kSegWarps - 1) / kSegWarps, (F + kF - 1) / kF, B);
     segment_sum_kernel<false><<<grid, kThreads, 0, stream>>>(grad_mu_y, nullptr, start, dur, offsets, lengths, nullptr, B,
                                                              F, Tx, Ty, grad_mu_x);
     MASB200_CUDA_TRY(cudaGetLastError());
@@ -251,7 +266,7 @@ int launch_prior_loss_bwd(const float *y, const float *mu_x, const int *start, c
     if (!y || !mu_x || !start || !dur || !y_lengths || !grad_loss || !grad_mu_x || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0)
         return MAS_B200_ERR_ARG;
     if (!grid_ok(B, F)) return MAS_B200_ERR_UNSUPPORTED;
-    dim3 grid((Tx + kThreads - 1) / kThreads, (F + kF - 1) / kF, B);
+    dim3 grid((Tx + kSegWarps - 1) / kSegWarps, (F + kF - 1) / kF, B);
     segment_sum_kernel<true><<<grid, kThreads, 0, stream>>>(y, mu_x, start, dur, offsets, y_lengths, grad_loss, B, F, Tx,
                                                             Ty, grad_mu_x);
     MASB200_CUDA_TRY(cudaGetLastError());

@@ -120,9 +120,11 @@ __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap 
     constexpr int NRAW = LpFrontSmem::nraw(F);
     if (elect_one()) {
         // the utterance's whole mu_x block [F][Tx] in one bulk copy (16-byte aligned since F % 4 == 0)
-        const uint32_t mu_bytes = (uint32_t)F * (uint32_t)Tx * 4u;
-        mbar_arrive_expect_tx(S.bar_mu, mu_bytes);
-        tma_bulk_load_1d(mu_stage, mu_b, mu_bytes, S.bar_mu);
+        if (mu_stage != nullptr) {
+            const uint32_t mu_bytes = (uint32_t)F * (uint32_t)Tx * 4u;
+            mbar_arrive_expect_tx(S.bar_mu, mu_bytes);
+            tma_bulk_load_1d(mu_stage, mu_b, mu_bytes, S.bar_mu);
+        }
         for (int q = 0; q < NRAW && q < ng; ++q) {
             mbar_arrive_expect_tx(&S.bar_raw[q], LpFrontSmem::raw_bytes(F));
             tma_load_3d(S.raw + (size_t)q * LpFrontSmem::raw_bytes(F), ymap, t_begin + q * t_stride, 0, b, &S.bar_raw[q]);
@@ -177,12 +179,15 @@ __device__ __forceinline__ void lp_mma_warp(const LpFront &S, const CUtensorMap 
 // MMA(g) and epilogue(g-1); hand-offs are mbarriers only (raw -> split -> MMA -> epilogue, bfree: MMA -> split).
 // ---------------------------------------------------------------------------------------------------
 // A prologue: row_of(mt, m) gives the text position parked in lane m of M-tile mt (any permutation).
-template <int KS, class RowOf>
+// mu_stage: the utterance's [F][Tx] block, in shared memory (GLOBAL_MU = false: staged by the MMA warp's bulk copy,
+// bar_mu) or straight in global memory (GLOBAL_MU = true: the split-M form reads only its own 128 columns, which
+// no 16-byte-aligned bulk copy can express for odd Tx; consecutive threads read consecutive x: coalesced).
+template <int KS, bool GLOBAL_MU = false, class RowOf>
 __device__ __forceinline__ void lp_aux_prologue(const LpFront &S, const float *mu_stage, int Tx, int MT, uint32_t tmem,
                                                 int tid, int warp, RowOf row_of, float (&musq)[2]) {
     constexpr int F = 8 * KS;
     const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-    mbar_wait(S.bar_mu, 0);
+    if (!GLOBAL_MU) mbar_wait(S.bar_mu, 0);
     musq[0] = musq[1] = 0.f;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -195,7 +200,7 @@ __device__ __forceinline__ void lp_aux_prologue(const LpFront &S, const float *m
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const float v = xin ? mu_stage[(f0 + k) * Tx + x] : 0.f;
+                    const float v = xin ? (GLOBAL_MU ? __ldg(mu_stage + (size_t)(f0 + k) * Tx + x) : mu_stage[(f0 + k) * Tx + x]) : 0.f;
                     tf32_split(v, hi[k], lo[k]);
                     sq = fmaf(-0.5f * v, v, sq);
                 }

@@ -135,7 +135,9 @@ def test_tcgen05_kernel_is_the_one_running_and_matches_ffma():
 
     # F = 128 (the reference default n_feats) runs the split-M form: one CTA per 128-row M-tile
     for (B, F, Tx, Ty) in [(3, 80, 190, 1000), (2, 64, 129, 136), (2, 96, 256, 420), (5, 80, 37, 68),
-                           (3, 128, 190, 1000), (2, 128, 256, 420), (4, 128, 61, 200), (2, 128, 128, 132), (1, 128, 129, 132)]:
+                           (3, 128, 190, 1000), (2, 128, 256, 420), (4, 128, 61, 200), (2, 128, 128, 132), (1, 128, 129, 132),
+                           # texts longer than two M-tiles: split-M for every n_feats (cfg4: Tx = 512)
+                           (2, 80, 512, 640), (1, 96, 300, 304), (2, 64, 257, 260), (1, 128, 513, 516), (1, 80, 1000, 1000)]:
         mu_x, y, _, _ = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=7, tx_lo=max(1, Tx // 3), ty_lo=max(Tx // 3, Ty // 3))
         mu_d, y_d = mu_x.to(DEV), y.to(DEV)
         tc = fgt.log_prior(mu_d, y_d, impl="tcgen05")
@@ -172,6 +174,27 @@ def test_overlapped_pipeline_equals_serial_pipeline(B, F):
     assert torch.equal(a.frame_token, b.frame_token) and torch.equal(a.status, b.status)
     assert torch.equal(a.path.sum(-1).int(), a.durations)
     assert int(a.status.abs().sum()) == 0
+
+
+def test_overlapped_pipeline_long_text_split_m():
+    """Tx = 300 (three M-tile CTAs per utterance, flags count to 3) through the overlapped pipeline == serial."""
+    from face_gan_tts_b200 import _lib
+
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=8, F=80, Tx=300, Ty=1000, seed=21, tx_lo=100, ty_lo=400)
+    mu_d, y_d = mu_x.to(DEV), y.to(DEV)
+    outs = []
+    for mode in (0, 1):
+        prev = _lib.set_option("fused_impl", mode)
+        try:
+            for _ in range(3):
+                r = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, path_dtype=torch.float32)
+            torch.cuda.synchronize()
+            outs.append(r)
+        finally:
+            _lib.set_option("fused_impl", prev)
+    a, b = outs
+    assert torch.equal(a.path, b.path) and torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token)
+    assert int(a.status.abs().sum()) == 0 and torch.equal(a.path.sum(-1).int(), a.durations)
 
 
 @pytest.mark.parametrize("F", [80, 128])
