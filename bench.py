@@ -255,6 +255,10 @@ def run_cuda(args):
 
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the only collective is a 24 KB all-gather that runs beside the next step's kernels: one channel (one CTA)
+        # is plenty and keeps NCCL off the SMs the two co-resident alignment kernels need
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("MAS_B200_NCCL_CHANNELS", "1"))
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -277,13 +281,15 @@ def run_cuda(args):
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
-    def fused(d, ws, dense=True):
+    def fused(d, ws, dense=True, on=None):
         rc = L.mas_b200_log_prior_maximum_path(
             d["mu"].data_ptr(), d["y"].data_ptr(), d["tx"].data_ptr(), d["ty"].data_ptr(), B, F, TX, TY, -1e9,
             d["path"].data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
             d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes,
-            _lib.LP_AUTO, sp)
+            _lib.LP_AUTO, sp if on is None else on.cuda_stream)
         _lib.check(rc, "mas_b200_log_prior_maximum_path")
+
+    graphs = [None]      # multi-GPU: CUDA graphs of the fused call, one per buffer set (see below)
 
     gathered = [torch.empty((world * B, TX), dtype=torch.int32, device=dev) for _ in range(2)] if dist else None
     comm_stream = torch.cuda.Stream(dev) if dist else None
@@ -292,7 +298,10 @@ def run_cuda(args):
 
     def step(i):
         d = sets[i % NSETS]
-        fused(d, wss[i % NSETS])
+        if graphs[0] is not None:
+            graphs[0][i % NSETS].replay()
+        else:
+            fused(d, wss[i % NSETS])
         if dist:
             # loss-bookkeeping collective: durations of every rank, asynchronous on a side stream
             ev = step_done[i % 4]
@@ -309,6 +318,28 @@ def run_cuda(args):
     for i in range(W):
         step(i)
     barrier()
+    if dist and not args.no_graph:
+        # With the NCCL enqueue beside it, one step costs ~56 us of host time per rank -- as long as the step itself --
+        # so the fused call (memset, fork, two kernels, join: captured as-is, scripts/graph_probe.py) is replayed
+        # from a CUDA graph per buffer set (5 us of host time); the all-gather stays an eager NCCL call.
+        try:
+            cap = torch.cuda.Stream(dev)
+            cap.wait_stream(stream)
+            gl = []
+            for s_ in range(NSETS):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=cap):
+                    fused(sets[s_], wss[s_], on=torch.cuda.current_stream(dev))
+                gl.append(g_)
+            torch.cuda.synchronize(dev)
+            graphs[0] = gl
+            for i in range(NSETS):
+                step(i)
+            barrier()
+        except Exception as ex:          # capture not possible: keep the eager launches
+            sys.stderr.write(f"bench.py: CUDA-graph capture failed ({ex!r}); eager launches\n")
+            graphs[0] = None
+            torch.cuda.synchronize(dev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -515,7 +546,9 @@ def run_cuda(args):
                        "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
                        else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "compute_loss_block": block, "e2e": e2e, "e2e_ragged_upload": e2e_ragged, "e2e_dense_path": e2e_dense,
-            "gpu_launches": launches_per_step * K, "host_enqueue_us_per_step": host_enqueue_us, "clocks": clocks,
+            "gpu_launches": launches_per_step * K, "host_enqueue_us_per_step": host_enqueue_us,
+            "launch": "CUDA graph replay of the fused call + eager NCCL all-gather" if graphs[0] is not None else "eager",
+            "clocks": clocks,
         }
     if dist:
         dist.barrier()
@@ -530,6 +563,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
