@@ -30,7 +30,7 @@ Opt g_opts[] = {
     {"lp_debug_ptr_hi", {0}},
     {"lp_debug_skip", {0}},          // diagnostics only: phases of the tcgen05 log-prior kernel to skip (results invalid)
     {"lp_impl", {0}},                // default log-prior implementation for MAS_B200_LP_AUTO
-    {"upload_impl", {0}},            // 0/1 SM zero-copy pull kernel, 2 copy engine (one 2-D copy per utterance and tensor)
+    {"upload_impl", {0}},            // 0/1 SM zero-copy pull kernel, 2 copy engine (one 2-D copy per utterance and tensor), 3 TMA bulk copies for y
     {"upload_l2_256b", {0}},         // 1: zero-copy loads carry the L2::256B fetch hint
     {"upload_ctas", {0}},            // CTAs of the zero-copy upload kernel (0 = one per SM)
     {"fused_impl", {0}},             // 0 auto, 1 force unfused pipeline, 2 force fused kernel

@@ -142,6 +142,17 @@ __device__ __forceinline__ void tma_bulk_load_1d(void *dst_smem, const void *src
                  : "memory");
 }
 
+// 1-D bulk copy shared -> global (bulk async-group completion): dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_bulk_store_1d(void *dst, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+// at most N committed bulk groups may still be reading shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // progress flags in shared memory (one writer warp, one reader warp)
 // ---------------------------------------------------------------------------

@@ -32,10 +32,11 @@ __device__ __forceinline__ float4 ld_host16(const float4 *p, int hint) {
 
 template <int VEC>
 __device__ __forceinline__ void pull_rows(const float *__restrict__ src, float *__restrict__ dst, int f0, int F, int T,
-                                          int valid, int hint) {
+                                          int valid, int hint, int from = 0) {
+    // elements [0, from) (from % 4 == 0) are someone else's job (the bulk-copy kernel below)
     if (VEC == 4) {
         const int nvec = T >> 2;
-        for (int i = threadIdx.x; i < nvec; i += kThreads) {
+        for (int i = (from >> 2) + threadIdx.x; i < nvec; i += kThreads) {
             const int c = i << 2;
             float4 v[kRows];
 #pragma unroll
@@ -54,7 +55,7 @@ __device__ __forceinline__ void pull_rows(const float *__restrict__ src, float *
             }
         }
     } else {
-        for (int c = threadIdx.x; c < T; c += kThreads) {
+        for (int c = from + threadIdx.x; c < T; c += kThreads) {
             float v[kRows];
 #pragma unroll
             for (int k = 0; k < kRows; ++k) v[k] = (f0 + k < F && c < valid) ? __ldcs(src + (size_t)(f0 + k) * T + c) : 0.f;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kThreads) upload_batch_kernel(const float *__r
                                                                 const int *__restrict__ tx_h, const int *__restrict__ ty_h,
                                                                 int B, int F, int Tx, int Ty, float *__restrict__ mu_d,
                                                                 float *__restrict__ y_d, int *__restrict__ tx_d,
-                                                                int *__restrict__ ty_d, int hint) {
+                                                                int *__restrict__ ty_d, int hint, int y_bulk) {
     // Persistent, one small CTA per SM: it only has to keep PCIe busy (a few hundred KB in flight), and it must
     // leave the thread slots of every SM to the alignment kernels of the previous step running beside it.
     const int groups = (F + kRows - 1) / kRows;
@@ -78,10 +79,65 @@ __global__ void __launch_bounds__(kThreads) upload_batch_kernel(const float *__r
         const int b = item / groups, f0 = (item - b * groups) * kRows;
         const int tx = tx_h[b], ty = ty_h[b];      // 8 bytes over PCIe per item
         if (f0 == 0 && threadIdx.x == 0) { tx_d[b] = tx; ty_d[b] = ty; }
-        pull_rows<VECY>(y_h + (size_t)b * F * Ty, y_d + (size_t)b * F * Ty, f0, F, Ty, min(max(ty, 0), Ty), hint);
+        // y_bulk: the leading 16-byte multiples of every y row travel by bulk copies (upload_bulk_kernel)
+        pull_rows<VECY>(y_h + (size_t)b * F * Ty, y_d + (size_t)b * F * Ty, f0, F, Ty, min(max(ty, 0), Ty), hint,
+                        y_bulk ? (min(max(ty, 0), Ty) & ~3) : 0);
         if (mu_h != nullptr)
             pull_rows<VECX>(mu_h + (size_t)b * F * Tx, mu_d + (size_t)b * F * Tx, f0, F, Tx, min(max(tx, 0), Tx), hint);
     }
+}
+
+// y rows through the TMA engine: global(host) -> shared -> global(device) bulk copies, one warp per CTA, a ring of
+// kBulkStages row buffers with kBulkAhead loads in flight.  Only whole 16-byte multiples of the valid part of a row
+// ([0, t_y & ~3)); the tail and the zero padding are the pull kernel's job.
+constexpr int kBulkStages = 8, kBulkAhead = 6, kBulkChunk = 4096, kBulkMaxB = 1024;
+__global__ void __launch_bounds__(32) upload_bulk_kernel(const float *__restrict__ y_h, const int *__restrict__ ty_h, int B, int F,
+                                                         int Ty, float *__restrict__ y_d) {
+    __shared__ __align__(128) unsigned char ring[kBulkStages][kBulkChunk];
+    __shared__ uint64_t full[kBulkStages];
+    __shared__ int ty_s[kBulkMaxB];
+    for (int i = threadIdx.x; i < B; i += 32) ty_s[i] = ty_h[i];      // the lengths cross PCIe once per CTA
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < kBulkStages; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+    // work items of this CTA: (row, chunk) pairs in order; rows c, c + G, ...
+    const int rows = B * F;
+    int lrow = blockIdx.x, loff = 0;          // next item to LOAD
+    int srow = blockIdx.x, soff = 0;          // next item to STORE
+    int kl = 0, ks = 0;
+    auto row_bytes = [&](int row) { return (min(max(ty_s[row / F], 0), Ty) & ~3) * 4; };
+    auto issue_load = [&]() -> bool {
+        while (lrow < rows) {
+            const int nb = row_bytes(lrow);
+            if (loff < nb) {
+                const int n = min(kBulkChunk, nb - loff);
+                const int st = kl % kBulkStages;
+                mbar_arrive_expect_tx(&full[st], (uint32_t)n);
+                tma_bulk_load_1d(ring[st], reinterpret_cast<const unsigned char *>(y_h + (size_t)lrow * Ty) + loff, (uint32_t)n, &full[st]);
+                loff += n; ++kl;
+                return true;
+            }
+            lrow += gridDim.x; loff = 0;
+        }
+        return false;
+    };
+    for (int i = 0; i < kBulkAhead; ++i) issue_load();
+    while (ks < kl) {
+        // item ks: find its (row, off, n) by replaying the same walk
+        int nb = row_bytes(srow);
+        while (soff >= nb) { srow += gridDim.x; soff = 0; nb = row_bytes(srow); }
+        const int n = min(kBulkChunk, nb - soff);
+        const int st = ks % kBulkStages;
+        mbar_wait(&full[st], (uint32_t)(ks / kBulkStages) & 1u);
+        tma_bulk_store_1d(reinterpret_cast<unsigned char *>(y_d + (size_t)srow * Ty) + soff, ring[st], (uint32_t)n);
+        tma_store_commit();
+        soff += n; ++ks;
+        // the stage the next load goes to was stored kBulkStages - kBulkAhead items ago
+        tma_store_wait_read_n<kBulkStages - kBulkAhead - 1>();
+        issue_load();
+    }
+    tma_store_wait_all();
 }
 
 // zero-fill of the padding only: elements [valid, T) of every row (copy-engine variant; lengths from the mapped host arrays)
@@ -165,14 +221,19 @@ int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const i
     }();
     (void)carveout_set;
     const int hint = option("upload_l2_256b");
+    const int y_bulk = (option("upload_impl") == 3 && vy && B <= kBulkMaxB) ? 1 : 0;
+    if (y_bulk) {
+        upload_bulk_kernel<<<di.sm_count, 32, 0, stream>>>(yy, typ, B, F, Ty, y_dev);
+        MASB200_CUDA_TRY(cudaGetLastError());
+    }
     if (vx && vy)
-        upload_batch_kernel<4, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
+        upload_batch_kernel<4, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint, y_bulk);
     else if (vy)
-        upload_batch_kernel<1, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
+        upload_batch_kernel<1, 4><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint, y_bulk);
     else if (vx)
-        upload_batch_kernel<4, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
+        upload_batch_kernel<4, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint, y_bulk);
     else
-        upload_batch_kernel<1, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint);
+        upload_batch_kernel<1, 1><<<grid, kThreads, 0, stream>>>(mu, yy, txp, typ, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, hint, y_bulk);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

@@ -124,12 +124,16 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev,
                        float *log_prior_dev, int impl, void *stream);
 
 /*
- * Fused log-prior + MAS: mu_x, y -> path / durations without the [B,Tx,Ty]
- * value matrix ever being written to HBM when the fused kernel covers the
- * shape (otherwise the library runs mas_b200_log_prior into the workspace and
- * mas_b200_maximum_path, still entirely on the device).
+ * Fused log-prior + MAS: mu_x, y -> path / durations / frame_token in one call, entirely on the device.
  * Replaces: model/face_tts.py:165-174 (log-prior block + maximum_path call).
- * workspace: >= mas_b200_fused_workspace_bytes(B,F,Tx,Ty).
+ * For batches that leave SMs free (B + log-prior CTAs <= SM count; the LRS2 training batch does) the tcgen05
+ * log-prior kernel and the MAS kernel run CONCURRENTLY on two streams forked from / joined into `stream`: the
+ * [B,Tx,Ty] value matrix is handed over through L2 in 64-frame groups guarded by device-scope release/acquire
+ * flags in the workspace, the search starts a few microseconds after the log-prior, and the dense path (if
+ * requested) is written by the log-prior CTAs as each utterance's backtrack completes.  Larger batches (or
+ * shapes the tensor-core kernel does not take, or a profiler that serialises kernels) run
+ * mas_b200_log_prior into the workspace and then mas_b200_maximum_path.  Same results either way.
+ * workspace: >= mas_b200_fused_workspace_bytes(B,F,Tx,Ty), 256-byte aligned.
  */
 size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty);
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,

@@ -29,10 +29,13 @@ t0 = time.perf_counter()
 for i in range(200): fgt.upload_batch(*host[i % 3], out=out)
 t1 = time.perf_counter(); torch.cuda.synchronize()
 print(f"  host enqueue {1e6*(t1-t0)/200:.1f} us/call")
+_lib.set_option("upload_impl", 3)
+s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out, mu_on_copy_engine=False))
+print(f"ragged upload, y by TMA bulk copies (+ pull kernel for mu_x, tails, padding, serial): {s*1e6:7.1f} us  {sum(valid)/3/s/1e9:6.1f} GB/s")
 _lib.set_option("upload_impl", 1)
-for hint in (1, 0):
+for hint in (0,):
   _lib.set_option("upload_l2_256b", hint); print("L2::256B hint", hint)
-  for ctas in (74, 148, 592):
+  for ctas in (148,):
     _lib.set_option("upload_ctas", ctas)
     s = ev_time(lambda i: fgt.upload_batch(*host[i % 3], out=out, mu_on_copy_engine=False))
     print(f"  ragged upload ctas={ctas:5d}: {s*1e6:7.1f} us  {sum(valid)/3/s/1e9:6.1f} GB/s over PCIe ({sum(valid)/3/1e6:.2f} MB valid)")

@@ -62,6 +62,18 @@ def test_host_argument_validation_happens_before_any_cuda_call():
     assert L.mas_b200_log_prior(None, None, 1, 80, 1, 1, None, 0, None) == _lib.ERR_ARG
     assert L.mas_b200_generate_path(None, None, None, 1, 1, 1, None, 1, None) == _lib.ERR_ARG
     assert L.mas_b200_maximum_path_host(None, None, None, None, 1, 1, 1, -1e9) == _lib.ERR_ARG
+    # the consumers of the alignment (loss_ops.cu) and the upload
+    assert L.mas_b200_sequence_mask(None, 1, 1, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_crop_frames(None, None, None, None, 1, 1, 1, 1, None, None, None, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_gather_mu_y(None, None, 1, 1, 1, 1, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_gather_mu_y_backward(None, None, None, None, None, 1, 1, 1, 1, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_prior_loss(None, None, None, None, 1, 1, 1, 1, None, None, None, 0, None) == _lib.ERR_ARG
+    assert L.mas_b200_prior_loss_backward(None, None, None, None, None, None, None, 1, 1, 1, 1, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_duration_loss(None, None, None, 1, 1, None, None, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_generate_path_f32(None, None, None, 1, 1, 1, None, 1, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_upload_batch(None, None, None, None, 1, 1, 1, 1, None, None, None, None, None) == _lib.ERR_ARG
+    assert L.mas_b200_prior_loss_workspace_bytes(32, 80, 1000) == 8 * 32 * 10 * 4
+    assert L.mas_b200_prior_loss_workspace_bytes(0, 80, 1000) == 0
 
 
 def test_no_cpu_fallback():

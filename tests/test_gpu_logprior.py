@@ -137,7 +137,8 @@ def test_tcgen05_kernel_is_the_one_running_and_matches_ffma():
     for (B, F, Tx, Ty) in [(3, 80, 190, 1000), (2, 64, 129, 136), (2, 96, 256, 420), (5, 80, 37, 68),
                            (3, 128, 190, 1000), (2, 128, 256, 420), (4, 128, 61, 200), (2, 128, 128, 132), (1, 128, 129, 132),
                            # texts longer than two M-tiles: split-M for every n_feats (cfg4: Tx = 512)
-                           (2, 80, 512, 640), (1, 96, 300, 304), (2, 64, 257, 260), (1, 128, 513, 516), (1, 80, 1000, 1000)]:
+                           (2, 80, 512, 640), (1, 96, 300, 304), (2, 64, 257, 260), (1, 128, 513, 516), (1, 80, 1000, 1000),
+                           (2, 80, 1, 4), (1, 64, 5, 8), (3, 96, 128, 192)]:
         mu_x, y, _, _ = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=7, tx_lo=max(1, Tx // 3), ty_lo=max(Tx // 3, Ty // 3))
         mu_d, y_d = mu_x.to(DEV), y.to(DEV)
         tc = fgt.log_prior(mu_d, y_d, impl="tcgen05")
@@ -240,7 +241,7 @@ def test_overlapped_pipeline_rejects_bad_items_without_hanging():
 # ---------------------------------------------------------------------------------------------
 # ragged zero-copy upload (mas_b200_upload_batch): the e2e path's host -> device transfer
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(params=[1, 2], ids=["sm_zero_copy_pull", "copy_engine_2d"])
+@pytest.fixture(params=[1, 2, 3], ids=["sm_zero_copy_pull", "copy_engine_2d", "tma_bulk"])
 def upload_impl(request):
     prev = fgt._lib.set_option("upload_impl", request.param)
     yield request.param
