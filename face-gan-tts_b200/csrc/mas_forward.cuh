@@ -815,27 +815,106 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     // ================================= outputs =================================
     // [start, duration] per token from the start frames; frame -> token index; dense path
     int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
-    for (int x = tid; x < P.Tx; x += nthreads) {
-        int s = 0, d = 0;
-        if (x < t_x) {
-            s = tok[x];
-            d = ((x + 1 < t_x) ? tok[x + 1] : t_y) - s;
+    // scratch of the scan below, in the (idle) ring behind tok / xin: heads [Ty], warp totals [32]
+    int *hd = xin + ((ntiles + 3) & ~3);
+    const bool scan_ft = SMEM_BITS && ((size_t)(XP + ((ntiles + 3) & ~3) + ((P.Ty + 3) & ~3) + 32) * sizeof(int) <= S::ring_bytes(NS));
+    if (scan_ft) {
+        // The [start,dur] table first: it is all the dense-path writers (this kernel or the one watching `done`)
+        // need, so `done` is released before the frame->token index is produced.
+        for (int x = tid; x < P.Tx; x += nthreads) {
+            int s = 0, d = 0;
+            if (x < t_x) {
+                s = tok[x];
+                d = ((x + 1 < t_x) ? tok[x + 1] : t_y) - s;
+            }
+            start_b[x] = s;
+            dur_b[x] = d;
         }
-        if (SMEM_BITS) start_b[x] = s;
-        dur_b[x] = d;
+        if (P.done != nullptr) {                 // the dense path of this item is written by the kernel watching `done`
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) gflag_release(P.done + b, 1);
+        }
+        if (ft) {
+            // frame -> token: tokens are non-decreasing along the frames, so it is a running MAX over "head" marks
+            // (hd[start frame of x] = x).  One thread per 8 frames, warp shuffle scan, 16-byte stores -- instead of
+            // one thread per token walking its frames (a 200-frame silence token was the whole tail).
+            int *wt = hd + ((P.Ty + 3) & ~3);
+            for (int t = tid; t < t_y; t += nthreads) hd[t] = -1;
+            __syncthreads();
+            for (int x = tid; x < t_x; x += nthreads) {
+                const int s = tok[x];
+                const int e = (x + 1 < t_x) ? tok[x + 1] : t_y;
+                if (e > s) hd[s] = x;
+            }
+            __syncthreads();
+            const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
+            const int nw = nthreads >> 5;
+            int carry = -1;
+            for (int base_t = 0; base_t < P.Ty; base_t += nthreads * 8) {
+                const int t0 = base_t + tid * 8;
+                int v[8], run = -1;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int t = t0 + k;
+                    const int h = (t < t_y) ? hd[t] : -1;
+                    run = max(run, h);
+                    v[k] = run;
+                }
+                int inc = run;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const int n = __shfl_up_sync(kFullMask, inc, dlt);
+                    if (lane >= dlt) inc = max(inc, n);
+                }
+                int exc = __shfl_up_sync(kFullMask, inc, 1);
+                if (lane == 0) exc = -1;
+                if (lane == 31) wt[warp] = inc;
+                __syncthreads();
+                int basev = max(carry, exc), nc = carry;
+                for (int w2 = 0; w2 < nw; ++w2) {
+                    const int wv = wt[w2];
+                    if (w2 < warp) basev = max(basev, wv);
+                    nc = max(nc, wv);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = (t0 + k < t_y) ? max(basev, v[k]) : -1;
+                if (vec && t0 + 7 < P.Ty) {
+                    *reinterpret_cast<int4 *>(ft + t0) = make_int4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<int4 *>(ft + t0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (t0 + k < P.Ty) ft[t0 + k] = v[k];
+                }
+                __syncthreads();                 // wt is reused by the next round
+                carry = nc;
+            }
+        }
+        if (P.done == nullptr) __syncthreads();  // start_b / dur_b of every thread are in place for the path writer
+    } else {
+        for (int x = tid; x < P.Tx; x += nthreads) {
+            int s = 0, d = 0;
+            if (x < t_x) {
+                s = tok[x];
+                d = ((x + 1 < t_x) ? tok[x + 1] : t_y) - s;
+            }
+            if (SMEM_BITS) start_b[x] = s;
+            dur_b[x] = d;
+            if (ft)
+                for (int y = s; y < s + d; ++y) ft[y] = x;
+        }
         if (ft)
-            for (int y = s; y < s + d; ++y) ft[y] = x;
-    }
-    if (ft)
-        for (int y = t_y + tid; y < P.Ty; y += nthreads) ft[y] = -1;
-    __syncthreads();
-    if (!SMEM_BITS)                                                        // tok aliases start_b: zero the padding rows
-        for (int x = t_x + tid; x < P.Tx; x += nthreads) start_b[x] = 0;
-    __syncthreads();
-    if (P.done != nullptr) {                     // the dense path of this item is written by the kernel watching `done`
-        __threadfence();
+            for (int y = t_y + tid; y < P.Ty; y += nthreads) ft[y] = -1;
         __syncthreads();
-        if (tid == 0) gflag_release(P.done + b, 1);
+        if (!SMEM_BITS)                                                    // tok aliases start_b: zero the padding rows
+            for (int x = t_x + tid; x < P.Tx; x += nthreads) start_b[x] = 0;
+        __syncthreads();
+        if (P.done != nullptr) {                 // the dense path of this item is written by the kernel watching `done`
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) gflag_release(P.done + b, 1);
+        }
     }
     write_path_any(P, b, start_b, dur_b, tid, nthreads);
     if (dbg && tid == 0) {
