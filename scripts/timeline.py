@@ -46,7 +46,7 @@ print("MAS gate spins       :", dm[:8, 10].tolist())
 i = int(torch.argmax(dm[:, 13]))
 s_ = dm[i].tolist()
 print(f"slowest MAS CTA b={i} t_x={s_[7] >> 32} t_y={s_[7] & 0xffffffff}: dp_done {s_[2]-s_[0]} all_warps {s_[4]-s_[0]} backtrack {s_[5]-s_[4]} tail {s_[6]-s_[5]} total {s_[6]-s_[0]} cycles; spins {s_[10]}")
-print(f"  helper done {s_[14]-s_[0]}  producer done {s_[15]-s_[0]}; gate wait cycles total {s_[9]} (first group {s_[8]})")
+print(f"  helper done {s_[14]-s_[0]}  producer done {s_[15]-s_[0]}; gate wait cycles total {s_[9]} (first group {s_[8]}); producer built upper transfer tables of {s_[11]} tiles in its slack")
 # same batch through the serial pipeline (MAS ungated)
 _lib.set_option("fused_impl", 1)
 for _ in range(3): call()
