@@ -70,8 +70,11 @@ static bool kernels_may_overlap() {
         const char *e = std::getenv("MAS_B200_PIPELINE");
         if (e && std::strcmp(e, "serial") == 0) return false;
         if (e && std::strcmp(e, "overlap") == 0) return true;
-        return std::getenv("CUDA_INJECTION64_PATH") == nullptr && std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr &&
-               std::getenv("NV_SANITIZER_INJECTION_PORT_BASE") == nullptr;
+        // what ncu 2025.x sets in the profiled process (scripts/ncu_env_probe.py), plus the CUDA injection hooks
+        for (const char *k : {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NVIDIA_PROCESS_INJECTION_XML_TARGET_SETTINGS",
+                              "NV_CUDA_START_SUSPENDED", "CUDA_INJECTION64_PATH", "NV_SANITIZER_INJECTION_PORT_BASE"})
+            if (std::getenv(k) != nullptr) return false;
+        return true;
     }();
     return v;
 }
