@@ -8,6 +8,7 @@ package is the thin PyTorch-facing host layer.  No CPU fallback.
 """
 from . import losses, monotonic_align, sharding  # noqa: F401
 from .alignment import (  # noqa: F401
+    AlignmentPlan,
     AlignmentResult,
     align,
     durations_to_logw,
@@ -29,7 +30,7 @@ from .losses import (  # noqa: F401
 )
 
 __all__ = [
-    "monotonic_align", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
+    "monotonic_align", "AlignmentPlan", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
     "durations_to_logw", "expand_durations", "upload_batch", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
     "duration_loss", "gather_mu_y", "prior_loss", "sequence_mask",
 ]

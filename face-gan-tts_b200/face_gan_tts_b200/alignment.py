@@ -177,6 +177,50 @@ def log_prior_maximum_path(mu_x: torch.Tensor, y: torch.Tensor, x_lengths, y_len
     return AlignmentResult(path, dur, ft, status)
 
 
+class AlignmentPlan:
+    """Reusable buffers for repeated fused calls of one shape (a training loop): outputs and workspace are
+    allocated once, so a call is argument checks + ONE C-ABI call (~20 us of host time instead of ~45 us for
+    `log_prior_maximum_path`, which allocates its outputs every time).  The returned AlignmentResult aliases the
+    plan's buffers: it is overwritten by the next call on the plan (stream-ordered)."""
+
+    def __init__(self, B: int, F: int, Tx: int, Ty: int, *, device=None, dense_path: bool = True,
+                 path_dtype=torch.float32, impl: str = "auto", max_neg_val: float = _lib.MAX_NEG_VAL):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.shape = (int(B), int(F), int(Tx), int(Ty))
+        self.device, self.impl, self.neg = dev, _IMPL[impl], float(max_neg_val)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            self.path = torch.empty((B, Tx, Ty), dtype=path_dtype, device=dev) if dense_path else None
+            self.path_code = _path_dtype_code(path_dtype) if dense_path else _lib.PATH_NONE
+            self.durations = torch.empty((B, Tx), dtype=torch.int32, device=dev)
+            self.frame_token = torch.empty((B, Ty), dtype=torch.int32, device=dev)
+            self.status = torch.empty((B,), dtype=torch.int32, device=dev)
+            self.ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, Tx, Ty)
+            self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+        self._fn = L.mas_b200_log_prior_maximum_path
+        self._result = AlignmentResult(self.path, self.durations, self.frame_token, self.status)
+
+    def __call__(self, mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor,
+                 check: bool = False) -> AlignmentResult:
+        """mu_x [B,F,Tx], y [B,F,Ty] float32 contiguous CUDA; x_lengths / y_lengths int32 [B] CUDA (no conversions
+        are done here -- that is the point)."""
+        B, F, Tx, Ty = self.shape
+        if mu_x.shape != (B, F, Tx) or y.shape != (B, F, Ty) or mu_x.dtype != torch.float32 or y.dtype != torch.float32 \
+                or not mu_x.is_contiguous() or not y.is_contiguous() or mu_x.device != self.device:
+            raise ValueError("AlignmentPlan: mu_x / y must be contiguous float32 CUDA tensors of the planned shape")
+        if x_lengths.dtype != torch.int32 or y_lengths.dtype != torch.int32 or x_lengths.device != self.device \
+                or y_lengths.device != self.device or x_lengths.shape != (B,) or y_lengths.shape != (B,):
+            raise ValueError("AlignmentPlan: lengths must be int32 [B] tensors on the plan's device")
+        rc = self._fn(mu_x.data_ptr(), y.data_ptr(), x_lengths.data_ptr(), y_lengths.data_ptr(), B, F, Tx, Ty, self.neg,
+                      self.path.data_ptr() if self.path is not None else None, self.path_code,
+                      self.durations.data_ptr(), self.frame_token.data_ptr(), self.status.data_ptr(),
+                      self.ws.data_ptr(), self.ws_bytes, self.impl, torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "mas_b200_log_prior_maximum_path")
+        if check:
+            _raise_on_bad(self.status, "AlignmentPlan")
+        return self._result
+
+
 def generate_path(duration: torch.Tensor, mask: torch.Tensor, *, return_index: bool = False):
     """Drop-in for reference model/utils.py:27-40 generate_path(duration, mask):
     duration [B,Tx] (float as at the call site face_tts.py:126, or integer), mask [B,Tx,Ty] prefix mask

@@ -83,6 +83,23 @@ def test_fused_call_bit_exact_on_its_own_value_and_agrees_with_reference_pipelin
     assert agree > 0.999
 
 
+def test_alignment_plan_equals_functional_api_and_reuses_buffers():
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=6, F=80, Tx=190, Ty=1000, seed=17)
+    mu2, y2, t_x2, t_y2 = synthetic.lrs2_batch(B=6, F=80, Tx=190, Ty=1000, seed=18)
+    plan = fgt.AlignmentPlan(6, 80, 190, 1000, device=DEV)
+    for (m, yy, a, b) in ((mu_x, y, t_x, t_y), (mu2, y2, t_x2, t_y2), (mu_x, y, t_x, t_y)):
+        md, yd, ad, bd = m.to(DEV), yy.to(DEV), a.to(DEV), b.to(DEV)
+        want = fgt.log_prior_maximum_path(md, yd, ad, bd)
+        got = plan(md, yd, ad, bd, check=True)
+        assert got.path.data_ptr() == plan.path.data_ptr()
+        assert torch.equal(got.path, want.path) and torch.equal(got.durations, want.durations)
+        assert torch.equal(got.frame_token, want.frame_token)
+    with pytest.raises(ValueError):
+        plan(mu_x.to(DEV)[:, :, :100], y.to(DEV), t_x.to(DEV), t_y.to(DEV))
+    with pytest.raises(ValueError):
+        plan(mu_x.to(DEV), y.to(DEV), t_x.long().to(DEV), t_y.to(DEV))
+
+
 def test_fused_call_without_dense_path():
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=4, F=80, Tx=190, Ty=1000, seed=99)
     a = fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, dense_path=False)
