@@ -278,6 +278,9 @@ def run_cuda(args):
         sets.append(d)
     ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, TX, TY)
     wss = [torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) for _ in range(NSETS)]
+    for w_ in wss:      # persistent workspaces, cleared once: the fused calls then skip their per-call flag memset
+        _lib.check(L.mas_b200_fused_workspace_prepare(w_.data_ptr(), ws_bytes, B, F, TX, TY, None), "workspace_prepare")
+    torch.cuda.synchronize(dev)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
@@ -286,7 +289,7 @@ def run_cuda(args):
             d["mu"].data_ptr(), d["y"].data_ptr(), d["tx"].data_ptr(), d["ty"].data_ptr(), B, F, TX, TY, -1e9,
             d["path"].data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
             d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes,
-            _lib.LP_AUTO, sp if on is None else on.cuda_stream)
+            _lib.LP_AUTO | _lib.WS_PREPARED, sp if on is None else on.cuda_stream)
         _lib.check(rc, "mas_b200_log_prior_maximum_path")
 
     graphs = [None]      # multi-GPU: CUDA graphs of the fused call, one per buffer set (see below)

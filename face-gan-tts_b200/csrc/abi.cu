@@ -168,11 +168,34 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev, int B, int F, 
     return launch_log_prior_ffma(mu_x_dev, y_dev, B, F, Tx, Ty, log_prior_dev, s);
 }
 
+// flag area of the fused workspace: [B][groups][slots] group flags + [B] done flags (slots = log-prior M-tile CTAs)
+static size_t fused_flag_ints(int B, int Tx, int Ty) {
+    return (size_t)B * ((Ty + 63) / 64) * (size_t)((Tx + 127) / 128) + (size_t)B;
+}
+
 size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty) {
     if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return 0;
     // MAS workspace + the [B,Tx,Ty] value matrix (L2-resident hand-off) + per-group ready flags
     return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256) +
-           align_up(sizeof(int) * (size_t)B * ((Ty + 63) / 64 + 1), 256);
+           align_up(sizeof(int) * fused_flag_ints(B, Tx, Ty), 256);
+}
+
+int mas_b200_fused_workspace_prepare(void *workspace_dev, size_t workspace_bytes, int B, int F, int Tx, int Ty, void *stream) {
+    if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    if (!workspace_dev || workspace_bytes < mas_b200_fused_workspace_bytes(B, F, Tx, Ty)) return MAS_B200_ERR_WORKSPACE;
+    char *flags = static_cast<char *>(workspace_dev) + align_up(workspace_layout(B, Tx, Ty).total, 256) +
+                  align_up(sizeof(float) * (size_t)B * Tx * Ty, 256);
+    MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * fused_flag_ints(B, Tx, Ty), static_cast<cudaStream_t>(stream)));
+    return MAS_B200_OK;
+}
+
+// One nonce per overlapped call, process-wide and never 0: group / done flags hold the nonce of the call that set
+// them, so entries left by earlier calls (all older nonces) or the zeros of a prepared workspace never look "set".
+static int next_nonce() {
+    static std::atomic<unsigned> counter{0};
+    unsigned v;
+    do { v = counter.fetch_add(1, std::memory_order_relaxed) + 1; } while ((v & 0x7fffffffu) == 0);
+    return (int)(v & 0x7fffffffu);
 }
 
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, const int *t_x_dev,
@@ -183,6 +206,8 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
     if (!mu_x_dev || !y_dev || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!workspace_dev || workspace_bytes < mas_b200_fused_workspace_bytes(B, F, Tx, Ty)) return MAS_B200_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) return MAS_B200_ERR_ALIGN;
+    const bool ws_prepared = (impl & MAS_B200_WS_PREPARED) != 0;      // flag area known clean: no memset in this call
+    impl &= ~MAS_B200_WS_PREPARED;
     const size_t mas_ws = align_up(workspace_layout(B, Tx, Ty).total, 256);
     float *value = reinterpret_cast<float *>(static_cast<char *>(workspace_dev) + mas_ws);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -202,30 +227,39 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
         if (aux != nullptr) {
             const int ngroups = (Ty + 63) / 64;
             int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(value) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256));
-            int *done = flags + (size_t)B * ngroups;            // [B] "table final" flags, same memset
+            const int slots = log_prior_tc_flag_target(F, Tx);
+            int *done = flags + (size_t)B * ngroups * slots;    // [B] "table final" flags
+            const int nonce = next_nonce();
             const bool want_path = path_dtype != MAS_B200_PATH_NONE && path_dev != nullptr;
             PathJob job{};
             if (want_path) {
                 job.start = mas_start_table(workspace_dev, B, Tx, Ty);
                 job.dur = mas_dur_table(workspace_dev, B, Tx, Ty, durations_dev);
-                job.done = done; job.path = path_dev; job.path_dtype = path_dtype;
+                job.done = done; job.done_value = nonce; job.path = path_dev; job.path_dtype = path_dtype;
             }
             if (fi == 3) {
                 // diagnostics only: log-prior first (serial), then the GATED MAS kernel with every flag already set --
                 // isolates the cost of the gating code path from the cost of waiting for the producer
                 rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, s);
                 if (rc != MAS_B200_OK) return rc;
-                MASB200_CUDA_TRY(cudaMemsetAsync(flags, 1, sizeof(int) * ((size_t)B * ngroups + B), s));
+                MASB200_CUDA_TRY(cudaMemsetAsync(flags, 1, sizeof(int) * ((size_t)B * ngroups * slots + B), s));
                 MasLaunch G{};
                 G.value = value; G.stride_b = (long long)Tx * Ty; G.stride_x = Ty;
                 G.t_x = t_x_dev; G.t_y = t_y_dev; G.B = B; G.Tx = Tx; G.Ty = Ty; G.neg = max_neg_val;
                 G.path = path_dev; G.path_dtype = path_dtype;
                 G.durations = durations_dev; G.frame_token = frame_token_dev; G.status = status_dev;
                 G.workspace = workspace_dev; G.workspace_bytes = mas_ws; G.stream = s;
-                G.gate = flags; G.gate_pitch = ngroups; G.gate_need = 1;
+                G.gate = flags; G.gate_pitch = ngroups; G.gate_slots = slots; G.flag_value = 0x01010101;
                 return launch_mas(G);
             }
-            MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)B * ngroups + B), s));
+            // A workspace the caller prepared once (mas_b200_fused_workspace_prepare) and has only used for fused
+            // calls since needs no clearing: stale flags hold older nonces.  Otherwise clear it now.
+            // (A CUDA-graph capture bakes this call's nonce into the kernel nodes, and every replay would then find
+            // its own previous flags "set": under capture the clearing always stays in, as a node of the graph.)
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+            if (!ws_prepared || cap != cudaStreamCaptureStatusNone)
+                MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)B * ngroups * slots + B), s));
             MASB200_CUDA_TRY(cudaEventRecord(aux->fork, s));
             MASB200_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
             // validate the consumer's plan before anything is launched (each kernel waits for the other's flags)
@@ -235,7 +269,7 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
             L.path = path_dev; L.path_dtype = path_dtype;
             L.durations = durations_dev; L.frame_token = frame_token_dev; L.status = status_dev;
             L.workspace = workspace_dev; L.workspace_bytes = mas_ws; L.stream = s;
-            L.gate = flags; L.gate_pitch = ngroups; L.gate_need = log_prior_tc_flag_target(F, Tx);
+            L.gate = flags; L.gate_pitch = ngroups; L.gate_slots = slots; L.flag_value = nonce;
             L.done = want_path ? done : nullptr;
             L.dry_run = 1;
             rc = launch_mas(L);
@@ -245,7 +279,7 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
             // The log-prior kernel is on the critical path (the search cannot start before its first group), so it
             // stays on the caller's stream right behind the memset; the MAS kernel takes the cross-stream hop.
             rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, s, flags, ngroups, di.sm_count - B,
-                                     want_path ? &job : nullptr);
+                                     want_path ? &job : nullptr, nonce);
             L.stream = aux->stream;
             if (rc == MAS_B200_OK) rc = launch_mas(L);
             MASB200_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));

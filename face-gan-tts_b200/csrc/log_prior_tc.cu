@@ -30,9 +30,11 @@ struct LpTcParams {
     int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
     PathJob job;         // optional: expand the dense path of utterance b once the MAS kernel reports it done
     long long *dbg;      // diagnostics: [ctas][32] globaltimer stamps / wait-cycle accumulators
-    int *flags;          // optional [B][flag_pitch]: counts the M-tile CTAs that have a 64-frame group of an utterance
+    int *flags;          // optional [B][flag_pitch][flag_slots]: entry (b, group, M-tile slot) = flag_value once that
+                         //   CTA's part of the 64-frame group is in memory
+    int flag_slots, flag_value;
     int skip;            // diagnostics (option lp_debug_skip): 1 no global stores, 2 no MMA issue, 4 no split math, 8 no staging
-    int flag_pitch;      //   in memory (1 when a CTA holds both M-tiles; split-M: ready at ceil(Tx/128))
+    int flag_pitch;
 };
 
 // SPLITM: one CTA per (utterance, group run, M-tile) -- blockIdx.z is the M-tile; see lp_tc_frontend.cuh.
@@ -113,8 +115,7 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                     // async-proxy / generic-proxy fence -> device-scope release
                     tma_store_wait_all();
                     asm volatile("fence.proxy.async;" ::: "memory");
-                    if (SPLITM) gflag_add_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
-                    else gflag_release(P.flags + (size_t)b * P.flag_pitch + gidx, 1);
+                    gflag_release(P.flags + ((size_t)b * P.flag_pitch + gidx) * P.flag_slots + mt0, P.flag_value);
                 }
             }
             __syncwarp();
@@ -188,8 +189,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
             while (remaining > 0) {
                 for (int base = 0; base < P.B; base += 32) {
                     const int u = base + lane;
-                    const int f = (u < P.B) ? gflag_acquire(P.job.done + u) : 0;
-                    uint32_t ready = __ballot_sync(kFullMask, f != 0) & ~proc[base >> 5];
+                    const bool f = (u < P.B) && gflag_acquire(P.job.done + u) == P.job.done_value;
+                    uint32_t ready = __ballot_sync(kFullMask, f) & ~proc[base >> 5];
                     proc[base >> 5] |= ready;
                     while (ready != 0u) {
                         const int ub = base + __ffs((int)ready) - 1;
@@ -275,7 +276,7 @@ int log_prior_tc_min_ctas(int B, int F, int Tx) { return lp_split_m(F, Tx) ? B *
 int log_prior_tc_flag_target(int F, int Tx) { return lp_split_m(F, Tx) ? (Tx + 127) / 128 : 1; }
 
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream, int *flags, int flag_pitch, int max_ctas, const PathJob *job) {
+                        cudaStream_t stream, int *flags, int flag_pitch, int max_ctas, const PathJob *job, int flag_value) {
     if (!mu_x || !y || !out || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!log_prior_tc_supported(mu_x, y, out, B, F, Tx, Ty)) return MAS_B200_ERR_UNSUPPORTED;
     DeviceInfo di;
@@ -294,7 +295,8 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     LpTcParams P{};
     P.mu = mu_x; P.out = out; P.B = B; P.Tx = Tx; P.Ty = Ty; P.cst = log_prior_const(F);
     P.ngroups = (Ty + kLpGroup - 1) / kLpGroup;
-    P.flags = flags; P.flag_pitch = flag_pitch;
+    P.flags = flags; P.flag_pitch = flag_pitch; P.flag_value = flag_value;
+    P.flag_slots = log_prior_tc_flag_target(F, Tx);
     {
         const unsigned lo = (unsigned)option("lp_debug_ptr_lo"), hi = (unsigned)option("lp_debug_ptr_hi");
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);

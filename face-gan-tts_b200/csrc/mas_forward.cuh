@@ -79,7 +79,10 @@ struct MasParams {
     int *done;               // optional [B]: set to 1 (device-scope release) once the [start,dur] table of item b is final
     const int *gate;         // optional [B][gate_pitch]: group g of utterance b may be read once gate != 0
     int gate_pitch;          //   (written by the log-prior kernel running concurrently), 64 frames per group
-    int gate_need;           // value a gate entry reaches when its group is complete (1, or the M-tile CTA count)
+    int gate_slots;          // entries per group (one per log-prior M-tile CTA); a group is ready when ALL hold gate_value
+    int gate_value;          // the call's nonce: stale entries of earlier calls (or the zeros of a fresh workspace) never
+                             //   match it, so the flags need no clearing between calls
+    int done_value;          // value released into done[b] (the same nonce)
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
@@ -496,7 +499,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_BAD_LENGTH;
         __syncthreads();
         write_path_any(P, b, start_b, dur_b, tid, nthreads);
-        if (P.done != nullptr) { __threadfence(); __syncthreads(); if (tid == 0) gflag_release(P.done + b, 1); }
+        if (P.done != nullptr) { __threadfence(); __syncthreads(); if (tid == 0) gflag_release(P.done + b, P.done_value); }
         return;
     }
     if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_OK;
@@ -556,8 +559,10 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                     const long long c0 = clock64();
                     while (true) {
                         const int g = g0 + lane;
-                        const int f = (g < P.gate_pitch) ? gflag_acquire(gf + g) : 0;
-                        const unsigned ready = __ballot_sync(kFullMask, f >= P.gate_need);
+                        bool all = g < P.gate_pitch;
+                        for (int m = 0; m < P.gate_slots; ++m)
+                            all = all && (gflag_acquire(gf + (size_t)min(g, P.gate_pitch - 1) * P.gate_slots + m) == P.gate_value);
+                        const unsigned ready = __ballot_sync(kFullMask, all);
                         if (ready & 1u) { gate_known = g0 + __ffs((int)~ready) - 1; break; }    // consecutive ready groups
                         __nanosleep(64);
                         ++gate_spins;
@@ -833,7 +838,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (P.done != nullptr) {                 // the dense path of this item is written by the kernel watching `done`
             __threadfence();
             __syncthreads();
-            if (tid == 0) gflag_release(P.done + b, 1);
+            if (tid == 0) gflag_release(P.done + b, P.done_value);
         }
         if (ft) {
             // frame -> token: tokens are non-decreasing along the frames, so it is a running MAX over "head" marks
@@ -913,7 +918,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (P.done != nullptr) {                 // the dense path of this item is written by the kernel watching `done`
             __threadfence();
             __syncthreads();
-            if (tid == 0) gflag_release(P.done + b, 1);
+            if (tid == 0) gflag_release(P.done + b, P.done_value);
         }
     }
     write_path_any(P, b, start_b, dur_b, tid, nthreads);

@@ -58,7 +58,8 @@ struct MasLaunch {
     cudaStream_t stream;
     const int *gate;    // optional device flags [B][gate_pitch] (see MasParams::gate); null normally
     int gate_pitch;
-    int gate_need;      // value a gate entry holds when its group is complete (0/1: one writer; split-M log-prior: 2)
+    int gate_slots;     // gate entries per group: one per log-prior M-tile CTA (0/1: one writer)
+    int flag_value;     // the call's nonce: what gate entries and done[] hold when set (see abi.cu)
     int dry_run;        // 1: validate arguments / plan only, launch nothing
     int *done;          // optional device flags [B]: when set, the dense path is NOT written here; the kernel
                         // watching `done` expands it from the [start,dur] table (see PathJob)
@@ -68,6 +69,7 @@ struct MasLaunch {
 struct PathJob {
     const int *start, *dur;   // [B,Tx] tables in the MAS workspace
     const int *done;          // [B]
+    int done_value;           // the call's nonce
     void *path;
     int path_dtype;
 };
@@ -107,7 +109,7 @@ int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int T
 // tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
                         cudaStream_t stream, int *flags = nullptr, int flag_pitch = 0, int max_ctas = 0,
-                        const PathJob *job = nullptr);
+                        const PathJob *job = nullptr, int flag_value = 1);
 int log_prior_tc_min_ctas(int B, int F, int Tx);
 int log_prior_tc_flag_target(int F, int Tx);
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty);

@@ -17,6 +17,7 @@ OK, ERR_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_ALIGN = 0, -1, -2, -3
 ITEM_OK, ITEM_BAD_LENGTH = 0, 1
 PATH_NONE, PATH_F32, PATH_I32 = 0, 1, 2
 LP_AUTO, LP_FFMA, LP_TCGEN05 = 0, 1, 2
+WS_PREPARED = 0x100
 MAX_NEG_VAL = -1e9
 
 c_int, c_float, c_size_t, c_void_p, c_char_p, c_ll = (
@@ -33,6 +34,7 @@ SIGNATURES = {
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mas_b200_log_prior": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mas_b200_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mas_b200_fused_workspace_prepare": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "mas_b200_log_prior_maximum_path": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                 c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_size_t, c_int, c_void_p]),

@@ -197,6 +197,10 @@ class AlignmentPlan:
             self.status = torch.empty((B,), dtype=torch.int32, device=dev)
             self.ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, Tx, Ty)
             self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+            # cleared once; the per-call nonce flags make every later clearing unnecessary (MAS_B200_WS_PREPARED)
+            _lib.check(L.mas_b200_fused_workspace_prepare(self.ws.data_ptr(), self.ws_bytes, B, F, Tx, Ty, _stream_ptr(dev)),
+                       "mas_b200_fused_workspace_prepare")
+            self.impl |= _lib.WS_PREPARED
         self._fn = L.mas_b200_log_prior_maximum_path
         self._result = AlignmentResult(self.path, self.durations, self.frame_token, self.status)
 

@@ -54,7 +54,11 @@ extern "C" {
 /* log-prior implementation selector */
 #define MAS_B200_LP_AUTO   0
 #define MAS_B200_LP_FFMA   1   /* fp32 CUDA-core contraction                     */
-#define MAS_B200_LP_TCGEN05 2  /* tcgen05/TMEM split-bf16 contraction (sm_100a)  */
+#define MAS_B200_LP_TCGEN05 2  /* tcgen05/TMEM 3xTF32 contraction (sm_100a)       */
+/* OR-ed into `impl` of mas_b200_log_prior_maximum_path: the workspace was cleared once with
+ * mas_b200_fused_workspace_prepare and has only been used for fused calls since (a training loop's persistent
+ * workspace), so the call does not clear its flag area again -- one launch less per step. */
+#define MAS_B200_WS_PREPARED 0x100
 
 /* default of core.pyx:40 */
 #define MAS_B200_MAX_NEG_VAL (-1e9f)
@@ -136,6 +140,10 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev,
  * workspace: >= mas_b200_fused_workspace_bytes(B,F,Tx,Ty), 256-byte aligned.
  */
 size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty);
+/* Clears the flag area of a fused workspace (once, after allocating it); see MAS_B200_WS_PREPARED.  The cross-kernel
+ * flags hold a per-call nonce, so entries left by earlier calls never read as "set". */
+int mas_b200_fused_workspace_prepare(void *workspace_dev, size_t workspace_bytes, int B, int F, int Tx, int Ty,
+                                     void *stream);
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,
                                     const int *t_x_dev, const int *t_y_dev,
                                     int B, int F, int Tx, int Ty, float max_neg_val,

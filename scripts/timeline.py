@@ -12,10 +12,12 @@ d = dict(mu=mu_x.to(dev), y=y.to(dev), tx=t_x.to(dev), ty=t_y.to(dev), dur=torch
          path=torch.empty((B, TX, TY), device=dev))
 ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, TX, TY)
 ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+PREP = int(os.environ.get("PREPARED", "1"))
+if PREP: assert L.mas_b200_fused_workspace_prepare(ws.data_ptr(), ws_bytes, B, F, TX, TY, None) == 0
 sp = torch.cuda.current_stream(dev).cuda_stream
 def call():
     rc = L.mas_b200_log_prior_maximum_path(d["mu"].data_ptr(), d["y"].data_ptr(), d["tx"].data_ptr(), d["ty"].data_ptr(), B, F, TX, TY, -1e9,
-                                           d["path"].data_ptr(), _lib.PATH_F32, d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes, _lib.LP_AUTO, sp)
+                                           d["path"].data_ptr(), _lib.PATH_F32, d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes, _lib.LP_AUTO | (_lib.WS_PREPARED if PREP else 0), sp)
     assert rc == 0, rc
 for _ in range(5): call()
 torch.cuda.synchronize()
@@ -65,3 +67,20 @@ setp("mas_debug_ptr", dm3); call(); torch.cuda.synchronize()
 _lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0); _lib.set_option("fused_impl", 0)
 s3 = dm3.cpu()[i].tolist()
 print(f"gated, flags preset b={i}: dp_done {s3[2]-s3[0]} all_warps {s3[4]-s3[0]} backtrack {s3[5]-s3[4]} tail {s3[6]-s3[5]} total {s3[6]-s3[0]}; spins {s3[10]} producer done {s3[15]-s3[0]}")
+
+# inter-step gap: two back-to-back overlapped calls with separate stamp buffers
+dlA = torch.zeros((B * 8, 32), dtype=torch.int64, device=dev); dlB = torch.zeros_like(dlA)
+dmA = torch.zeros((B, 16), dtype=torch.int64, device=dev); dmB = torch.zeros_like(dmA)
+for _ in range(3): call()
+torch.cuda.synchronize()
+setp("lp_debug_ptr", dlA); setp("mas_debug_ptr", dmA); call()
+setp("lp_debug_ptr", dlB); setp("mas_debug_ptr", dmB); call()
+torch.cuda.synchronize()
+for n in ("mas_debug_ptr", "lp_debug_ptr"):
+    _lib.set_option(n + "_lo", 0); _lib.set_option(n + "_hi", 0)
+a, b2 = dlA.cpu(), dlB.cpu(); ma, mb = dmA.cpu(), dmB.cpu()
+a = a[a[:, 0] != 0]; b2 = b2[b2[:, 0] != 0]
+endA = max(int(a[:, 2].max()), int(a[:, 1].max()), int(ma[:, 13].max()))
+print("back-to-back: step A LP start %.2f .. last stamp %.2f us; step B LP start %.2f (gap %.2f us), B first MAS start %.2f" % (
+    0.0, (endA - int(a[:, 0].min())) / 1e3, (int(b2[:, 0].min()) - int(a[:, 0].min())) / 1e3,
+    (int(b2[:, 0].min()) - endA) / 1e3, (int(mb[:, 12].min()) - int(a[:, 0].min())) / 1e3))

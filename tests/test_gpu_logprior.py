@@ -83,6 +83,50 @@ def test_fused_call_bit_exact_on_its_own_value_and_agrees_with_reference_pipelin
     assert agree > 0.999
 
 
+def test_prepared_workspace_nonce_flags_survive_reuse_and_stale_contents():
+    """MAS_B200_WS_PREPARED: the flag area is cleared once and never again; stale flags of earlier calls (older
+    nonces) must never read as set -- also when the SAME workspace serves different inputs back to back, with and
+    without the dense path, interleaved with unprepared calls on it."""
+    from face_gan_tts_b200 import _lib
+
+    L = _lib.lib()
+    B, F, Tx, Ty = 32, 80, 190, 1000
+    sets = []
+    for k in range(3):
+        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=300 + k)
+        sets.append((mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV)))
+    prev = _lib.set_option("fused_impl", 1)
+    try:
+        want = [fgt.log_prior_maximum_path(*s_, path_dtype=torch.float32) for s_ in sets]
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("fused_impl", prev)
+    ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, Tx, Ty)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=DEV)
+    ws.fill_(0xAB)                                             # garbage everywhere, then prepare
+    assert L.mas_b200_fused_workspace_prepare(ws.data_ptr(), ws_bytes, B, F, Tx, Ty, None) == 0
+    path = torch.empty((B, Tx, Ty), device=DEV)
+    dur = torch.empty((B, Tx), dtype=torch.int32, device=DEV)
+    ft = torch.empty((B, Ty), dtype=torch.int32, device=DEV)
+    st = torch.empty((B,), dtype=torch.int32, device=DEV)
+    sp = torch.cuda.current_stream().cuda_stream
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    for i in range(120):
+        mu, yy, tx, ty = sets[i % 3]
+        dense = (i % 4) != 3
+        impl = _lib.LP_AUTO | (_lib.WS_PREPARED if (i % 7) != 5 else 0)
+        rc = L.mas_b200_log_prior_maximum_path(mu.data_ptr(), yy.data_ptr(), tx.data_ptr(), ty.data_ptr(), B, F, Tx, Ty, -1e9,
+                                               path.data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
+                                               dur.data_ptr(), ft.data_ptr(), st.data_ptr(), ws.data_ptr(), ws_bytes, impl, sp)
+        assert rc == 0
+        w = want[i % 3]
+        bad += (dur != w.durations).sum() + (ft != w.frame_token).sum()
+        if dense:
+            bad += (path != w.path).sum()
+    torch.cuda.synchronize()
+    assert int(bad) == 0
+
+
 def test_alignment_plan_equals_functional_api_and_reuses_buffers():
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=6, F=80, Tx=190, Ty=1000, seed=17)
     mu2, y2, t_x2, t_y2 = synthetic.lrs2_batch(B=6, F=80, Tx=190, Ty=1000, seed=18)
