@@ -28,6 +28,7 @@ UNITS = [
     ("upload.cu", "upload", []),
     ("log_prior_ffma.cu", "log_prior_ffma", []),
     ("log_prior_tc.cu", "log_prior_tc", []),
+    ("lp_mas_fused.cu", "lp_mas_fused", []),
 ]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

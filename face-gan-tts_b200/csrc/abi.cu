@@ -33,7 +33,7 @@ Opt g_opts[] = {
     {"upload_impl", {0}},            // 0/1 SM zero-copy pull kernel, 2 copy engine (one 2-D copy per utterance and tensor), 3 TMA bulk copies for y
     {"upload_l2_256b", {0}},         // 1: zero-copy loads carry the L2::256B fetch hint
     {"upload_ctas", {0}},            // CTAs of the zero-copy upload kernel (0 = one per SM)
-    {"fused_impl", {0}},             // 0 auto, 1 force unfused pipeline, 2 force fused kernel
+    {"fused_impl", {0}},             // 0 auto (fused kernel when the shape is covered), 1 force the serial form
 };
 }  // namespace
 
@@ -61,41 +61,6 @@ int device_info(DeviceInfo *out) {
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// The overlapped pipeline runs two kernels that wait for each other's flags; a tool that serialises kernel
-// launches (ncu replay, compute-sanitizer) would starve it, so it is switched off when one is attached.
-// MAS_B200_PIPELINE=serial|overlap overrides the detection.
-static bool kernels_may_overlap() {
-    static const bool v = [] {
-        const char *e = std::getenv("MAS_B200_PIPELINE");
-        if (e && std::strcmp(e, "serial") == 0) return false;
-        if (e && std::strcmp(e, "overlap") == 0) return true;
-        // what ncu 2025.x sets in the profiled process (scripts/ncu_env_probe.py), plus the CUDA injection hooks
-        for (const char *k : {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NVIDIA_PROCESS_INJECTION_XML_TARGET_SETTINGS",
-                              "NV_CUDA_START_SUSPENDED", "CUDA_INJECTION64_PATH", "NV_SANITIZER_INJECTION_PORT_BASE"})
-            if (std::getenv(k) != nullptr) return false;
-        return true;
-    }();
-    return v;
-}
-
-// One auxiliary stream + fork/join events per (host thread, device): the overlapped log-prior || MAS pipeline
-// forks from and joins back into the caller's stream, so the call stays stream-ordered for the caller.
-struct AuxStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-static AuxStream *aux_stream() {
-    static thread_local AuxStream cache[16];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    AuxStream &a = cache[dev];
-    if (a.stream == nullptr) {
-        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) { a.stream = nullptr; return nullptr; }
-        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) {
-            cudaStreamDestroy(a.stream); a.stream = nullptr; return nullptr;
-        }
-    }
-    return &a;
-}
 
 }  // namespace masb200
 
@@ -168,34 +133,18 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev, int B, int F, 
     return launch_log_prior_ffma(mu_x_dev, y_dev, B, F, Tx, Ty, log_prior_dev, s);
 }
 
-// flag area of the fused workspace: [B][groups][slots] group flags + [B] done flags (slots = log-prior M-tile CTAs)
-static size_t fused_flag_ints(int B, int Tx, int Ty) {
-    return (size_t)B * ((Ty + 63) / 64) * (size_t)((Tx + 127) / 128) + (size_t)B;
-}
-
 size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty) {
     if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return 0;
-    // MAS workspace + the [B,Tx,Ty] value matrix (L2-resident hand-off) + per-group ready flags
-    return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256) +
-           align_up(sizeof(int) * fused_flag_ints(B, Tx, Ty), 256);
+    // MAS workspace + the [B,Tx,Ty] value matrix of the serial form (shapes the fused kernel does not cover)
+    return align_up(workspace_layout(B, Tx, Ty).total, 256) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256);
 }
 
 int mas_b200_fused_workspace_prepare(void *workspace_dev, size_t workspace_bytes, int B, int F, int Tx, int Ty, void *stream) {
+    // kept for ABI compatibility: the fused call keeps no state in the workspace between calls any more
+    (void)stream;
     if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!workspace_dev || workspace_bytes < mas_b200_fused_workspace_bytes(B, F, Tx, Ty)) return MAS_B200_ERR_WORKSPACE;
-    char *flags = static_cast<char *>(workspace_dev) + align_up(workspace_layout(B, Tx, Ty).total, 256) +
-                  align_up(sizeof(float) * (size_t)B * Tx * Ty, 256);
-    MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * fused_flag_ints(B, Tx, Ty), static_cast<cudaStream_t>(stream)));
     return MAS_B200_OK;
-}
-
-// One nonce per overlapped call, process-wide and never 0: group / done flags hold the nonce of the call that set
-// them, so entries left by earlier calls (all older nonces) or the zeros of a prepared workspace never look "set".
-static int next_nonce() {
-    static std::atomic<unsigned> counter{0};
-    unsigned v;
-    do { v = counter.fetch_add(1, std::memory_order_relaxed) + 1; } while ((v & 0x7fffffffu) == 0);
-    return (int)(v & 0x7fffffffu);
 }
 
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, const int *t_x_dev,
@@ -206,89 +155,19 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
     if (!mu_x_dev || !y_dev || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!workspace_dev || workspace_bytes < mas_b200_fused_workspace_bytes(B, F, Tx, Ty)) return MAS_B200_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) return MAS_B200_ERR_ALIGN;
-    const bool ws_prepared = (impl & MAS_B200_WS_PREPARED) != 0;      // flag area known clean: no memset in this call
-    impl &= ~MAS_B200_WS_PREPARED;
+    impl &= ~MAS_B200_WS_PREPARED;                                  // accepted for compatibility, no effect
     const size_t mas_ws = align_up(workspace_layout(B, Tx, Ty).total, 256);
     float *value = reinterpret_cast<float *>(static_cast<char *>(workspace_dev) + mas_ws);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-    // Overlapped pipeline: the tcgen05 log-prior kernel (aux stream, on the SMs the B MAS CTAs leave free)
-    // publishes every 64-frame group of every utterance with a device-scope flag; the MAS kernel's TMA
-    // producer acquires the flag before loading the tiles of that group.  The value matrix is handed over
-    // through L2, and the alignment search starts while most of the log-prior is still being computed.
-    DeviceInfo di;
-    int rc = device_info(&di);
-    if (rc != MAS_B200_OK) return rc;
-    const int fi = option("fused_impl");
-    const bool tc_ok = (impl == MAS_B200_LP_AUTO || impl == MAS_B200_LP_TCGEN05) && option("lp_impl") != MAS_B200_LP_FFMA &&
-                       log_prior_tc_supported(mu_x_dev, y_dev, value, B, F, Tx, Ty);
-    if (tc_ok && fi != 1 && B + log_prior_tc_min_ctas(B, F, Tx) <= di.sm_count && (fi == 2 || kernels_may_overlap())) {
-        AuxStream *aux = aux_stream();
-        if (aux != nullptr) {
-            const int ngroups = (Ty + 63) / 64;
-            int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(value) + align_up(sizeof(float) * (size_t)B * Tx * Ty, 256));
-            const int slots = log_prior_tc_flag_target(F, Tx);
-            int *done = flags + (size_t)B * ngroups * slots;    // [B] "table final" flags
-            const int nonce = next_nonce();
-            const bool want_path = path_dtype != MAS_B200_PATH_NONE && path_dev != nullptr;
-            PathJob job{};
-            if (want_path) {
-                job.start = mas_start_table(workspace_dev, B, Tx, Ty);
-                job.dur = mas_dur_table(workspace_dev, B, Tx, Ty, durations_dev);
-                job.done = done; job.done_value = nonce; job.path = path_dev; job.path_dtype = path_dtype;
-            }
-            if (fi == 3) {
-                // diagnostics only: log-prior first (serial), then the GATED MAS kernel with every flag already set --
-                // isolates the cost of the gating code path from the cost of waiting for the producer
-                rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, s);
-                if (rc != MAS_B200_OK) return rc;
-                MASB200_CUDA_TRY(cudaMemsetAsync(flags, 1, sizeof(int) * ((size_t)B * ngroups * slots + B), s));
-                MasLaunch G{};
-                G.value = value; G.stride_b = (long long)Tx * Ty; G.stride_x = Ty;
-                G.t_x = t_x_dev; G.t_y = t_y_dev; G.B = B; G.Tx = Tx; G.Ty = Ty; G.neg = max_neg_val;
-                G.path = path_dev; G.path_dtype = path_dtype;
-                G.durations = durations_dev; G.frame_token = frame_token_dev; G.status = status_dev;
-                G.workspace = workspace_dev; G.workspace_bytes = mas_ws; G.stream = s;
-                G.gate = flags; G.gate_pitch = ngroups; G.gate_slots = slots; G.flag_value = 0x01010101;
-                return launch_mas(G);
-            }
-            // A workspace the caller prepared once (mas_b200_fused_workspace_prepare) and has only used for fused
-            // calls since needs no clearing: stale flags hold older nonces.  Otherwise clear it now.
-            // (A CUDA-graph capture bakes this call's nonce into the kernel nodes, and every replay would then find
-            // its own previous flags "set": under capture the clearing always stays in, as a node of the graph.)
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-            if (!ws_prepared || cap != cudaStreamCaptureStatusNone)
-                MASB200_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)B * ngroups * slots + B), s));
-            MASB200_CUDA_TRY(cudaEventRecord(aux->fork, s));
-            MASB200_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-            // validate the consumer's plan before anything is launched (each kernel waits for the other's flags)
-            MasLaunch L{};
-            L.value = value; L.stride_b = (long long)Tx * Ty; L.stride_x = Ty;
-            L.t_x = t_x_dev; L.t_y = t_y_dev; L.B = B; L.Tx = Tx; L.Ty = Ty; L.neg = max_neg_val;
-            L.path = path_dev; L.path_dtype = path_dtype;
-            L.durations = durations_dev; L.frame_token = frame_token_dev; L.status = status_dev;
-            L.workspace = workspace_dev; L.workspace_bytes = mas_ws; L.stream = s;
-            L.gate = flags; L.gate_pitch = ngroups; L.gate_slots = slots; L.flag_value = nonce;
-            L.done = want_path ? done : nullptr;
-            L.dry_run = 1;
-            rc = launch_mas(L);
-            if (rc != MAS_B200_OK) return rc;
-            L.dry_run = 0;
-            // producer first (the block scheduler must place its CTAs before the consumer's start spinning)
-            // The log-prior kernel is on the critical path (the search cannot start before its first group), so it
-            // stays on the caller's stream right behind the memset; the MAS kernel takes the cross-stream hop.
-            rc = launch_log_prior_tc(mu_x_dev, y_dev, B, F, Tx, Ty, value, s, flags, ngroups, di.sm_count - B,
-                                     want_path ? &job : nullptr, nonce);
-            L.stream = aux->stream;
-            if (rc == MAS_B200_OK) rc = launch_mas(L);
-            MASB200_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
-            // join even on error so the aux stream never runs ahead of the caller's stream
-            MASB200_CUDA_TRY(cudaStreamWaitEvent(s, aux->join, 0));
-            return rc;
-        }
-    }
-    rc = mas_b200_log_prior(mu_x_dev, y_dev, B, F, Tx, Ty, value, impl, stream);
+    // One kernel, one CTA per utterance: the tcgen05 epilogue writes the value tiles into the shared-memory ring
+    // of the alignment search (lp_mas_fused.cu).  Shapes it does not cover (n_feats = 128, texts longer than 256
+    // tokens, very long utterances) run the serial form: log-prior kernel -> [B,Tx,Ty] in the workspace -> MAS kernel.
+    const bool tc_wanted = (impl == MAS_B200_LP_AUTO || impl == MAS_B200_LP_TCGEN05) && option("lp_impl") != MAS_B200_LP_FFMA;
+    if (tc_wanted && option("fused_impl") != 1 && lp_mas_fused_supported(mu_x_dev, y_dev, B, F, Tx, Ty))
+        return launch_lp_mas_fused(mu_x_dev, y_dev, t_x_dev, t_y_dev, B, F, Tx, Ty, max_neg_val, path_dev, path_dtype,
+                                   durations_dev, frame_token_dev, status_dev, workspace_dev, mas_ws,
+                                   static_cast<cudaStream_t>(stream));
+    int rc = mas_b200_log_prior(mu_x_dev, y_dev, B, F, Tx, Ty, value, impl, stream);
     if (rc != MAS_B200_OK) return rc;
     return mas_b200_maximum_path(value, (long long)Tx * Ty, Ty, t_x_dev, t_y_dev, B, Tx, Ty, max_neg_val, path_dev,
                                  path_dtype, durations_dev, frame_token_dev, status_dev, workspace_dev, mas_ws, stream);

@@ -1,7 +1,7 @@
 // log_prior_tc.cu -- Grad-TTS log-prior on the 5th-generation tensor cores (tcgen05 + TMEM), unfused:
 // the front end of lp_tc_frontend.cuh with an epilogue that streams [B,Tx,Ty] to HBM.
 // One CTA = one utterance x a run of 64-frame groups; warps 0-3 epilogue, warps 4-7 operand split, warp 8 TMA loads + MMA issue,
-// warps 9-10 (even / odd groups) TMA stores of the finished tiles + publication to a concurrent MAS kernel.
+// warps 9-10 (even / odd groups) TMA stores of the finished tiles.
 #include <atomic>
 #include <cstring>
 
@@ -17,7 +17,7 @@ float log_prior_const(int F);   // log_prior_ffma.cu
 
 namespace {
 
-constexpr int kTcThreads = 352;        // warps 0-3 epilogue, 4-7 split, 8 TMA loads + MMA issue, 9-10 TMA stores + publication
+constexpr int kTcThreads = 352;        // warps 0-3 epilogue, 4-7 split, 8 TMA loads + MMA issue, 9-10 TMA stores
 constexpr int kMaxF = 96;             // 4F (A hi/lo, two M-tiles) + 128 (D) <= 512 columns; beyond: split-M (2F + 64)
 
 struct LpTcParams {
@@ -27,14 +27,8 @@ struct LpTcParams {
     float cst;
     int groups_per_cta, ngroups;
     int chunks;          // CTAs per utterance
-    int strided;         // 1: CTA c takes groups c, c+chunks, ... (frame order across CTAs: feeds a concurrent MAS kernel)
-    PathJob job;         // optional: expand the dense path of utterance b once the MAS kernel reports it done
     long long *dbg;      // diagnostics: [ctas][32] globaltimer stamps / wait-cycle accumulators
-    int *flags;          // optional [B][flag_pitch][flag_slots]: entry (b, group, M-tile slot) = flag_value once that
-                         //   CTA's part of the 64-frame group is in memory
-    int flag_slots, flag_value;
     int skip;            // diagnostics (option lp_debug_skip): 1 no global stores, 2 no MMA issue, 4 no split math, 8 no staging
-    int flag_pitch;
 };
 
 // SPLITM: one CTA per (utterance, group run, M-tile) -- blockIdx.z is the M-tile; see lp_tc_frontend.cuh.
@@ -62,9 +56,9 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
     const int lane = tid & 31;
     const int b = blockIdx.y;
-    const int gs = P.strided ? P.chunks : 1;                                  // group stride of this CTA
-    const int g0 = P.strided ? (int)blockIdx.x : (int)blockIdx.x * P.groups_per_cta;
-    const int ng = P.strided ? (P.ngroups - g0 + gs - 1) / gs : min(P.groups_per_cta, P.ngroups - g0);   // groups of this CTA
+    constexpr int gs = 1;                                                     // group stride of this CTA
+    const int g0 = (int)blockIdx.x * P.groups_per_cta;
+    const int ng = min(P.groups_per_cta, P.ngroups - g0);                     // groups of this CTA
     if (ng <= 0) return;
     const int MT = SPLITM ? 1 : (P.Tx + 127) >> 7;                           // M-tiles of 128 text positions in this CTA
     const int mt0 = SPLITM ? (int)blockIdx.z : 0;
@@ -89,9 +83,8 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
         for (int g = 0; g < ng; ++g) lp_aux_split<KS>(S, g, tid - 128, warp - 4, lane, (P.skip & 4) != 0);
         if (dbg && tid == 128) dbg[9] = clock64() - cs0;
     } else if (warp >= 9) {
-        // ---- store / publication warps: warp 9 takes the even groups, warp 10 the odd ones, so that waiting for the
-        // completion of one group's bulk stores (before its flag may be released) never delays the next group's
-        // stores.  One elected lane per step, warp-uniform control flow.
+        // ---- store warps: warp 9 takes the even groups, warp 10 the odd ones.  One elected lane per step,
+        // warp-uniform control flow.
         for (int gg = warp - 9; gg < ng; gg += 2) {
             const int gidx = g0 + gg * gs;
             const int t0 = gidx * kLpGroup;
@@ -109,16 +102,6 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                 }
                 __syncwarp();
             }
-            if (elect_one()) {
-                if (P.flags != nullptr) {
-                    // publish the group to the MAS kernel running next to this one: bulk stores complete ->
-                    // async-proxy / generic-proxy fence -> device-scope release
-                    tma_store_wait_all();
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    gflag_release(P.flags + ((size_t)b * P.flag_pitch + gidx) * P.flag_slots + mt0, P.flag_value);
-                }
-            }
-            __syncwarp();
         }
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
@@ -171,50 +154,6 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kLpTmemCols);
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[1] = t; }
-
-    // ---- dense path: every warp of this kernel owns the rows {gw, gw + total_warps, ...} of EVERY utterance and
-    // streams them out as soon as the MAS kernel (running on other SMs) publishes that utterance's [start,dur]
-    // table -- the last utterance to finish is written by all SMs of the kernel at once.  32 done-flags are
-    // polled per load (one lane each), so a sweep costs one L2 round trip.
-    if (P.job.path != nullptr) {
-        // rows are dealt CTA-major (warp w of CTA c takes row w*nctas + c, ...): a text of 190 rows keeps two warps
-        // of EVERY CTA busy instead of all warps of the first few
-        const int nctas = (int)(gridDim.x * gridDim.y * gridDim.z);
-        const int total_warps = nctas * (kTcThreads / 32);
-        const int gw = warp * nctas + (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
-        if (gw < P.Tx) {
-            uint32_t proc[4] = {0u, 0u, 0u, 0u};
-            int remaining = P.B;
-            const long long c0 = clock64();
-            while (remaining > 0) {
-                for (int base = 0; base < P.B; base += 32) {
-                    const int u = base + lane;
-                    const bool f = (u < P.B) && gflag_acquire(P.job.done + u) == P.job.done_value;
-                    uint32_t ready = __ballot_sync(kFullMask, f) & ~proc[base >> 5];
-                    proc[base >> 5] |= ready;
-                    while (ready != 0u) {
-                        const int ub = base + __ffs((int)ready) - 1;
-                        ready &= ready - 1;
-                        --remaining;
-                        for (int x = gw; x < P.Tx; x += total_warps) {
-                            const size_t row = (size_t)ub * P.Tx + x;
-                            if (P.job.path_dtype == MAS_B200_PATH_F32)
-                                write_path_row<float>(reinterpret_cast<float *>(P.job.path) + row * P.Ty, P.job.start[row],
-                                                      P.job.dur[row], P.Ty, lane);
-                            else
-                                write_path_row<int>(reinterpret_cast<int *>(P.job.path) + row * P.Ty, P.job.start[row],
-                                                    P.job.dur[row], P.Ty, lane);
-                        }
-                    }
-                }
-                if (remaining > 0) {
-                    __nanosleep(256);
-                    if (clock64() - c0 > (1ll << 33)) __trap();
-                }
-            }
-        }
-        if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[2] = t; }
-    }
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 encoder() {
@@ -232,13 +171,13 @@ PFN_cuTensorMapEncodeTiled_v12000 encoder() {
 
 }  // namespace
 
-// 3-D map over y[b, f, t]: box {64 frames, F mel bins, 1}, no swizzle, zero fill beyond Ty.
-int make_y_tensor_map(const float *y, int B, int F, int Ty, CUtensorMap *out) {
+// 3-D map over y[b, f, t]: box {box_frames, F mel bins, 1}, no swizzle, zero fill beyond Ty.
+int make_y_tensor_map(const float *y, int B, int F, int Ty, int box_frames, CUtensorMap *out) {
     auto enc = encoder();
     if (!enc) return MAS_B200_ERR_CUDA;
     cuuint64_t gdim[3] = {(cuuint64_t)Ty, (cuuint64_t)F, (cuuint64_t)B};
     cuuint64_t gstr[2] = {(cuuint64_t)Ty * 4, (cuuint64_t)F * Ty * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kLpGroup, (cuuint32_t)F, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_frames, (cuuint32_t)F, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(y), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -267,16 +206,12 @@ bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out,
     return true;
 }
 
-// CTAs the kernel needs co-resident at least (one per utterance and M-tile) and the count a `flags` entry reaches
-// when a group is complete -- what the overlapped pipeline (abi.cu) sizes itself with.
 // split-M (one CTA per 128-row M-tile): n_feats = 128, whose A operand alone fills TMEM, and texts longer than the
 // two M-tiles one CTA holds
 static bool lp_split_m(int F, int Tx) { return F > kMaxF || Tx > 256; }
-int log_prior_tc_min_ctas(int B, int F, int Tx) { return lp_split_m(F, Tx) ? B * ((Tx + 127) / 128) : B; }
-int log_prior_tc_flag_target(int F, int Tx) { return lp_split_m(F, Tx) ? (Tx + 127) / 128 : 1; }
 
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream, int *flags, int flag_pitch, int max_ctas, const PathJob *job, int flag_value) {
+                        cudaStream_t stream) {
     if (!mu_x || !y || !out || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     if (!log_prior_tc_supported(mu_x, y, out, B, F, Tx, Ty)) return MAS_B200_ERR_UNSUPPORTED;
     DeviceInfo di;
@@ -284,7 +219,7 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     if (rc != MAS_B200_OK) return rc;
     CUtensorMap ymap;
     std::memset(&ymap, 0, sizeof(ymap));
-    rc = make_y_tensor_map(y, B, F, Ty, &ymap);
+    rc = make_y_tensor_map(y, B, F, Ty, kLpGroup, &ymap);
     if (rc != MAS_B200_OK) return rc;
 
     CUtensorMap omap;
@@ -295,23 +230,19 @@ int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx,
     LpTcParams P{};
     P.mu = mu_x; P.out = out; P.B = B; P.Tx = Tx; P.Ty = Ty; P.cst = log_prior_const(F);
     P.ngroups = (Ty + kLpGroup - 1) / kLpGroup;
-    P.flags = flags; P.flag_pitch = flag_pitch; P.flag_value = flag_value;
-    P.flag_slots = log_prior_tc_flag_target(F, Tx);
     {
         const unsigned lo = (unsigned)option("lp_debug_ptr_lo"), hi = (unsigned)option("lp_debug_ptr_hi");
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
     }
-    if (job) P.job = *job;
     P.skip = option("lp_debug_skip");
     const bool splitm = lp_split_m(F, Tx);
     const int mtiles = splitm ? (Tx + 127) / 128 : 1;          // grid.z
-    const int cta_budget = (max_ctas > 0 && max_ctas < di.sm_count) ? max_ctas : di.sm_count;
+    const int cta_budget = di.sm_count;
     int chunks = cta_budget / (B * mtiles);                                // one wave of CTAs (one CTA per SM: TMEM + smem)
     chunks = chunks < 1 ? 1 : (chunks > P.ngroups ? P.ngroups : chunks);
     P.groups_per_cta = (P.ngroups + chunks - 1) / chunks;
     chunks = (P.ngroups + P.groups_per_cta - 1) / P.groups_per_cta;
     P.chunks = chunks;
-    P.strided = flags != nullptr ? 1 : 0;
     size_t smem = ((LpFrontSmem::total(F) + 1023) / 1024) * 1024 + (size_t)(splitm ? 1 : 2) * 32768 + 1024;
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;   // > half an SM: one CTA per SM (each allocates all of TMEM)
 

@@ -1,0 +1,540 @@
+// lp_mas_fused.cu -- the fused log-prior + Monotonic Alignment Search kernel: ONE CTA per utterance, ONE launch,
+// the [Tx,Ty] value matrix never leaves the SM.
+//
+// Replaces reference model/face_tts.py:165-174 (log_prior -> maximum_path) for F = n_feats in {64, 80, 96} and
+// Tx <= 256 (the LRS2 training shapes).  The tcgen05 front end (TMA y tiles -> exact tf32 hi/lo split -> 3xTF32
+// tcgen05.mma with A = mu_x parked in TENSOR MEMORY, lp_tc_frontend.cuh) produces the value matrix one 32-frame
+// tile at a time; its epilogue writes every tile STRAIGHT INTO THE SHARED-MEMORY RING the alignment search reads
+// (mas_forward.cuh: register-resident column, SHFL halo, 1 direction bit per cell in shared memory, per-token
+// backtrack).  Values and paths are bit-identical to the serial form (log_prior_tc_kernel -> HBM -> mas_forward_kernel):
+// same K order, same ((ysq + dot) + musq) + const association, same DP.
+//
+// Warp roles (15 warps; warp % 4 = scheduler partition, the arbiter favours the higher warp id):
+//    0..3   epilogue: prologue (mu_x -> hi/lo -> TMEM), then per tile TMEM -> registers -> + ysq/musq/const -> ring
+//    6, 7   operand split: raw y tile [F][32] -> hi/lo K-major core matrices + ysq
+//    10     TMA loads (mu_x block, y tiles) + tcgen05.mma issue
+//    11, 14 backtrack helpers: per-tile transfer tables in the shadow of the DP
+//    12, 13 DP warps (text rows 0..127 / 128..255): alone with one epilogue warp on partitions 0 / 1, highest ids there
+//    4, 5, 8, 9  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
+// TMEM lane m of M-tile mt holds text row x = 128*mt + 4*(m & 31) + (m >> 5): the epilogue thread of that lane then owns
+// ring slot (m >> 5) * 32W + 32*mt + (m & 31) -- the lane-major permuted layout of mas_common.cuh -- so its eight 16-byte
+// stores are bank-conflict free, M-tile mt is exactly DP warp mt's rows, and each (stage, M-tile) has its own
+// full / empty mbarrier pair.
+//
+// Pipeline per 32-frame tile g:  TMA raw[g&1] -> split -> hi/lo[g&1] -> MMA -> D[g&1] (TMEM, two stages)
+//                                -> epilogue -> ring[g % NS] -> DP -> direction words -> helpers.
+#include <atomic>
+#include <cstring>
+
+#include <cudaTypedefs.h>
+
+#include "lp_tc_frontend.cuh"
+#include "mas_forward.cuh"
+#include "mas_host.h"
+
+namespace masb200 {
+
+float log_prior_const(int F);                                                                        // log_prior_ffma.cu
+int make_y_tensor_map(const float *y, int B, int F, int Ty, int box_frames, CUtensorMap *out);       // log_prior_tc.cu
+
+namespace {
+
+constexpr int kFR = 4;                       // text rows per DP lane
+constexpr int kFusedWarps = 15;
+constexpr int kFusedThreads = kFusedWarps * 32;
+constexpr int kWarpSplit = 6;                // 6, 7
+constexpr int kWarpMma = 10;
+constexpr int kWarpHelpA = 11;
+constexpr int kWarpDp = 12;                  // 12, 13
+constexpr int kWarpHelpB = 14;
+constexpr int kYsqRing = 8;                  // ysq ring entries (the split warps run at most ~4 tiles ahead of the epilogue)
+
+struct FusedParams {
+    MasParams mas;       // t_x, t_y, B, Tx, Ty, neg, ring_stages, start, dur, frame_token, status, path, path_dtype, dbg
+    const float *mu;     // [B,F,Tx]
+    float cst;           // -0.5 * F * log(2 pi)
+};
+
+// Shared-memory carve-up (bytes from a 1024-aligned base):
+//   [ring: NS value tiles][halo rings][raw y: 2][hi: 2][lo: 2][ysq partials][ysq ring][mbarriers][flags][direction words + transfer tables]
+// The [F][Tx] staging of mu_x for the prologue aliases the front (ring, halo, possibly raw).
+template <int KS, int W>
+struct FusedSmem {
+    static constexpr int F = 8 * KS;
+    static constexpr int XP = 32 * kFR * W;
+    using M = MasSmem<kFR, W>;
+    static constexpr uint32_t kRaw = (uint32_t)F * 32u * 4u;      // one raw y tile [F][32 frames]
+    static constexpr uint32_t kOp = (uint32_t)F * 32u * 4u;       // one hi (or lo) operand tile
+    __host__ __device__ static constexpr size_t off_halo(int ns) { return M::ring_bytes(ns); }
+    __host__ __device__ static constexpr size_t off_raw(int ns) { return off_halo(ns) + M::halo_bytes(ns); }
+    __host__ __device__ static constexpr size_t off_hi(int ns) { return off_raw(ns) + 2 * kRaw; }
+    __host__ __device__ static constexpr size_t off_lo(int ns) { return off_hi(ns) + 2 * kOp; }
+    __host__ __device__ static constexpr size_t off_part(int ns) { return off_lo(ns) + 2 * kOp; }             // [2][2][32] f32
+    __host__ __device__ static constexpr size_t off_ysq(int ns) { return off_part(ns) + 2 * 2 * 32 * 4; }     // [8][32] f32
+    __host__ __device__ static constexpr size_t off_bars(int ns) { return off_ysq(ns) + kYsqRing * 32 * 4; }  // 16 + 4*ns mbarriers
+    __host__ __device__ static constexpr size_t off_flags(int ns) { return off_bars(ns) + 8 * (size_t)(16 + 4 * ns); }
+    __host__ __device__ static constexpr size_t off_bits(int ns) { return ((off_flags(ns) + 64 + 127) / 128) * 128; }
+    // direction words (4 B) + transfer table (1 B) per row and tile
+    __host__ __device__ static constexpr size_t total(int ns, int ntiles) { return off_bits(ns) + (size_t)5 * ntiles * XP; }
+};
+
+template <int KS, int W>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ymap) {
+    using FS = FusedSmem<KS, W>;
+    constexpr int R = kFR;
+    constexpr int F = 8 * KS;
+    constexpr int XP = FS::XP;
+    constexpr int NT = kTileFrames;
+    constexpr int kTileFloats = XP * kTilePitch;
+    constexpr int kG = XP / 32, kGH = kG / 2;                 // row groups of a tile: [0,kGH) helper A, [kGH,kG) helper B
+    constexpr uint32_t kSbo = (uint32_t)F * 32u;              // 8 frames x F mel bins x 4 B per row group of an operand tile
+    const MasParams &P = FP.mas;
+    const int NS = P.ring_stages;
+    const int HS = NS + 1;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    float *hbuf = reinterpret_cast<float *>(smem_raw + FS::off_halo(NS));                 // [W+1][HS][32] + [W][32]
+    unsigned char *raw = smem_raw + FS::off_raw(NS);
+    unsigned char *ophi = smem_raw + FS::off_hi(NS);
+    unsigned char *oplo = smem_raw + FS::off_lo(NS);
+    float *part = reinterpret_cast<float *>(smem_raw + FS::off_part(NS));
+    float *ysq = reinterpret_cast<float *>(smem_raw + FS::off_ysq(NS));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + FS::off_bars(NS));
+    uint64_t *bar_mu = bars, *bar_aready = bars + 1, *bar_raw = bars + 2, *bar_split = bars + 4, *bar_bfree = bars + 6;
+    uint64_t *bar_dfull = bars + 8;              // [D stage][M-tile]
+    uint64_t *bar_dempty = bars + 12;            // [D stage]
+    uint64_t *ring_full = bars + 16;             // [ring stage][M-tile]
+    uint64_t *ring_empty = ring_full + 2 * NS;   // [ring stage][M-tile]
+    int *hprog = reinterpret_cast<int *>(smem_raw + FS::off_flags(NS));                   // [W+2] progress flags
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hprog + 8);
+    uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem_raw + FS::off_bits(NS));
+    float *mu_s = reinterpret_cast<float *>(smem_raw);                                    // prologue staging [F][Tx]
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(kFullMask, tid >> 5, 0);     // provably warp-uniform for ptxas
+    const int lane = tid & 31;
+    const int t_x = __shfl_sync(kFullMask, P.t_x[b], 0);
+    const int t_y = __shfl_sync(kFullMask, P.t_y[b], 0);
+    int *start_b = P.start + (size_t)b * P.Tx;
+    int *dur_b = P.dur + (size_t)b * P.Tx;
+
+    // ---- per-item validation (the reference is undefined here: core.pyx:34) ----
+    if (t_x < 1 || t_y < 1 || t_x > P.Tx || t_y > P.Ty || t_x > t_y) {
+        for (int x = tid; x < P.Tx; x += kFusedThreads) { start_b[x] = 0; dur_b[x] = 0; }
+        if (P.frame_token)
+            for (int y = tid; y < P.Ty; y += kFusedThreads) P.frame_token[(size_t)b * P.Ty + y] = -1;
+        if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_BAD_LENGTH;
+        __syncthreads();
+        write_path_any(P, b, start_b, dur_b, tid, kFusedThreads);
+        return;
+    }
+    if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_OK;
+
+    const int ntiles = (t_y + NT - 1) / NT;
+    const int w_act = (t_x + 32 * R - 1) / (32 * R);          // active DP warps == M-tiles with valid rows
+    unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XP);   // [ntiles][XP] transfer table
+    long long *dbg = P.dbg ? P.dbg + (size_t)b * 16 : nullptr;
+    if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
+    // the prologue's mu_x staging reaches into the raw y buffers: y tiles (and everything behind them) start late
+    const bool late_start = (size_t)F * P.Tx * 4 > FS::off_raw(NS);
+
+    if (tid == 0) {
+        mbar_init(bar_mu, 1);
+        mbar_init(bar_aready, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_raw[i], 1); mbar_init(&bar_split[i], 64); mbar_init(&bar_bfree[i], 1); mbar_init(&bar_dempty[i], 128);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_dfull[i], 1);
+        for (int i = 0; i < 2 * NS; ++i) { mbar_init(&ring_full[i], 128); mbar_init(&ring_empty[i], 1); }
+        for (int i = 0; i < W; ++i) hprog[i] = 0;
+        hprog[W] = 0x7fffffff;                               // the flag a warp without predecessor polls
+        hprog[W + 1] = 0;
+        mbar_fence_init();
+    }
+    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(kFullMask, *tmem_slot, 0);
+    // TMEM columns: A hi/lo of M-tile mt at (2*mt + lo) * F; D of (stage p, M-tile mt) behind them
+    auto col_d = [](int p, int mt) { return (uint32_t)(2 * W * F + (p * W + mt) * 32); };
+
+    if (warp == kWarpMma) {
+        // ======================= TMA loads + MMA issue (warp-uniform; one elected lane acts) =======================
+        const uint32_t mu_bytes = (uint32_t)F * (uint32_t)P.Tx * 4u;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_mu, mu_bytes);
+            tma_bulk_load_1d(mu_s, FP.mu + (size_t)b * F * P.Tx, mu_bytes, bar_mu);
+        }
+        __syncwarp();
+        if (late_start) mbar_wait_warp(bar_aready, 0);
+        if (elect_one()) {
+            for (int q = 0; q < 2 && q < ntiles; ++q) {
+                mbar_arrive_expect_tx(&bar_raw[q], FS::kRaw);
+                tma_load_3d(raw + (size_t)q * FS::kRaw, &ymap, q * NT, 0, b, &bar_raw[q]);
+            }
+        }
+        __syncwarp();
+        mbar_wait_warp(bar_aready, 0);
+        const uint32_t idesc = umma_idesc_tf32_ts(128, NT);
+        for (int g = 0; g < ntiles; ++g) {
+            const int p = g & 1;
+            const uint32_t par = (uint32_t)(g >> 1) & 1u;
+            mbar_wait_warp(&bar_split[p], par);
+            // every split thread is done with raw buffer p: fetch tile g + 2 into it
+            if (g + 2 < ntiles && elect_one()) {
+                mbar_arrive_expect_tx(&bar_raw[p], FS::kRaw);
+                tma_load_3d(raw + (size_t)p * FS::kRaw, &ymap, (g + 2) * NT, 0, b, &bar_raw[p]);
+            }
+            __syncwarp();
+            if (g >= 2) mbar_wait_warp(&bar_dempty[p], par ^ 1u);           // epilogue drained D stage p (tile g - 2)
+            tc_fence_after();
+            const uint32_t bh = smem_u32(ophi) + (uint32_t)p * FS::kOp;
+            const uint32_t bl = smem_u32(oplo) + (uint32_t)p * FS::kOp;
+#pragma unroll
+            for (int mt = 0; mt < W; ++mt) {
+                if (mt < w_act) {
+                    const uint32_t dcol = tmem + col_d(p, mt);
+                    const uint32_t ah = tmem + lp_col_a(F, mt, 0), al = tmem + lp_col_a(F, mt, 1);
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const uint64_t dh = umma_smem_desc_k_nosw(bh + ks * 256u, 128u, kSbo);
+                        const uint64_t dl = umma_smem_desc_k_nosw(bl + ks * 256u, 128u, kSbo);
+                        umma_tf32_ts_elect(dcol, ah + 8u * ks, dh, idesc, ks > 0 ? 1u : 0u);     // hi * hi
+                        umma_tf32_ts_elect(dcol, ah + 8u * ks, dl, idesc, 1u);                    // hi * lo
+                        umma_tf32_ts_elect(dcol, al + 8u * ks, dh, idesc, 1u);                    // lo * hi
+                    }
+                    umma_commit_elect(&bar_dfull[p * 2 + mt]);     // D of (tile g, M-tile mt) complete -> epilogue warps
+                }
+            }
+            umma_commit_elect(&bar_bfree[p]);                      // operand buffer p may be refilled -> split warps
+            __syncwarp();
+        }
+    } else if (warp == kWarpSplit || warp == kWarpSplit + 1) {
+        // ======================= operand split: raw [F][32] -> hi/lo K-major core matrices, ysq =======================
+        // thread = (frame n = lane, mel-bin chunks kc = sw, sw + 2, ...): 4 conflict-free LDS.32 down a column of the raw
+        // tile, one STS.128 per operand into core matrix (n / 8, kc), row n % 8.
+        const int sw = warp - kWarpSplit;
+        if (late_start) mbar_wait(bar_aready, 0);
+        const int n = lane;
+        const uint32_t row_off = (uint32_t)(n >> 3) * kSbo + (uint32_t)(n & 7) * 16u;
+        for (int g = 0; g < ntiles; ++g) {
+            const int p = g & 1;
+            const uint32_t par = (uint32_t)(g >> 1) & 1u;
+            if (g >= 2) mbar_wait(&bar_bfree[p], par ^ 1u);        // MMA(g - 2) has read operand buffer p
+            mbar_wait(&bar_raw[p], par);
+            const float *rw = reinterpret_cast<const float *>(raw + (size_t)p * FS::kRaw);
+            unsigned char *hb = ophi + (size_t)p * FS::kOp, *lb = oplo + (size_t)p * FS::kOp;
+            float q = 0.f;
+#pragma unroll
+            for (int kc = sw; kc < 2 * KS; kc += 2) {
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = rw[(4 * kc + k) * NT + n];
+                uint4 h, l;
+                tf32_split(v[0], h.x, l.x); tf32_split(v[1], h.y, l.y);
+                tf32_split(v[2], h.z, l.z); tf32_split(v[3], h.w, l.w);
+                *reinterpret_cast<uint4 *>(hb + row_off + (uint32_t)kc * 128u) = h;
+                *reinterpret_cast<uint4 *>(lb + row_off + (uint32_t)kc * 128u) = l;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q = fmaf(-0.5f * v[k], v[k], q);
+            }
+            float *pd = part + p * 64;
+            pd[sw * 32 + n] = q;
+            fence_proxy_async_smem();              // hi/lo stores -> visible to the tensor core's smem reads
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            if (sw == 0) ysq[(g & (kYsqRing - 1)) * 32 + n] = pd[n] + pd[32 + n];
+            mbar_arrive(&bar_split[p]);            // also: raw buffer p may be refilled
+        }
+    } else if (warp < 4) {
+        // ======================= epilogue warps: TMEM lane quadrant = warp =======================
+        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        float musq[W];
+        // ---- prologue: mu_x rows -> exact tf32 hi/lo -> TMEM (A operand for the whole CTA), musq
+        mbar_wait(bar_mu, 0);
+#pragma unroll
+        for (int mt = 0; mt < W; ++mt) {
+            musq[mt] = 0.f;
+            if (mt < w_act) {
+                const int x = 128 * mt + 4 * lane + warp;
+                const bool xin = x < P.Tx;
+                float sq = 0.f;
+#pragma unroll
+                for (int f0 = 0; f0 < F; f0 += 8) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float v = xin ? mu_s[(f0 + k) * P.Tx + x] : 0.f;
+                        tf32_split(v, hi[k], lo[k]);
+                        sq = fmaf(-0.5f * v, v, sq);
+                    }
+                    tmem_st8(tmem + lane_base + lp_col_a(F, mt, 0) + f0, hi);
+                    tmem_st8(tmem + lane_base + lp_col_a(F, mt, 1) + f0, lo);
+                }
+                musq[mt] = sq;
+            }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_aready);
+        if (dbg && tid == 0) dbg[1] = clock64();
+        // ---- per tile: D (TMEM) -> ((ysq + dot) + musq) + const -> ring slot of this lane's text row
+        int stage = 0;
+        uint32_t sphase = 0;                                       // parity of the ring stage's CURRENT use
+        for (int g = 0; g < ntiles; ++g) {
+            const int p = g & 1;
+            const uint32_t par = (uint32_t)(g >> 1) & 1u;
+            const float *yq_row = ysq + (g & (kYsqRing - 1)) * 32;
+#pragma unroll
+            for (int mt = 0; mt < W; ++mt) {
+                if (mt < w_act) {
+                    uint32_t d[32];
+                    mbar_wait(&bar_dfull[p * 2 + mt], par);
+                    tc_fence_after();
+                    tmem_ld32(tmem + lane_base + col_d(p, mt), d);
+                    tmem_wait_ld();
+                    if (mt == w_act - 1) { tc_fence_before(); mbar_arrive(&bar_dempty[p]); }
+                    if (g >= NS) mbar_wait(&ring_empty[stage * 2 + mt], sphase ^ 1u);     // DP warp mt released the stage
+                    float *rowp = ring + (size_t)stage * kTileFloats + (size_t)(warp * (32 * W) + 32 * mt + lane) * kTilePitch;
+                    const float ms = musq[mt];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 yq = *reinterpret_cast<const float4 *>(yq_row + 4 * c);
+                        float4 o;
+                        o.x = ((yq.x + __uint_as_float(d[4 * c + 0])) + ms) + FP.cst;
+                        o.y = ((yq.y + __uint_as_float(d[4 * c + 1])) + ms) + FP.cst;
+                        o.z = ((yq.z + __uint_as_float(d[4 * c + 2])) + ms) + FP.cst;
+                        o.w = ((yq.w + __uint_as_float(d[4 * c + 3])) + ms) + FP.cst;
+                        *reinterpret_cast<float4 *>(rowp + ((c ^ (lane & 7)) << 2)) = o;
+                    }
+                    mbar_arrive(&ring_full[stage * 2 + mt]);
+                }
+            }
+            if (++stage == NS) { stage = 0; sphase ^= 1u; }
+        }
+    } else if (warp == kWarpHelpA || warp == kWarpHelpB) {
+        // ======================= backtrack helpers: transfer tables behind the LAST active DP warp =======================
+        const int *flag_last = hprog + (w_act - 1);
+        int known = 0;
+        for (int jt = 0; jt < ntiles; ++jt) {
+            if (known < jt + 1) known = flag_wait_ge_warp(flag_last, jt + 1);
+            if (warp == kWarpHelpA)
+                bt_tile_transfer<0, kGH>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane);
+            else
+                bt_tile_transfer<kGH, kG>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane);
+        }
+    } else if (warp >= kWarpDp && warp < kWarpDp + w_act) {
+        // ======================= DP warps (see mas_forward_kernel: nothing in the tile loop may branch or predicate
+        // on a loop-invariant condition; role differences are ADDRESSES) =======================
+        const int w = warp - kWarpDp;
+        const int lane_cta = 32 * w + lane;
+        const int x0 = lane_cta * R;                             // lane's first text position
+        const int xw0 = 32 * R * w;                              // warp's first text position
+        const int lane7 = lane & 7;
+        const uint32_t lane0_mask = (lane == 0) ? 0xffffffffu : 0u;
+        const bool has_consumer = (w + 1 < w_act);
+        float *hconst = hbuf + (size_t)W * HS * NT;              // warp 0's halo input (one constant row)
+        float *hdump = hconst + (size_t)HS * NT;                 // [W][32] where lanes without a consumer store
+        const float *hb_in = (w > 0) ? hbuf + (size_t)(w - 1) * HS * NT : hconst;
+        const int hin_step = (w > 0) ? NT : 0;
+        float *hb_out = hbuf + (size_t)w * HS * NT;
+        const uint32_t hout_base = (has_consumer && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * NT);
+        const uint32_t hout_step = (has_consumer && lane == 31) ? NT * 4u : 0u;
+        const int *flag_in = (w > 0) ? hprog + (w - 1) : hprog + W;           // hprog[W] is pre-satisfied
+        int *flag_out = hprog + w;
+
+        float q[R];
+        uint32_t acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { q[r] = P.neg; acc[r] = 0u; }
+        // neighbour value for frame 0: only text position 0 has a defined one (core.pyx:24-25, y == 0)
+        float up = (x0 == 0) ? 0.f : P.neg;
+        int known = 0, stage = 0, hs = 0;
+        uint32_t phase = 0;
+        // the first tile of this warp's M-tile is in the ring: the prologue is over, and with it every read of the mu_x
+        // staging that aliases the halo area -- only now may the halo rows be initialised
+        mbar_wait_warp(&ring_full[w], 0);
+        bool tile_ready = true;
+        if (w == 0) {
+            hconst[lane] = P.neg;                                // the row above text position 0 (core.pyx:26-27)
+            __syncwarp();
+            if (dbg && lane == 0) dbg[2] = clock64();
+        }
+        for (int j = 0; j < ntiles; ++j) {
+            const int t0 = j * NT;
+            if (!tile_ready) mbar_wait_warp(&ring_full[stage * 2 + w], phase);
+            if (known < j + 1) known = flag_wait_ge_warp(flag_in, j + 1);
+            const int next_stage = (stage + 1 == NS) ? 0 : stage + 1;
+            const uint32_t next_phase = (stage + 1 == NS) ? (phase ^ 1) : phase;
+            const int next_hs = (hs + 1 == HS) ? 0 : hs + 1;
+            tile_ready = (j + 1 < ntiles) && mbar_test_warp(&ring_full[next_stage * 2 + w], next_phase);
+
+            const float *lane_tile = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
+            const float *hin = hb_in + hs * hin_step;
+            const uint32_t hout_addr = hout_base + hs * hout_step;
+            const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
+            const int dl0 = lane_cta - t0 / R;
+            if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+            else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+
+            // direction words of this tile, walk-ready (see mas_forward_kernel)
+            if (diag) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (((x0 + r) >> 5) == j) acc[r] |= 1u << ((x0 + r) & 31);
+            }
+            if (x0 == 0) acc[0] = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = __brev(acc[r]);
+            store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, acc);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = 0u;
+
+            __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
+            if (elect_one()) {
+                flag_release(flag_out, j + 1);
+                mbar_arrive(&ring_empty[stage * 2 + w]);
+            }
+            stage = next_stage;
+            phase = next_phase;
+            hs = next_hs;
+        }
+        if (dbg && lane == 0 && w == w_act - 1) dbg[4] = clock64();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kLpTmemCols); }
+    if (dbg && tid == 0) dbg[3] = clock64();
+
+    // ================================ backtrack + outputs (the ring is idle now) ================================
+    int *tok = reinterpret_cast<int *>(ring);
+    int *xin = tok + XP;
+    mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid);
+    if (dbg && tid == 0) dbg[5] = clock64();
+    int *hd = xin + ((ntiles + 3) & ~3);
+    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid);
+    write_path_any(P, b, start_b, dur_b, tid, kFusedThreads);
+    if (dbg && tid == 0) {
+        dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y;
+        long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[13] = t;
+    }
+}
+
+constexpr size_t kFusedMaxSmem = 232448 - 1024;
+
+template <int KS, int W>
+int fused_plan(int Tx, int Ty, int *ns_out, size_t *smem_out) {
+    using FS = FusedSmem<KS, W>;
+    const int ntiles = (Ty + kTileFrames - 1) / kTileFrames;
+    int cap = option("mas_ring_stages");
+    if (cap <= 0 || cap > 6) cap = 6;
+    int ns = 0;
+    while (ns < cap && FS::total(ns + 1, ntiles) <= kFusedMaxSmem) ++ns;
+    if (ns < 2) return MAS_B200_ERR_UNSUPPORTED;
+    // the tail's scratch (token starts, tile entry tokens, frame heads) lives in the idle ring
+    if (mas_tail_scratch_ints(FS::XP, ntiles, Ty) * sizeof(int) > FS::M::ring_bytes(ns)) return MAS_B200_ERR_UNSUPPORTED;
+    *ns_out = ns;
+    *smem_out = FS::total(ns, ntiles);
+    return MAS_B200_OK;
+}
+
+template <int KS, int W>
+int fused_launch(FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
+    int ns = 0;
+    size_t smem = 0;
+    int rc = fused_plan<KS, W>(FP.mas.Tx, FP.mas.Ty, &ns, &smem);
+    if (rc != MAS_B200_OK || dry_run) return rc;
+    FP.mas.ring_stages = ns;
+    static std::atomic<int> configured[16];
+    int dev = 0;
+    MASB200_CUDA_TRY(cudaGetDevice(&dev));
+    auto kern = lp_mas_fused_kernel<KS, W>;
+    if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
+        MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedMaxSmem));
+        if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
+    }
+    kern<<<FP.mas.B, kFusedThreads, smem, stream>>>(FP, ymap);
+    MASB200_CUDA_TRY(cudaGetLastError());
+    return MAS_B200_OK;
+}
+
+template <int KS>
+int fused_dispatch_w(FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
+    return FP.mas.Tx <= 128 ? fused_launch<KS, 1>(FP, ymap, stream, dry_run) : fused_launch<KS, 2>(FP, ymap, stream, dry_run);
+}
+
+int fused_dispatch(int F, FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
+    switch (F) {
+        case 64: return fused_dispatch_w<8>(FP, ymap, stream, dry_run);
+        case 80: return fused_dispatch_w<10>(FP, ymap, stream, dry_run);
+        case 96: return fused_dispatch_w<12>(FP, ymap, stream, dry_run);
+        default: return MAS_B200_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+// Shapes the fused kernel covers (everything else runs the serial form: log-prior kernel -> HBM -> MAS kernel):
+// F in {64, 80, 96} (A = mu_x hi/lo of two M-tiles + two D stages within the 512 TMEM columns), Tx <= 256 (two
+// M-tiles / two DP warps), Ty % 4 == 0 and 16-byte aligned operands (TMA), direction words + a >= 2-stage ring within
+// 227 KB of shared memory (Ty <= ~2900 frames at Tx <= 128, ~1500 at Tx <= 256).
+bool lp_mas_fused_supported(const float *mu_x, const float *y, int B, int F, int Tx, int Ty) {
+    if (!(F == 64 || F == 80 || F == 96) || Tx > 256 || Ty % 4 != 0 || B <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(mu_x) & 15)) return false;
+    FusedParams FP{};
+    FP.mas.Tx = Tx; FP.mas.Ty = Ty;
+    CUtensorMap dummy;
+    std::memset(&dummy, 0, sizeof(dummy));
+    return fused_dispatch(F, FP, dummy, nullptr, true) == MAS_B200_OK;
+}
+
+int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const int *t_y, int B, int F, int Tx, int Ty,
+                        float neg, void *path, int path_dtype, int *durations, int *frame_token, int *status,
+                        void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!mu_x || !y || !t_x || !t_y || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    if (path_dtype != MAS_B200_PATH_NONE && path_dtype != MAS_B200_PATH_F32 && path_dtype != MAS_B200_PATH_I32)
+        return MAS_B200_ERR_ARG;
+    if (path_dtype != MAS_B200_PATH_NONE && !path) return MAS_B200_ERR_ARG;
+    if (!lp_mas_fused_supported(mu_x, y, B, F, Tx, Ty)) return MAS_B200_ERR_UNSUPPORTED;
+    const Workspace ws = workspace_layout(B, Tx, Ty);
+    if (!workspace || workspace_bytes < ws.total) return MAS_B200_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return MAS_B200_ERR_ALIGN;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != MAS_B200_OK) return rc;
+    CUtensorMap ymap;
+    std::memset(&ymap, 0, sizeof(ymap));
+    rc = make_y_tensor_map(y, B, F, Ty, kTileFrames, &ymap);
+    if (rc != MAS_B200_OK) return rc;
+
+    char *wsb = static_cast<char *>(workspace);
+    FusedParams FP{};
+    MasParams &P = FP.mas;
+    P.t_x = t_x; P.t_y = t_y; P.B = B; P.Tx = Tx; P.Ty = Ty; P.neg = neg;
+    P.start = reinterpret_cast<int *>(wsb + ws.start_off);
+    P.dur = durations ? durations : reinterpret_cast<int *>(wsb + ws.dur_off);
+    P.frame_token = frame_token;
+    P.status = status;
+    {
+        const unsigned lo = (unsigned)option("mas_debug_ptr_lo"), hi = (unsigned)option("mas_debug_ptr_hi");
+        P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
+    }
+    // dense path: in-kernel for batches of several waves (the writes of finished CTAs overlap the others' search),
+    // a separate streaming kernel on all SMs otherwise
+    int fuse = option("mas_fused_path_write");
+    if (fuse < 0) fuse = (B >= 2 * di.sm_count) ? 1 : 0;
+    const bool want_path = path_dtype != MAS_B200_PATH_NONE;
+    P.path = (want_path && fuse) ? path : nullptr;
+    P.path_dtype = (want_path && fuse) ? path_dtype : MAS_B200_PATH_NONE;
+    FP.mu = mu_x;
+    FP.cst = log_prior_const(F);
+    rc = fused_dispatch(F, FP, ymap, stream, false);
+    if (rc != MAS_B200_OK) return rc;
+    if (want_path && !fuse) return launch_path_expand(P.start, P.dur, B, Tx, Ty, path, path_dtype, stream);
+    return MAS_B200_OK;
+}
+
+}  // namespace masb200

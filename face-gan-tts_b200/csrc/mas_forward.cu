@@ -177,8 +177,6 @@ int launch_mas(const MasLaunch &L) {
     P.gbits_stride_b = (long long)ws.tiles * ws.rows_pitch;
     P.gline = reinterpret_cast<float *>(wsb + ws.gline_off);
     P.line_pitch = ws.line_pitch;
-    P.gate = L.gate; P.gate_pitch = L.gate_pitch; P.gate_slots = L.gate_slots > 0 ? L.gate_slots : 1;
-    P.gate_value = L.flag_value; P.done_value = L.flag_value; P.done = L.done;
     {   // diagnostics: device pointer to a [B][8] int64 buffer smuggled through two int options
         const unsigned lo = (unsigned)option("mas_debug_ptr_lo"), hi = (unsigned)option("mas_debug_ptr_hi");
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
@@ -186,7 +184,7 @@ int launch_mas(const MasLaunch &L) {
 
     int fuse = option("mas_fused_path_write");
     if (fuse < 0) fuse = (L.B >= 2 * di.sm_count) ? 1 : 0;
-    const bool want_path = L.path_dtype != MAS_B200_PATH_NONE && L.done == nullptr;
+    const bool want_path = L.path_dtype != MAS_B200_PATH_NONE;
     P.path = (want_path && fuse) ? L.path : nullptr;
     P.path_dtype = (want_path && fuse) ? L.path_dtype : MAS_B200_PATH_NONE;
 

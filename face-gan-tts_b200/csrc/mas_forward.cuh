@@ -76,13 +76,6 @@ struct MasParams {
     int line_pitch;
     void *path;              // optional in-kernel dense path write
     int path_dtype;          // MAS_B200_PATH_*
-    int *done;               // optional [B]: set to 1 (device-scope release) once the [start,dur] table of item b is final
-    const int *gate;         // optional [B][gate_pitch]: group g of utterance b may be read once gate != 0
-    int gate_pitch;          //   (written by the log-prior kernel running concurrently), 64 frames per group
-    int gate_slots;          // entries per group (one per log-prior M-tile CTA); a group is ready when ALL hold gate_value
-    int gate_value;          // the call's nonce: stale entries of earlier calls (or the zeros of a fresh workspace) never
-                             //   match it, so the flags need no clearing between calls
-    int done_value;          // value released into done[b] (the same nonce)
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
@@ -454,6 +447,127 @@ __device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, i
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tail shared by mas_forward_kernel (SMEM_BITS) and the fused log-prior + MAS kernel (lp_mas_fused.cu).
+// ---------------------------------------------------------------------------------------------------
+// Backtrack over walk-ready direction words in shared memory: the transfer tables of row groups [G0, G1) still owed
+// for tiles [jt_owed, ntiles) are shared by all warps, then one dependent shared-memory load per TILE gives the
+// token each tile is entered with, then one thread per tile emits the start frames tok[x] of its tokens.
+template <int XP, int NTHREADS, int G0, int G1>
+__device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsigned char *nj_s, int *tok, int *xin,
+                                                   int jt_owed, int ntiles, int t_x, int t_y, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if constexpr (G0 < G1) {
+        constexpr int nwarps = NTHREADS / 32;
+        for (int jt = jt_owed + warp; jt < ntiles; jt += nwarps)
+            bt_tile_transfer<G0, G1>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane);
+        __syncthreads();
+    }
+    if (tid == 0) {                                                       // one dependent load per tile
+        int x = t_x - 1;
+        for (int jt = ntiles - 1; jt >= 0; --jt) {
+            xin[jt] = x;
+            const int n = nj_s[(size_t)jt * XP + x];
+            x -= n;
+        }
+        tok[0] = 0;
+    }
+    __syncthreads();
+    for (int jt = tid; jt < ntiles; jt += NTHREADS) {                     // one thread per tile: start frames
+        const uint32_t *bj = bits_s + (size_t)jt * XP;
+        const int lo = jt > 0 ? xin[jt - 1] : 0;
+        uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
+        for (int x = xin[jt]; x > lo; --x) {
+            const uint32_t m = bj[x] & mk;
+            tok[x] = (jt << 5) + 32 - __ffs((int)m);
+            mk = m ^ (0u - m);
+        }
+    }
+    __syncthreads();
+}
+
+// [start, duration] per token from the start frames tok[] (shared memory), then frame -> token index.
+// Tokens are non-decreasing along the frames, so frame -> token is a running MAX over "head" marks
+// (hd[start frame of x] = x): one thread per 8 frames, warp shuffle scan, 16-byte stores -- instead of one thread
+// per token walking its frames (a 200-frame silence token was the whole tail).
+//   hd   scratch in shared memory: [(Ty + 3) & ~3] heads + [32] warp totals
+template <int NTHREADS>
+__device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b, const int *tok, int *hd, int t_x, int t_y,
+                                                      int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    int *start_b = P.start + (size_t)b * P.Tx;
+    int *dur_b = P.dur + (size_t)b * P.Tx;
+    int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
+    for (int x = tid; x < P.Tx; x += NTHREADS) {
+        int s = 0, d = 0;
+        if (x < t_x) {
+            s = tok[x];
+            d = ((x + 1 < t_x) ? tok[x + 1] : t_y) - s;
+        }
+        start_b[x] = s;
+        dur_b[x] = d;
+    }
+    if (ft) {
+        int *wt = hd + ((P.Ty + 3) & ~3);
+        for (int t = tid; t < t_y; t += NTHREADS) hd[t] = -1;
+        __syncthreads();
+        for (int x = tid; x < t_x; x += NTHREADS) {
+            const int s = tok[x];
+            const int e = (x + 1 < t_x) ? tok[x + 1] : t_y;
+            if (e > s) hd[s] = x;
+        }
+        __syncthreads();
+        const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
+        constexpr int nw = NTHREADS >> 5;
+        int carry = -1;
+        for (int base_t = 0; base_t < P.Ty; base_t += NTHREADS * 8) {
+            const int t0 = base_t + tid * 8;
+            int v[8], run = -1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t0 + k;
+                const int h = (t < t_y) ? hd[t] : -1;
+                run = max(run, h);
+                v[k] = run;
+            }
+            int inc = run;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const int n = __shfl_up_sync(kFullMask, inc, dlt);
+                if (lane >= dlt) inc = max(inc, n);
+            }
+            int exc = __shfl_up_sync(kFullMask, inc, 1);
+            if (lane == 0) exc = -1;
+            if (lane == 31) wt[warp] = inc;
+            __syncthreads();
+            int basev = max(carry, exc), nc = carry;
+            for (int w2 = 0; w2 < nw; ++w2) {
+                const int wv = wt[w2];
+                if (w2 < warp) basev = max(basev, wv);
+                nc = max(nc, wv);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (t0 + k < t_y) ? max(basev, v[k]) : -1;
+            if (vec && t0 + 7 < P.Ty) {
+                *reinterpret_cast<int4 *>(ft + t0) = make_int4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<int4 *>(ft + t0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (t0 + k < P.Ty) ft[t0 + k] = v[k];
+            }
+            __syncthreads();                 // wt is reused by the next round
+            carry = nc;
+        }
+    }
+    __syncthreads();                         // start_b / dur_b of every thread are in place for the path writer
+}
+
+// ints of shared-memory scratch the two functions above need: tok [XP] + xin [tiles] + heads [Ty] + warp totals [32]
+__host__ __device__ constexpr size_t mas_tail_scratch_ints(int XP, int ntiles, int Ty) {
+    return (size_t)XP + (size_t)((ntiles + 3) & ~3) + (size_t)((Ty + 3) & ~3) + 32;
+}
+
 // MULTIPASS: text longer than XP rows (carry line between row passes); its runtime role flags cost
 // the single-pass instantiations nothing.
 // Warps: 0..W-1 DP, W TMA producer, W+1 (SMEM_BITS only) backtrack helper.
@@ -499,7 +613,6 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_BAD_LENGTH;
         __syncthreads();
         write_path_any(P, b, start_b, dur_b, tid, nthreads);
-        if (P.done != nullptr) { __threadfence(); __syncthreads(); if (tid == 0) gflag_release(P.done + b, P.done_value); }
         return;
     }
     if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_OK;
@@ -543,35 +656,12 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             // ============================ producer warp ============================
             int stage = 0;
             uint32_t phase = 0;
-            long long gate_spins = 0, gate_cycles = 0, gate_first = 0;
-            int gate_known = 0;                                // groups [0, gate_known) are known to be in memory
             int jt_next = 0;                                   // next tile whose transfer table (upper groups) is owed
             const int *flag_last = hprog + (w_act - 1);
             for (int j = 0; j < ntiles; ++j) {
                 mbar_wait(&ring_empty[stage], phase ^ 1);
                 float *dst = ring + (size_t)stage * kTileFloats;
                 const int t0 = j * NT;
-                if (P.gate != nullptr && (j >> 1) >= gate_known) {
-                    // the value matrix is being produced by another kernel: wait for this 64-frame group.  Lane l
-                    // looks at group (j/2 + l), so one L2 round trip also learns how far ahead the producer is.
-                    const int g0 = j >> 1;
-                    const int *gf = P.gate + (size_t)b * P.gate_pitch;
-                    const long long c0 = clock64();
-                    while (true) {
-                        const int g = g0 + lane;
-                        bool all = g < P.gate_pitch;
-                        for (int m = 0; m < P.gate_slots; ++m)
-                            all = all && (gflag_acquire(gf + (size_t)min(g, P.gate_pitch - 1) * P.gate_slots + m) == P.gate_value);
-                        const unsigned ready = __ballot_sync(kFullMask, all);
-                        if (ready & 1u) { gate_known = g0 + __ffs((int)~ready) - 1; break; }    // consecutive ready groups
-                        __nanosleep(64);
-                        ++gate_spins;
-                        if (clock64() - c0 > (1ll << 31)) __trap();
-                    }
-                    { const long long dc = clock64() - c0; gate_cycles += dc; if (j == 0) gate_first = dc; }
-                    asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> the TMA reads below
-                    __syncwarp();
-                }
                 const int nfr = min(NT, P.Ty - t0);                 // frames that exist in memory
                 if (P.aligned) {
                     // lane i issues request (r, qb): rows {rows_base + (qb*NB + l)*R + r : l < NB}
@@ -621,7 +711,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
                 }
             }
             if (lane == 0) bt_state[3] = jt_next;      // the rest is shared by all warps once the DP is done
-            if (dbg && lane == 0) { dbg[10] = gate_spins; dbg[11] = jt_next; dbg[15] = clock64(); dbg[9] = gate_cycles; dbg[8] = gate_first; }
+            if (dbg && lane == 0) { dbg[11] = jt_next; dbg[15] = clock64(); }
         } else if (SMEM_BITS && warp == W + 1) {
             // ========================== backtrack helper warp ==========================
             // trails the LAST active DP warp (its progress flag implies every earlier warp is past the tile too)
@@ -742,35 +832,8 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     int *tok = SMEM_BITS ? reinterpret_cast<int *>(ring) : start_b;
     int *xin = SMEM_BITS ? tok + XP : reinterpret_cast<int *>(gline_b);
     if constexpr (SMEM_BITS) {
-        if constexpr (kGH < kG) {
-            // transfer tables (upper row groups) the producer warp did not get to: one tile per warp
-            constexpr int nwarps = nthreads / 32;
-            for (int jt = bt_state[3] + warp; jt < ntiles; jt += nwarps)
-                bt_tile_transfer<kGH, kG>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x,
-                                          bt_tile_mask(jt, ntiles, t_y), lane);
-            __syncthreads();
-        }
-        if (tid == 0) {                                                       // one dependent load per tile
-            int x = t_x - 1;
-            for (int jt = ntiles - 1; jt >= 0; --jt) {
-                xin[jt] = x;
-                const int n = nj_s[(size_t)jt * XP + x];
-                x -= n;
-            }
-            tok[0] = 0;
-        }
-        __syncthreads();
-        for (int jt = tid; jt < ntiles; jt += nthreads) {                     // one thread per tile: start frames
-            const uint32_t *bj = bits_s + (size_t)jt * XP;
-            const int lo = jt > 0 ? xin[jt - 1] : 0;
-            uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
-            for (int x = xin[jt]; x > lo; --x) {
-                const uint32_t m = bj[x] & mk;
-                tok[x] = (jt << 5) + 32 - __ffs((int)m);
-                mk = m ^ (0u - m);
-            }
-        }
-        __syncthreads();
+        // transfer tables (upper row groups) the producer warp did not get to, tile entry tokens, start frames
+        mas_backtrack_smem<XP, nthreads, kGH, kG>(bits_s, nj_s, tok, xin, bt_state[3], ntiles, t_x, t_y, tid);
     } else {
         const int rows_pitch = P.gbits_rows_pitch;
         uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
@@ -822,81 +885,9 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
     // scratch of the scan below, in the (idle) ring behind tok / xin: heads [Ty], warp totals [32]
     int *hd = xin + ((ntiles + 3) & ~3);
-    const bool scan_ft = SMEM_BITS && ((size_t)(XP + ((ntiles + 3) & ~3) + ((P.Ty + 3) & ~3) + 32) * sizeof(int) <= S::ring_bytes(NS));
+    const bool scan_ft = SMEM_BITS && (mas_tail_scratch_ints(XP, ntiles, P.Ty) * sizeof(int) <= S::ring_bytes(NS));
     if (scan_ft) {
-        // The [start,dur] table first: it is all the dense-path writers (this kernel or the one watching `done`)
-        // need, so `done` is released before the frame->token index is produced.
-        for (int x = tid; x < P.Tx; x += nthreads) {
-            int s = 0, d = 0;
-            if (x < t_x) {
-                s = tok[x];
-                d = ((x + 1 < t_x) ? tok[x + 1] : t_y) - s;
-            }
-            start_b[x] = s;
-            dur_b[x] = d;
-        }
-        if (P.done != nullptr) {                 // the dense path of this item is written by the kernel watching `done`
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) gflag_release(P.done + b, P.done_value);
-        }
-        if (ft) {
-            // frame -> token: tokens are non-decreasing along the frames, so it is a running MAX over "head" marks
-            // (hd[start frame of x] = x).  One thread per 8 frames, warp shuffle scan, 16-byte stores -- instead of
-            // one thread per token walking its frames (a 200-frame silence token was the whole tail).
-            int *wt = hd + ((P.Ty + 3) & ~3);
-            for (int t = tid; t < t_y; t += nthreads) hd[t] = -1;
-            __syncthreads();
-            for (int x = tid; x < t_x; x += nthreads) {
-                const int s = tok[x];
-                const int e = (x + 1 < t_x) ? tok[x + 1] : t_y;
-                if (e > s) hd[s] = x;
-            }
-            __syncthreads();
-            const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
-            const int nw = nthreads >> 5;
-            int carry = -1;
-            for (int base_t = 0; base_t < P.Ty; base_t += nthreads * 8) {
-                const int t0 = base_t + tid * 8;
-                int v[8], run = -1;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int t = t0 + k;
-                    const int h = (t < t_y) ? hd[t] : -1;
-                    run = max(run, h);
-                    v[k] = run;
-                }
-                int inc = run;
-#pragma unroll
-                for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    const int n = __shfl_up_sync(kFullMask, inc, dlt);
-                    if (lane >= dlt) inc = max(inc, n);
-                }
-                int exc = __shfl_up_sync(kFullMask, inc, 1);
-                if (lane == 0) exc = -1;
-                if (lane == 31) wt[warp] = inc;
-                __syncthreads();
-                int basev = max(carry, exc), nc = carry;
-                for (int w2 = 0; w2 < nw; ++w2) {
-                    const int wv = wt[w2];
-                    if (w2 < warp) basev = max(basev, wv);
-                    nc = max(nc, wv);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = (t0 + k < t_y) ? max(basev, v[k]) : -1;
-                if (vec && t0 + 7 < P.Ty) {
-                    *reinterpret_cast<int4 *>(ft + t0) = make_int4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<int4 *>(ft + t0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (t0 + k < P.Ty) ft[t0 + k] = v[k];
-                }
-                __syncthreads();                 // wt is reused by the next round
-                carry = nc;
-            }
-        }
-        if (P.done == nullptr) __syncthreads();  // start_b / dur_b of every thread are in place for the path writer
+        mas_emit_outputs_scan<nthreads>(P, b, tok, hd, t_x, t_y, tid);
     } else {
         for (int x = tid; x < P.Tx; x += nthreads) {
             int s = 0, d = 0;
@@ -915,11 +906,6 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
         if (!SMEM_BITS)                                                    // tok aliases start_b: zero the padding rows
             for (int x = t_x + tid; x < P.Tx; x += nthreads) start_b[x] = 0;
         __syncthreads();
-        if (P.done != nullptr) {                 // the dense path of this item is written by the kernel watching `done`
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) gflag_release(P.done + b, P.done_value);
-        }
     }
     write_path_any(P, b, start_b, dur_b, tid, nthreads);
     if (dbg && tid == 0) {

@@ -56,23 +56,9 @@ struct MasLaunch {
     void *workspace;
     size_t workspace_bytes;
     cudaStream_t stream;
-    const int *gate;    // optional device flags [B][gate_pitch] (see MasParams::gate); null normally
-    int gate_pitch;
-    int gate_slots;     // gate entries per group: one per log-prior M-tile CTA (0/1: one writer)
-    int flag_value;     // the call's nonce: what gate entries and done[] hold when set (see abi.cu)
     int dry_run;        // 1: validate arguments / plan only, launch nothing
-    int *done;          // optional device flags [B]: when set, the dense path is NOT written here; the kernel
-                        // watching `done` expands it from the [start,dur] table (see PathJob)
 };
 
-// dense-path expansion job handed to the log-prior kernel of the overlapped pipeline
-struct PathJob {
-    const int *start, *dur;   // [B,Tx] tables in the MAS workspace
-    const int *done;          // [B]
-    int done_value;           // the call's nonce
-    void *path;
-    int path_dtype;
-};
 const int *mas_start_table(void *workspace, int B, int Tx, int Ty);
 const int *mas_dur_table(void *workspace, int B, int Tx, int Ty, const int *user_durations);
 int launch_mas(const MasLaunch &L);
@@ -108,10 +94,12 @@ int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int T
                           cudaStream_t stream);
 // tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.
 int launch_log_prior_tc(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
-                        cudaStream_t stream, int *flags = nullptr, int flag_pitch = 0, int max_ctas = 0,
-                        const PathJob *job = nullptr, int flag_value = 1);
-int log_prior_tc_min_ctas(int B, int F, int Tx);
-int log_prior_tc_flag_target(int F, int Tx);
+                        cudaStream_t stream);
+// lp_mas_fused.cu: one CTA per utterance, value tiles handed over in shared memory (F in {64,80,96}, Tx <= 256)
+bool lp_mas_fused_supported(const float *mu_x, const float *y, int B, int F, int Tx, int Ty);
+int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const int *t_y, int B, int F, int Tx, int Ty,
+                        float neg, void *path, int path_dtype, int *durations, int *frame_token, int *status,
+                        void *workspace, size_t workspace_bytes, cudaStream_t stream);
 bool log_prior_tc_supported(const float *mu_x, const float *y, const float *out, int B, int F, int Tx, int Ty);
 
 }  // namespace masb200
