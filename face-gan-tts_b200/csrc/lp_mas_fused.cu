@@ -136,7 +136,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     const int ntiles = (t_y + NT - 1) / NT;
     const int w_act = (t_x + 32 * R - 1) / (32 * R);          // active DP warps == M-tiles with valid rows
     unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XP);   // [ntiles][XP] transfer table
-    long long *dbg = P.dbg ? P.dbg + (size_t)b * 16 : nullptr;
+    long long *dbg = P.dbg ? P.dbg + (size_t)b * 32 : nullptr;   // diagnostics: phase stamps [0..15], wait cycles [16..31]
     if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
     // the prologue's mu_x staging reaches into the raw y buffers: y tiles (and everything behind them) start late
     const bool late_start = (size_t)F * P.Tx * 4 > FS::off_raw(NS);
@@ -159,6 +159,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(kFullMask, *tmem_slot, 0);
+    if (dbg && tid == 0) dbg[8] = clock64();
     // TMEM columns: A hi/lo of M-tile mt at (2*mt + lo) * F; D of (stage p, M-tile mt) behind them
     auto col_d = [](int p, int mt) { return (uint32_t)(2 * W * F + (p * W + mt) * 32); };
 
@@ -180,17 +181,22 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         __syncwarp();
         mbar_wait_warp(bar_aready, 0);
         const uint32_t idesc = umma_idesc_tf32_ts(128, NT);
+        long long w_split = 0, w_dempty = 0;
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
+            long long c0 = clock64();
             mbar_wait_warp(&bar_split[p], par);
+            w_split += clock64() - c0;
             // every split thread is done with raw buffer p: fetch tile g + 2 into it
             if (g + 2 < ntiles && elect_one()) {
                 mbar_arrive_expect_tx(&bar_raw[p], FS::kRaw);
                 tma_load_3d(raw + (size_t)p * FS::kRaw, &ymap, (g + 2) * NT, 0, b, &bar_raw[p]);
             }
             __syncwarp();
+            c0 = clock64();
             if (g >= 2) mbar_wait_warp(&bar_dempty[p], par ^ 1u);           // epilogue drained D stage p (tile g - 2)
+            w_dempty += clock64() - c0;
             tc_fence_after();
             const uint32_t bh = smem_u32(ophi) + (uint32_t)p * FS::kOp;
             const uint32_t bl = smem_u32(oplo) + (uint32_t)p * FS::kOp;
@@ -199,10 +205,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                 if (mt < w_act) {
                     const uint32_t dcol = tmem + col_d(p, mt);
                     const uint32_t ah = tmem + lp_col_a(F, mt, 0), al = tmem + lp_col_a(F, mt, 1);
-#pragma unroll
+                    // a compact loop (two K steps per iteration), not 6*KS unrolled instructions: the code of all
+                    // roles has to share the instruction cache with the latency-critical DP warps
+                    const uint64_t dh0 = umma_smem_desc_k_nosw(bh, 128u, kSbo);
+                    const uint64_t dl0 = umma_smem_desc_k_nosw(bl, 128u, kSbo);
+#pragma unroll 2
                     for (int ks = 0; ks < KS; ++ks) {
-                        const uint64_t dh = umma_smem_desc_k_nosw(bh + ks * 256u, 128u, kSbo);
-                        const uint64_t dl = umma_smem_desc_k_nosw(bl + ks * 256u, 128u, kSbo);
+                        const uint64_t dh = dh0 + (uint64_t)(ks * 16);          // + ks * 256 bytes (address field, >> 4)
+                        const uint64_t dl = dl0 + (uint64_t)(ks * 16);
                         umma_tf32_ts_elect(dcol, ah + 8u * ks, dh, idesc, ks > 0 ? 1u : 0u);     // hi * hi
                         umma_tf32_ts_elect(dcol, ah + 8u * ks, dl, idesc, 1u);                    // hi * lo
                         umma_tf32_ts_elect(dcol, al + 8u * ks, dh, idesc, 1u);                    // lo * hi
@@ -213,6 +223,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             umma_commit_elect(&bar_bfree[p]);                      // operand buffer p may be refilled -> split warps
             __syncwarp();
         }
+        if (dbg && lane == 0) { dbg[16] = w_split; dbg[17] = w_dempty; }
     } else if (warp == kWarpSplit || warp == kWarpSplit + 1) {
         // ======================= operand split: raw [F][32] -> hi/lo K-major core matrices, ysq =======================
         // thread = (frame n = lane, mel-bin chunks kc = sw, sw + 2, ...): 4 conflict-free LDS.32 down a column of the raw
@@ -221,26 +232,40 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         if (late_start) mbar_wait(bar_aready, 0);
         const int n = lane;
         const uint32_t row_off = (uint32_t)(n >> 3) * kSbo + (uint32_t)(n & 7) * 16u;
+        long long w_bfree = 0, w_raw = 0;
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
+            long long c0 = clock64();
             if (g >= 2) mbar_wait(&bar_bfree[p], par ^ 1u);        // MMA(g - 2) has read operand buffer p
+            long long c1 = clock64();
             mbar_wait(&bar_raw[p], par);
+            w_bfree += c1 - c0; w_raw += clock64() - c1;
             const float *rw = reinterpret_cast<const float *>(raw + (size_t)p * FS::kRaw);
             unsigned char *hb = ophi + (size_t)p * FS::kOp, *lb = oplo + (size_t)p * FS::kOp;
+            // two halves of KS/2 chunks; in each all loads go first (the compiler cannot move shared-memory loads
+            // above the operand stores itself)
+            constexpr int KH = KS / 2;
             float q = 0.f;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int kc0 = sw + 2 * KH * half;
+                float v[KH][4];
 #pragma unroll
-            for (int kc = sw; kc < 2 * KS; kc += 2) {
-                float v[4];
+                for (int i = 0; i < KH; ++i)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = rw[(4 * kc + k) * NT + n];
-                uint4 h, l;
-                tf32_split(v[0], h.x, l.x); tf32_split(v[1], h.y, l.y);
-                tf32_split(v[2], h.z, l.z); tf32_split(v[3], h.w, l.w);
-                *reinterpret_cast<uint4 *>(hb + row_off + (uint32_t)kc * 128u) = h;
-                *reinterpret_cast<uint4 *>(lb + row_off + (uint32_t)kc * 128u) = l;
+                    for (int k = 0; k < 4; ++k) v[i][k] = rw[(4 * (kc0 + 2 * i) + k) * NT + n];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) q = fmaf(-0.5f * v[k], v[k], q);
+                for (int i = 0; i < KH; ++i) {
+                    const uint32_t kc = (uint32_t)(kc0 + 2 * i);
+                    uint4 h, l;
+                    tf32_split(v[i][0], h.x, l.x); tf32_split(v[i][1], h.y, l.y);
+                    tf32_split(v[i][2], h.z, l.z); tf32_split(v[i][3], h.w, l.w);
+                    *reinterpret_cast<uint4 *>(hb + row_off + kc * 128u) = h;
+                    *reinterpret_cast<uint4 *>(lb + row_off + kc * 128u) = l;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) q = fmaf(-0.5f * v[i][k], v[i][k], q);
+                }
             }
             float *pd = part + p * 64;
             pd[sw * 32 + n] = q;
@@ -249,12 +274,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             if (sw == 0) ysq[(g & (kYsqRing - 1)) * 32 + n] = pd[n] + pd[32 + n];
             mbar_arrive(&bar_split[p]);            // also: raw buffer p may be refilled
         }
+        if (dbg && sw == 0 && lane == 0) { dbg[18] = w_bfree; dbg[19] = w_raw; }
     } else if (warp < 4) {
         // ======================= epilogue warps: TMEM lane quadrant = warp =======================
         const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
         float musq[W];
         // ---- prologue: mu_x rows -> exact tf32 hi/lo -> TMEM (A operand for the whole CTA), musq
         mbar_wait(bar_mu, 0);
+        if (dbg && tid == 0) dbg[9] = clock64();
 #pragma unroll
         for (int mt = 0; mt < W; ++mt) {
             musq[mt] = 0.f;
@@ -284,6 +311,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         // ---- per tile: D (TMEM) -> ((ysq + dot) + musq) + const -> ring slot of this lane's text row
         int stage = 0;
         uint32_t sphase = 0;                                       // parity of the ring stage's CURRENT use
+        long long w_dfull = 0, w_rempty = 0;
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
@@ -292,12 +320,16 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             for (int mt = 0; mt < W; ++mt) {
                 if (mt < w_act) {
                     uint32_t d[32];
+                    long long c0 = clock64();
                     mbar_wait(&bar_dfull[p * 2 + mt], par);
+                    w_dfull += clock64() - c0;
                     tc_fence_after();
                     tmem_ld32(tmem + lane_base + col_d(p, mt), d);
                     tmem_wait_ld();
                     if (mt == w_act - 1) { tc_fence_before(); mbar_arrive(&bar_dempty[p]); }
+                    c0 = clock64();
                     if (g >= NS) mbar_wait(&ring_empty[stage * 2 + mt], sphase ^ 1u);     // DP warp mt released the stage
+                    w_rempty += clock64() - c0;
                     float *rowp = ring + (size_t)stage * kTileFloats + (size_t)(warp * (32 * W) + 32 * mt + lane) * kTilePitch;
                     const float ms = musq[mt];
 #pragma unroll
@@ -315,6 +347,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             }
             if (++stage == NS) { stage = 0; sphase ^= 1u; }
         }
+        if (dbg && tid == 0) { dbg[20] = w_dfull; dbg[21] = w_rempty; }
     } else if (warp == kWarpHelpA || warp == kWarpHelpB) {
         // ======================= backtrack helpers: transfer tables behind the LAST active DP warp =======================
         const int *flag_last = hprog + (w_act - 1);
@@ -358,6 +391,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         // staging that aliases the halo area -- only now may the halo rows be initialised
         mbar_wait_warp(&ring_full[w], 0);
         bool tile_ready = true;
+        long long w_full = 0, w_flag = 0, w_body = 0;
         if (w == 0) {
             hconst[lane] = P.neg;                                // the row above text position 0 (core.pyx:26-27)
             __syncwarp();
@@ -365,8 +399,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         }
         for (int j = 0; j < ntiles; ++j) {
             const int t0 = j * NT;
+            const long long c0 = clock64();
             if (!tile_ready) mbar_wait_warp(&ring_full[stage * 2 + w], phase);
+            const long long c1 = clock64();
             if (known < j + 1) known = flag_wait_ge_warp(flag_in, j + 1);
+            w_full += c1 - c0; w_flag += clock64() - c1;
             const int next_stage = (stage + 1 == NS) ? 0 : stage + 1;
             const uint32_t next_phase = (stage + 1 == NS) ? (phase ^ 1) : phase;
             const int next_hs = (hs + 1 == HS) ? 0 : hs + 1;
@@ -377,8 +414,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             const uint32_t hout_addr = hout_base + hs * hout_step;
             const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
             const int dl0 = lane_cta - t0 / R;
+            const long long cb0 = clock64();
             if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+            w_body += clock64() - cb0;
 
             // direction words of this tile, walk-ready (see mas_forward_kernel)
             if (diag) {
@@ -402,6 +441,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             phase = next_phase;
             hs = next_hs;
         }
+        if (dbg && lane == 0) { dbg[22 + 2 * w] = w_full; dbg[23 + 2 * w] = w_flag; dbg[26 + w] = w_body; }
         if (dbg && lane == 0 && w == w_act - 1) dbg[4] = clock64();
     }
     tc_fence_before();

@@ -149,34 +149,36 @@ __device__ __forceinline__ float f4_get(const float4 &v) {
     return I == 0 ? v.x : I == 1 ? v.y : I == 2 ? v.z : v.w;
 }
 
-// The lane's R rows of frame group G (frames 4G..4G+3 of the tile): one LDS.128 per row.
+// The lane's R rows of frame group g (frames 4g..4g+3 of the tile, g a RUNTIME value): one LDS.128 per row.
 //   lane_tile = &stage[lane_cta * kTilePitch]; chunk c of a row sits at position c ^ (lane & 7).
-template <int R, int XP, int G>
-__device__ __forceinline__ void load_group(float4 (&v)[R], const float *lane_tile, int lane7) {
+template <int R, int XP>
+__device__ __forceinline__ void load_group(float4 (&v)[R], const float *lane_tile, int lane7, int g) {
     constexpr int kRowStride = (XP / R) * kTilePitch;      // floats between the lane's consecutive rows
-    const int o = (G ^ lane7) << 2;
+    const int o = (g ^ lane7) << 2;
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const float4 *>(lane_tile + r * kRowStride + o);
 }
 
-// One frame (FRAME = position inside the tile) of the lane's R rows.
+// One frame of the lane's R rows.  K = position of the frame inside its 8-frame block (compile time): the
+// direction bit goes to bit 24 + K of the accumulator (the block loop shifts the word right by 8 per block, so
+// after four blocks bit k of the word is frame k of the tile), the halo goes to hout_addr + 4*K.
 //   q[r]    running previous-column Q of the lane's rows, updated in place bottom-up
 //   up      Q of the row above the lane's first row at the previous frame
 //   hq      Q of the row above the WARP at this frame (what lane 0 takes instead of a shuffle)
-//   dl0     DIAG only: lane_global - t0/R; the lane owns the diagonal cell of this frame, in row
-//           FRAME % R, exactly when dl0 == FRAME / R      (R | 32 | t0)
-template <int R, int FRAME, bool DIAG>
+//   dlb     DIAG only: lane_global - (first frame of the block) / R; the lane owns the diagonal cell of this
+//           frame, in row K % R, exactly when dlb == K / R      (R | 8 | first frame of the block)
+template <int R, int K, bool DIAG>
 __device__ __forceinline__ void dp_frame(float (&q)[R], uint32_t (&acc)[R], float &up, const float (&v)[R], float hq,
-                                         uint32_t lane0_mask, int dl0, float neg, uint32_t hout_addr) {
+                                         uint32_t lane0_mask, int dlb, float neg, uint32_t hout_addr) {
     float up_next = up;
 #pragma unroll
     for (int r = R - 1; r >= 0; --r) {
         float v_cur = q[r];
-        if (DIAG && r == FRAME % R) v_cur = (dl0 == FRAME / R) ? neg : v_cur;      // x == y (core.pyx:19-20)
+        if (DIAG && r == K % R) v_cur = (dlb == K / R) ? neg : v_cur;      // x == y (core.pyx:19-20)
         const float v_prev = (r == 0) ? up : q[r - 1];
-        q[r] = mas_cell<FRAME>(v_cur, v_prev, v[r], acc[r]);
+        q[r] = mas_cell<24 + K>(v_cur, v_prev, v[r], acc[r]);
         if (r == R - 1) {
-            sts_f32(hout_addr + 4u * FRAME, q[R - 1]);
+            sts_f32(hout_addr + 4u * K, q[R - 1]);
             const float s = __shfl_up_sync(kFullMask, q[R - 1], 1);
             up_next = bitselect(lane0_mask, hq, s);
         }
@@ -184,50 +186,53 @@ __device__ __forceinline__ void dp_frame(float (&q)[R], uint32_t (&acc)[R], floa
     up = up_next;
 }
 
-template <int R, int G, bool DIAG>
+// four frames (group H = 0 / 1 of an 8-frame block)
+template <int R, int H, bool DIAG>
 __device__ __forceinline__ void dp_group(float (&q)[R], uint32_t (&acc)[R], float &up, const float4 (&v4)[R],
-                                         const float4 &h4, uint32_t lane0_mask, int dl0, float neg,
+                                         const float4 &h4, uint32_t lane0_mask, int dlb, float neg,
                                          uint32_t hout_addr) {
     float v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].x;
-    dp_frame<R, 4 * G + 0, DIAG>(q, acc, up, v, h4.x, lane0_mask, dl0, neg, hout_addr);
+    dp_frame<R, 4 * H + 0, DIAG>(q, acc, up, v, h4.x, lane0_mask, dlb, neg, hout_addr);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].y;
-    dp_frame<R, 4 * G + 1, DIAG>(q, acc, up, v, h4.y, lane0_mask, dl0, neg, hout_addr);
+    dp_frame<R, 4 * H + 1, DIAG>(q, acc, up, v, h4.y, lane0_mask, dlb, neg, hout_addr);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].z;
-    dp_frame<R, 4 * G + 2, DIAG>(q, acc, up, v, h4.z, lane0_mask, dl0, neg, hout_addr);
+    dp_frame<R, 4 * H + 2, DIAG>(q, acc, up, v, h4.z, lane0_mask, dlb, neg, hout_addr);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].w;
-    dp_frame<R, 4 * G + 3, DIAG>(q, acc, up, v, h4.w, lane0_mask, dl0, neg, hout_addr);
+    dp_frame<R, 4 * H + 3, DIAG>(q, acc, up, v, h4.w, lane0_mask, dlb, neg, hout_addr);
 }
 
-// A whole 32-frame tile as one basic block; value and halo groups are register double-buffered.
+// A whole 32-frame tile: a loop of four 8-frame blocks (value and halo groups register double-buffered across the
+// loop).  The block body is ~2.7 KB of code and stays in the instruction cache of the scheduler partition; the
+// fully unrolled tile (11 KB per variant, beside the other roles' loops) did not -- the DP warps ran at 50-67
+// cycles/frame instead of the ~30 the instruction stream costs, varying from SM pair to SM pair.
 //   hin   32 floats in shared memory: Q of the row above the warp at the tile's frames
+//   acc   must be zero on entry; on exit bit k of acc[r] is the direction bit of frame k
 template <int R, int XP, bool DIAG>
 __device__ __forceinline__ void dp_tile(float (&q)[R], uint32_t (&acc)[R], float &up, const float *lane_tile,
                                         const float *hin, int lane7, uint32_t lane0_mask, int dl0, float neg,
                                         uint32_t hout_addr) {
+    static_assert(8 % R == 0, "rows per lane must divide the 8-frame block");
     float4 va[R], vb[R];
     float4 ha, hb;
     const float4 *h4 = reinterpret_cast<const float4 *>(hin);
-    load_group<R, XP, 0>(va, lane_tile, lane7); ha = h4[0];
-    load_group<R, XP, 1>(vb, lane_tile, lane7); hb = h4[1];
-    dp_group<R, 0, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
-    load_group<R, XP, 2>(va, lane_tile, lane7); ha = h4[2];
-    dp_group<R, 1, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
-    load_group<R, XP, 3>(vb, lane_tile, lane7); hb = h4[3];
-    dp_group<R, 2, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
-    load_group<R, XP, 4>(va, lane_tile, lane7); ha = h4[4];
-    dp_group<R, 3, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
-    load_group<R, XP, 5>(vb, lane_tile, lane7); hb = h4[5];
-    dp_group<R, 4, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
-    load_group<R, XP, 6>(va, lane_tile, lane7); ha = h4[6];
-    dp_group<R, 5, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
-    load_group<R, XP, 7>(vb, lane_tile, lane7); hb = h4[7];
-    dp_group<R, 6, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
-    dp_group<R, 7, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+    load_group<R, XP>(va, lane_tile, lane7, 0); ha = h4[0];
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        load_group<R, XP>(vb, lane_tile, lane7, 2 * i + 1); hb = h4[2 * i + 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] >>= 8;
+        dp_group<R, 0, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+        // next block's first group; the last block re-reads group 0 (no branch in the body)
+        load_group<R, XP>(va, lane_tile, lane7, (2 * i + 2) & 7); ha = h4[(2 * i + 2) & 7];
+        dp_group<R, 1, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+        dl0 -= 8 / R;
+        hout_addr += 32u;
+    }
 }
 
 template <int R>

@@ -101,13 +101,14 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                  : "memory");
 }
 
-// fp32 -> exact tf32 pair: hi = x rounded to tf32 (10 mantissa bits), lo = (x - hi) rounded to tf32
-// (x - hi is exact in fp32).  hi + lo carries ~22 mantissa bits of x; both are exactly representable
-// in tf32, so the tensor core's own input rounding never acts.
+// fp32 -> exact tf32 pair: hi = x rounded to tf32 (10 mantissa bits, to nearest, ties away from zero: what
+// cvt.rna.tf32.f32 computes for finite x, as two integer-pipe instructions instead of the four ptxas emits for
+// the cvt), lo = (x - hi) truncated to tf32 (x - hi is exact in fp32).  hi + lo carries >= 21 mantissa bits of x;
+// both are exactly representable in tf32, so the tensor core's own input handling never acts.
 __device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     const float rem = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
+    lo = __float_as_uint(rem) & 0xffffe000u;
 }
 
 }  // namespace masb200

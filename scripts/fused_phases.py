@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Diagnostics: per-CTA clock64 phase stamps of the fused log-prior + MAS kernel.
+dbg: [0] start, [1] A parked in TMEM (prologue done), [2] first value tile in the ring (DP starts), [4] last DP warp
+done, [3] all roles joined, [5] backtrack done, [6] end, [12]/[13] globaltimer at start / end."""
+import os, sys
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "face-gan-tts_b200"))
+import torch
+import face_gan_tts_b200 as fgt
+from face_gan_tts_b200 import synthetic, _lib
+
+def run(B, F, Tx, Ty, full=False):
+    mu, y, tx, ty = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=1234)
+    if full:
+        tx[:] = Tx; ty[:] = Ty
+    mu, y, tx, ty = mu.cuda(), y.cuda(), tx.cuda().int(), ty.cuda().int()
+    plan = fgt.AlignmentPlan(B, F, Tx, Ty, device="cuda:0", dense_path=False)
+    for _ in range(3):
+        plan(mu, y, tx, ty)
+    dbg = torch.zeros((B, 32), dtype=torch.int64, device="cuda")
+    p = dbg.data_ptr()
+    lo, hi = p & 0xFFFFFFFF, p >> 32
+    _lib.set_option("mas_debug_ptr_lo", lo - (1 << 32) if lo >= (1 << 31) else lo)
+    _lib.set_option("mas_debug_ptr_hi", hi)
+    plan(mu, y, tx, ty)
+    torch.cuda.synchronize()
+    _lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0)
+    d = dbg.cpu()
+    print(f"--- fused B={B} F={F} Tx={Tx} Ty={Ty} full={full}")
+    print("  b  t_x   t_y | (setup mu_load park_A) prologue first_tile   dp_total  cyc/frame |  join backtrack outputs | total cyc   wall us")
+    t0 = int(d[:, 12].min())
+    for b in list(range(min(B, 8))) + ([B - 1] if B > 8 else []):
+        s = d[b].tolist()
+        txb, tyb = s[7] >> 32, s[7] & 0xFFFFFFFF
+        print(f"{b:3d} {txb:4d} {tyb:5d} | ({s[8]-s[0]:5d} {s[9]-s[8]:5d} {s[1]-s[9]:5d}) {s[1]-s[0]:8d} {s[2]-s[0]:10d} {s[4]-s[2]:10d} {(s[4]-s[2])/max(tyb,1):10.1f} | "
+              f"{s[3]-s[4]:5d} {s[5]-s[3]:9d} {s[6]-s[5]:7d} | {s[6]-s[0]:9d} {(s[13]-s[12])/1e3:8.1f}  (start +{(s[12]-t0)/1e3:.1f} us)")
+    print("  wait cycles per frame:  mma<-split mma<-dempty | split<-bfree split<-raw | epi<-dfull epi<-ring_empty | dp0<-ring_full dp0<-flag dp1<-ring_full dp1<-flag | dp0 body dp1 body")
+    for b in list(range(min(B, 8))):
+        s = d[b].tolist(); tyb = max(s[7] & 0xFFFFFFFF, 1)
+        print(f"{b:3d} " + " ".join(f"{s[k]/tyb:9.1f}" for k in range(16, 28)))
+    print(f"  kernel span (globaltimer): {(int(d[:,13].max())-t0)/1e3:.1f} us")
+
+if __name__ == "__main__":
+    run(32, 80, 190, 1000)
+    run(32, 80, 190, 1000, full=True)
+    run(8, 80, 100, 400)
+    run(296, 80, 190, 1000)
