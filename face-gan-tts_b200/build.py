@@ -38,6 +38,9 @@ FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
+# diagnostics build: in-loop wait / body cycle counters of the fused kernel (scripts/fused_phases.py)
+if os.environ.get("MASB200_PROF"):
+    FLAGS.append("-DMASB200_FUSED_PROF=1")
 
 
 def _digest():

@@ -135,10 +135,12 @@ log_prior_tc_kernel(const LpTcParams P, const __grid_constant__ CUtensorMap ymap
                             const float4 yq = *reinterpret_cast<const float4 *>(S.ysq + p * 64 + 32 * h + 4 * c);
                             const uint32_t *r = (mt == 0) ? &d0[h][4 * c] : &d1[h][4 * c];
                             float4 o;
-                            o.x = ((yq.x + __uint_as_float(r[0])) + musq[mt]) + P.cst;
-                            o.y = ((yq.y + __uint_as_float(r[1])) + musq[mt]) + P.cst;
-                            o.z = ((yq.z + __uint_as_float(r[2])) + musq[mt]) + P.cst;
-                            o.w = ((yq.w + __uint_as_float(r[3])) + musq[mt]) + P.cst;
+                            // (ysq + dot) + (musq + const): the association the fused kernel uses (lp_mas_fused.cu)
+                            const float ms = musq[mt] + P.cst;
+                            o.x = (yq.x + __uint_as_float(r[0])) + ms;
+                            o.y = (yq.y + __uint_as_float(r[1])) + ms;
+                            o.z = (yq.z + __uint_as_float(r[2])) + ms;
+                            o.w = (yq.w + __uint_as_float(r[3])) + ms;
                             *reinterpret_cast<float4 *>(box + ((c ^ (tid & 7)) << 4)) = o;
                         }
                     }

@@ -71,12 +71,36 @@ struct FusedSmem {
     __host__ __device__ static constexpr size_t off_lo(int ns) { return off_hi(ns) + 2 * kOp; }
     __host__ __device__ static constexpr size_t off_part(int ns) { return off_lo(ns) + 2 * kOp; }             // [2][2][32] f32
     __host__ __device__ static constexpr size_t off_ysq(int ns) { return off_part(ns) + 2 * 2 * 32 * 4; }     // [8][32] f32
-    __host__ __device__ static constexpr size_t off_bars(int ns) { return off_ysq(ns) + kYsqRing * 32 * 4; }  // 16 + 4*ns mbarriers
+    __host__ __device__ static constexpr size_t off_bars(int ns) { return off_ysq(ns) + kYsqRing * 32 * 4; }  // 16 + 2*ns mbarriers (room for 4*ns)
     __host__ __device__ static constexpr size_t off_flags(int ns) { return off_bars(ns) + 8 * (size_t)(16 + 4 * ns); }
-    __host__ __device__ static constexpr size_t off_bits(int ns) { return ((off_flags(ns) + 64 + 127) / 128) * 128; }
+    __host__ __device__ static constexpr size_t off_bits(int ns) { return ((off_flags(ns) + 128 + 127) / 128) * 128; }
     // direction words (4 B) + transfer table (1 B) per row and tile
     __host__ __device__ static constexpr size_t total(int ns, int ntiles) { return off_bits(ns) + (size_t)5 * ntiles * XP; }
 };
+
+// in-loop wait / body cycle accumulators (scripts/fused_phases.py); off in production builds: the clock reads sit in
+// the latency-critical loops
+#ifndef MASB200_FUSED_PROF
+#define MASB200_FUSED_PROF 0
+#endif
+#if MASB200_FUSED_PROF
+#define PROF_DECL(...) long long __VA_ARGS__
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define PROF_DECL(...)
+#define PROF_T(var)
+#define PROF_ADD(acc, t0)
+#endif
+
+// {x0, x1} = {a0, a1} + {b0, b1}: one packed fp32x2 add (two RN adds, identical results to two add.rn.f32)
+__device__ __forceinline__ void add_f32x2(float &x0, float &x1, float a0, float a1, float b0, float b1) {
+    uint64_t a, b2, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+}
 
 template <int KS, int W>
 __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -102,15 +126,17 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     float *part = reinterpret_cast<float *>(smem_raw + FS::off_part(NS));
     float *ysq = reinterpret_cast<float *>(smem_raw + FS::off_ysq(NS));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + FS::off_bars(NS));
-    uint64_t *bar_mu = bars, *bar_aready = bars + 1, *bar_raw = bars + 2, *bar_split = bars + 4, *bar_bfree = bars + 6;
+    uint64_t *bar_aready = bars /*[M-tile]*/, *bar_raw = bars + 2, *bar_split = bars + 4, *bar_bfree = bars + 6;
     uint64_t *bar_dfull = bars + 8;              // [D stage][M-tile]
     uint64_t *bar_dempty = bars + 12;            // [D stage]
-    uint64_t *ring_full = bars + 16;             // [ring stage][M-tile]
-    uint64_t *ring_empty = ring_full + 2 * NS;   // [ring stage][M-tile]
-    int *hprog = reinterpret_cast<int *>(smem_raw + FS::off_flags(NS));                   // [W+2] progress flags
+    uint64_t *ring_empty = bars + 16;            // [ring stage][M-tile]
+    int *hprog = reinterpret_cast<int *>(smem_raw + FS::off_flags(NS));                   // [W+2] DP progress flags
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hprog + 8);
+    int *eprog = hprog + 12;                                                              // [W][4] epilogue progress flags
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem_raw + FS::off_bits(NS));
-    float *mu_s = reinterpret_cast<float *>(smem_raw);                                    // prologue staging [F][Tx]
+    // prologue staging of mu_x, transposed for the TMEM lane order: element (f, x) with x = 128*mt + 4*l + q at
+    //   ((f*W + mt)*4 + q)*32 + (l ^ 8q)      -- coalesced global reads land conflict-free, and so do the readers
+    float *mu_s = reinterpret_cast<float *>(smem_raw);
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -139,22 +165,55 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     long long *dbg = P.dbg ? P.dbg + (size_t)b * 32 : nullptr;   // diagnostics: phase stamps [0..15], wait cycles [16..31]
     if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
     // the prologue's mu_x staging reaches into the raw y buffers: y tiles (and everything behind them) start late
-    const bool late_start = (size_t)F * P.Tx * 4 > FS::off_raw(NS);
+    const bool late_start = (size_t)F * W * 128 * 4 > FS::off_raw(NS);
+
+    // ---- mu_x block of this utterance: coalesced global loads issued first, consumed after the set-up below.
+    // One warp per mel-bin row f (f = warp, warp + 15, ...), lane + 32j the text position: no index arithmetic per load.
+    constexpr int kMuRows = (F + kFusedWarps - 1) / kFusedWarps;
+    constexpr int kMuCols = 4 * W;                            // 32-position column groups of a row
+    float mu_reg[kMuRows][kMuCols];
+    {
+        const float *mu_b = FP.mu + (size_t)b * F * P.Tx + lane;
+#pragma unroll
+        for (int k = 0; k < kMuRows; ++k) {
+            const int f = warp + kFusedWarps * k;
+            const float *rp = mu_b + (size_t)f * P.Tx;
+#pragma unroll
+            for (int j = 0; j < kMuCols; ++j)
+                mu_reg[k][j] = (f < F && lane + 32 * j < t_x) ? __ldg(rp + 32 * j) : 0.f;
+        }
+    }
 
     if (tid == 0) {
-        mbar_init(bar_mu, 1);
-        mbar_init(bar_aready, 128);
+        mbar_init(&bar_aready[0], 12 * 32); mbar_init(&bar_aready[1], 12 * 32);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_raw[i], 1); mbar_init(&bar_split[i], 64); mbar_init(&bar_bfree[i], 1); mbar_init(&bar_dempty[i], 128);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&bar_dfull[i], 1);
-        for (int i = 0; i < 2 * NS; ++i) { mbar_init(&ring_full[i], 128); mbar_init(&ring_empty[i], 1); }
+        for (int i = 0; i < 2 * NS; ++i) mbar_init(&ring_empty[i], 1);
         for (int i = 0; i < W; ++i) hprog[i] = 0;
-        hprog[W] = 0x7fffffff;                               // the flag a warp without predecessor polls
+        hprog[W] = 0x7fffffff;                               // the flag a lane without anything to wait for polls
         hprog[W + 1] = 0;
+        for (int i = 0; i < 4 * W; ++i) eprog[i] = 0;
         mbar_fence_init();
     }
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
+    {
+        // x = 32j + lane = 128*mt + 4*l + q with mt = j >> 2, l = 8*(j & 3) + (lane >> 2), q = lane & 3:
+        //   position ((f*W + mt)*4 + q)*32 + (l ^ 8q) = f*W*128 + mt*128 + [q*32 + (lane >> 2) + ((8*(j & 3)) ^ 8q)]
+        const int q = lane & 3;
+        int e[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[c] = q * 32 + (lane >> 2) + ((8 * c) ^ (8 * q));
+#pragma unroll
+        for (int k = 0; k < kMuRows; ++k) {
+            const int f = warp + kFusedWarps * k;
+            if (f < F) {
+#pragma unroll
+                for (int j = 0; j < kMuCols; ++j) mu_s[f * W * 128 + (j >> 2) * 128 + e[j & 3]] = mu_reg[k][j];
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,15 +222,8 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     // TMEM columns: A hi/lo of M-tile mt at (2*mt + lo) * F; D of (stage p, M-tile mt) behind them
     auto col_d = [](int p, int mt) { return (uint32_t)(2 * W * F + (p * W + mt) * 32); };
 
-    if (warp == kWarpMma) {
-        // ======================= TMA loads + MMA issue (warp-uniform; one elected lane acts) =======================
-        const uint32_t mu_bytes = (uint32_t)F * (uint32_t)P.Tx * 4u;
-        if (elect_one()) {
-            mbar_arrive_expect_tx(bar_mu, mu_bytes);
-            tma_bulk_load_1d(mu_s, FP.mu + (size_t)b * F * P.Tx, mu_bytes, bar_mu);
-        }
-        __syncwarp();
-        if (late_start) mbar_wait_warp(bar_aready, 0);
+    if (warp == kWarpMma && !late_start) {
+        // the first two y tiles are on their way while the A operand is being parked
         if (elect_one()) {
             for (int q = 0; q < 2 && q < ntiles; ++q) {
                 mbar_arrive_expect_tx(&bar_raw[q], FS::kRaw);
@@ -179,30 +231,89 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             }
         }
         __syncwarp();
-        mbar_wait_warp(bar_aready, 0);
+    }
+
+    // ---- prologue (warps 0..11; warp % 4 = TMEM lane quadrant): mu_x rows -> exact tf32 hi/lo -> TMEM, the A operand
+    // for the whole CTA.  Warps 4..7 take the lower half of the mel bins, warps 8..11 the upper half; warps 0..3 (the
+    // epilogue warps) compute musq[x] = -0.5 sum_f mu^2 in the serial kernel's order.
+    float mc[W];                                              // epilogue warps: musq + const per M-tile
+    if (warp < 12) {
+        const int q = warp & 3, grp = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+#pragma unroll
+        for (int mt = 0; mt < W; ++mt) {
+            if (grp == 0) mc[mt] = 0.f;
+            if (mt < w_act) {
+                const float *src = mu_s + (mt * 4 + q) * 32 + (lane ^ (8 * q));       // + f * W * 128
+                if (grp == 0) {
+                    float sq = 0.f;
+#pragma unroll 8
+                    for (int f = 0; f < F; ++f) {
+                        const float v = src[f * W * 128];
+                        sq = fmaf(-0.5f * v, v, sq);
+                    }
+                    mc[mt] = sq + FP.cst;
+                } else {
+                    constexpr int KH = KS / 2;
+                    const int fbase = (grp - 1) * KH * 8;
+#pragma unroll 1
+                    for (int c = 0; c < KH; ++c) {
+                        const int f0 = fbase + 8 * c;
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) tf32_split(src[(f0 + k) * W * 128], hi[k], lo[k]);
+                        tmem_st8(tmem + lane_base + lp_col_a(F, mt, 0) + f0, hi);
+                        tmem_st8(tmem + lane_base + lp_col_a(F, mt, 1) + f0, lo);
+                    }
+                }
+            }
+            // M-tile by M-tile: the first tile's MMAs on M-tile 0 start while M-tile 1 is still being parked
+            if (grp != 0) { tmem_wait_st(); tc_fence_before(); }
+            mbar_arrive(&bar_aready[mt]);
+        }
+    }
+    if (dbg && tid == 0) dbg[9] = clock64();
+
+    if (warp == kWarpMma) {
+        // ======================= TMA loads + MMA issue (warp-uniform; one elected lane acts) =======================
+        if (late_start) {
+            mbar_wait_warp(&bar_aready[W - 1], 0);
+            if (elect_one()) {
+                for (int q = 0; q < 2 && q < ntiles; ++q) {
+                    mbar_arrive_expect_tx(&bar_raw[q], FS::kRaw);
+                    tma_load_3d(raw + (size_t)q * FS::kRaw, &ymap, q * NT, 0, b, &bar_raw[q]);
+                }
+            }
+            __syncwarp();
+        }
         const uint32_t idesc = umma_idesc_tf32_ts(128, NT);
-        long long w_split = 0, w_dempty = 0;
+        PROF_DECL(w_split = 0, w_dempty = 0);
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
-            long long c0 = clock64();
+            PROF_T(c0);
             mbar_wait_warp(&bar_split[p], par);
-            w_split += clock64() - c0;
+            PROF_ADD(w_split, c0);
             // every split thread is done with raw buffer p: fetch tile g + 2 into it
             if (g + 2 < ntiles && elect_one()) {
                 mbar_arrive_expect_tx(&bar_raw[p], FS::kRaw);
                 tma_load_3d(raw + (size_t)p * FS::kRaw, &ymap, (g + 2) * NT, 0, b, &bar_raw[p]);
             }
             __syncwarp();
-            c0 = clock64();
+            PROF_T(c1);
             if (g >= 2) mbar_wait_warp(&bar_dempty[p], par ^ 1u);           // epilogue drained D stage p (tile g - 2)
-            w_dempty += clock64() - c0;
+            PROF_ADD(w_dempty, c1);
             tc_fence_after();
             const uint32_t bh = smem_u32(ophi) + (uint32_t)p * FS::kOp;
             const uint32_t bl = smem_u32(oplo) + (uint32_t)p * FS::kOp;
 #pragma unroll
             for (int mt = 0; mt < W; ++mt) {
                 if (mt < w_act) {
+                    if (g == 0) {                                   // A of this M-tile is parked
+                        mbar_wait_warp(&bar_aready[mt], 0);
+                        tc_fence_after();
+                        if (dbg && lane == 0 && mt == 0) dbg[1] = clock64();
+                    }
                     const uint32_t dcol = tmem + col_d(p, mt);
                     const uint32_t ah = tmem + lp_col_a(F, mt, 0), al = tmem + lp_col_a(F, mt, 1);
                     // a compact loop (two K steps per iteration), not 6*KS unrolled instructions: the code of all
@@ -223,24 +334,27 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             umma_commit_elect(&bar_bfree[p]);                      // operand buffer p may be refilled -> split warps
             __syncwarp();
         }
+#if MASB200_FUSED_PROF
         if (dbg && lane == 0) { dbg[16] = w_split; dbg[17] = w_dempty; }
+#endif
     } else if (warp == kWarpSplit || warp == kWarpSplit + 1) {
         // ======================= operand split: raw [F][32] -> hi/lo K-major core matrices, ysq =======================
         // thread = (frame n = lane, mel-bin chunks kc = sw, sw + 2, ...): 4 conflict-free LDS.32 down a column of the raw
         // tile, one STS.128 per operand into core matrix (n / 8, kc), row n % 8.
         const int sw = warp - kWarpSplit;
-        if (late_start) mbar_wait(bar_aready, 0);
+        if (late_start) mbar_wait(&bar_aready[W - 1], 0);
         const int n = lane;
         const uint32_t row_off = (uint32_t)(n >> 3) * kSbo + (uint32_t)(n & 7) * 16u;
-        long long w_bfree = 0, w_raw = 0;
+        PROF_DECL(w_bfree = 0, w_raw = 0);
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
-            long long c0 = clock64();
+            PROF_T(c0);
             if (g >= 2) mbar_wait(&bar_bfree[p], par ^ 1u);        // MMA(g - 2) has read operand buffer p
-            long long c1 = clock64();
+            PROF_ADD(w_bfree, c0);
+            PROF_T(c1);
             mbar_wait(&bar_raw[p], par);
-            w_bfree += c1 - c0; w_raw += clock64() - c1;
+            PROF_ADD(w_raw, c1);
             const float *rw = reinterpret_cast<const float *>(raw + (size_t)p * FS::kRaw);
             unsigned char *hb = ophi + (size_t)p * FS::kOp, *lb = oplo + (size_t)p * FS::kOp;
             // two halves of KS/2 chunks; in each all loads go first (the compiler cannot move shared-memory loads
@@ -274,44 +388,16 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             if (sw == 0) ysq[(g & (kYsqRing - 1)) * 32 + n] = pd[n] + pd[32 + n];
             mbar_arrive(&bar_split[p]);            // also: raw buffer p may be refilled
         }
+#if MASB200_FUSED_PROF
         if (dbg && sw == 0 && lane == 0) { dbg[18] = w_bfree; dbg[19] = w_raw; }
+#endif
     } else if (warp < 4) {
         // ======================= epilogue warps: TMEM lane quadrant = warp =======================
+        // per tile: D (TMEM) -> (ysq + dot) + (musq + const) -> ring slot of this lane's text row, as packed fp32x2 adds
         const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-        float musq[W];
-        // ---- prologue: mu_x rows -> exact tf32 hi/lo -> TMEM (A operand for the whole CTA), musq
-        mbar_wait(bar_mu, 0);
-        if (dbg && tid == 0) dbg[9] = clock64();
-#pragma unroll
-        for (int mt = 0; mt < W; ++mt) {
-            musq[mt] = 0.f;
-            if (mt < w_act) {
-                const int x = 128 * mt + 4 * lane + warp;
-                const bool xin = x < P.Tx;
-                float sq = 0.f;
-#pragma unroll
-                for (int f0 = 0; f0 < F; f0 += 8) {
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float v = xin ? mu_s[(f0 + k) * P.Tx + x] : 0.f;
-                        tf32_split(v, hi[k], lo[k]);
-                        sq = fmaf(-0.5f * v, v, sq);
-                    }
-                    tmem_st8(tmem + lane_base + lp_col_a(F, mt, 0) + f0, hi);
-                    tmem_st8(tmem + lane_base + lp_col_a(F, mt, 1) + f0, lo);
-                }
-                musq[mt] = sq;
-            }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_aready);
-        if (dbg && tid == 0) dbg[1] = clock64();
-        // ---- per tile: D (TMEM) -> ((ysq + dot) + musq) + const -> ring slot of this lane's text row
         int stage = 0;
         uint32_t sphase = 0;                                       // parity of the ring stage's CURRENT use
-        long long w_dfull = 0, w_rempty = 0;
+        PROF_DECL(w_dfull = 0, w_rempty = 0);
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
@@ -320,34 +406,37 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             for (int mt = 0; mt < W; ++mt) {
                 if (mt < w_act) {
                     uint32_t d[32];
-                    long long c0 = clock64();
+                    PROF_T(c0);
                     mbar_wait(&bar_dfull[p * 2 + mt], par);
-                    w_dfull += clock64() - c0;
+                    PROF_ADD(w_dfull, c0);
                     tc_fence_after();
                     tmem_ld32(tmem + lane_base + col_d(p, mt), d);
                     tmem_wait_ld();
                     if (mt == w_act - 1) { tc_fence_before(); mbar_arrive(&bar_dempty[p]); }
-                    c0 = clock64();
+                    PROF_T(c1);
                     if (g >= NS) mbar_wait(&ring_empty[stage * 2 + mt], sphase ^ 1u);     // DP warp mt released the stage
-                    w_rempty += clock64() - c0;
+                    PROF_ADD(w_rempty, c1);
                     float *rowp = ring + (size_t)stage * kTileFloats + (size_t)(warp * (32 * W) + 32 * mt + lane) * kTilePitch;
-                    const float ms = musq[mt];
+                    const float ms = mc[mt];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float4 yq = *reinterpret_cast<const float4 *>(yq_row + 4 * c);
                         float4 o;
-                        o.x = ((yq.x + __uint_as_float(d[4 * c + 0])) + ms) + FP.cst;
-                        o.y = ((yq.y + __uint_as_float(d[4 * c + 1])) + ms) + FP.cst;
-                        o.z = ((yq.z + __uint_as_float(d[4 * c + 2])) + ms) + FP.cst;
-                        o.w = ((yq.w + __uint_as_float(d[4 * c + 3])) + ms) + FP.cst;
+                        add_f32x2(o.x, o.y, yq.x, yq.y, __uint_as_float(d[4 * c + 0]), __uint_as_float(d[4 * c + 1]));
+                        add_f32x2(o.z, o.w, yq.z, yq.w, __uint_as_float(d[4 * c + 2]), __uint_as_float(d[4 * c + 3]));
+                        add_f32x2(o.x, o.y, o.x, o.y, ms, ms);
+                        add_f32x2(o.z, o.w, o.z, o.w, ms, ms);
                         *reinterpret_cast<float4 *>(rowp + ((c ^ (lane & 7)) << 2)) = o;
                     }
-                    mbar_arrive(&ring_full[stage * 2 + mt]);
+                    __syncwarp();
+                    if (lane == 0) flag_release(&eprog[mt * 4 + warp], g + 1);      // this warp's rows of (tile g, M-tile mt) are in the ring
                 }
             }
             if (++stage == NS) { stage = 0; sphase ^= 1u; }
         }
+#if MASB200_FUSED_PROF
         if (dbg && tid == 0) { dbg[20] = w_dfull; dbg[21] = w_rempty; }
+#endif
     } else if (warp == kWarpHelpA || warp == kWarpHelpB) {
         // ======================= backtrack helpers: transfer tables behind the LAST active DP warp =======================
         const int *flag_last = hprog + (w_act - 1);
@@ -376,8 +465,12 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         float *hb_out = hbuf + (size_t)w * HS * NT;
         const uint32_t hout_base = (has_consumer && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * NT);
         const uint32_t hout_step = (has_consumer && lane == 31) ? NT * 4u : 0u;
-        const int *flag_in = (w > 0) ? hprog + (w - 1) : hprog + W;           // hprog[W] is pre-satisfied
         int *flag_out = hprog + w;
+        // what tile j needs, one word per lane: lanes 0..3 the four epilogue warps' progress on this warp's M-tile
+        // (>= j + 1: the tile is in the ring), lane 4 the progress of DP warp w - 1 (its halo row), the other lanes a
+        // word that is always satisfied.  ONE shared-memory load covers everything, and the load for tile j + 1 is
+        // issued before the body of tile j, so its latency never stalls the in-order warp.
+        const int *sync_word = (lane < 4) ? eprog + 4 * w + lane : ((lane == 4 && w > 0) ? hprog + (w - 1) : hprog + W);
 
         float q[R];
         uint32_t acc[R];
@@ -385,13 +478,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         for (int r = 0; r < R; ++r) { q[r] = P.neg; acc[r] = 0u; }
         // neighbour value for frame 0: only text position 0 has a defined one (core.pyx:24-25, y == 0)
         float up = (x0 == 0) ? 0.f : P.neg;
-        int known = 0, stage = 0, hs = 0;
-        uint32_t phase = 0;
+        int stage = 0, hs = 0;
+        PROF_DECL(w_full = 0, w_body = 0);
         // the first tile of this warp's M-tile is in the ring: the prologue is over, and with it every read of the mu_x
         // staging that aliases the halo area -- only now may the halo rows be initialised
-        mbar_wait_warp(&ring_full[w], 0);
-        bool tile_ready = true;
-        long long w_full = 0, w_flag = 0, w_body = 0;
+        flag_wait_ge_warp(sync_word, 1);
         if (w == 0) {
             hconst[lane] = P.neg;                                // the row above text position 0 (core.pyx:26-27)
             __syncwarp();
@@ -399,25 +490,19 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         }
         for (int j = 0; j < ntiles; ++j) {
             const int t0 = j * NT;
-            const long long c0 = clock64();
-            if (!tile_ready) mbar_wait_warp(&ring_full[stage * 2 + w], phase);
-            const long long c1 = clock64();
-            if (known < j + 1) known = flag_wait_ge_warp(flag_in, j + 1);
-            w_full += c1 - c0; w_flag += clock64() - c1;
+            const int sync_next = flag_acquire(sync_word);       // consumed after the body
             const int next_stage = (stage + 1 == NS) ? 0 : stage + 1;
-            const uint32_t next_phase = (stage + 1 == NS) ? (phase ^ 1) : phase;
             const int next_hs = (hs + 1 == HS) ? 0 : hs + 1;
-            tile_ready = (j + 1 < ntiles) && mbar_test_warp(&ring_full[next_stage * 2 + w], next_phase);
 
             const float *lane_tile = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
             const float *hin = hb_in + hs * hin_step;
             const uint32_t hout_addr = hout_base + hs * hout_step;
             const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
             const int dl0 = lane_cta - t0 / R;
-            const long long cb0 = clock64();
+            PROF_T(cb0);
             if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
-            w_body += clock64() - cb0;
+            PROF_ADD(w_body, cb0);
 
             // direction words of this tile, walk-ready (see mas_forward_kernel)
             if (diag) {
@@ -438,10 +523,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                 mbar_arrive(&ring_empty[stage * 2 + w]);
             }
             stage = next_stage;
-            phase = next_phase;
             hs = next_hs;
+            PROF_T(cw0);
+            if (j + 1 < ntiles && !__all_sync(kFullMask, sync_next >= j + 2)) flag_wait_ge_warp(sync_word, j + 2);
+            PROF_ADD(w_full, cw0);
         }
-        if (dbg && lane == 0) { dbg[22 + 2 * w] = w_full; dbg[23 + 2 * w] = w_flag; dbg[26 + w] = w_body; }
+#if MASB200_FUSED_PROF
+        if (dbg && lane == 0) { dbg[22 + 2 * w] = w_full; dbg[26 + w] = w_body; }
+#endif
         if (dbg && lane == 0 && w == w_act - 1) dbg[4] = clock64();
     }
     tc_fence_before();
@@ -452,10 +541,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     // ================================ backtrack + outputs (the ring is idle now) ================================
     int *tok = reinterpret_cast<int *>(ring);
     int *xin = tok + XP;
-    mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid);
+    mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg);
     if (dbg && tid == 0) dbg[5] = clock64();
     int *hd = xin + ((ntiles + 3) & ~3);
-    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid);
+    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg);
     write_path_any(P, b, start_b, dur_b, tid, kFusedThreads);
     if (dbg && tid == 0) {
         dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y;

@@ -2,7 +2,7 @@
 // (log_prior_tc.cu: epilogue -> HBM) and the fused kernel (lp_mas_fused.cu: epilogue -> MAS value ring).
 //
 // Replaces reference model/face_tts.py:165-171 (term-by-term mapping in log_prior_ffma.cu):
-//   log_prior[x,t] = ((ysq[t] + dot[x,t]) + musq[x]) + const,   dot = sum_f mu_x[f,x] * y[f,t]
+//   log_prior[x,t] = (ysq[t] + dot[x,t]) + (musq[x] + const),   dot = sum_f mu_x[f,x] * y[f,t]
 // The K = n_feats contraction runs as 3xTF32 (hi*hi + hi*lo + lo*hi over exact tf32 hi/lo pairs, fp32
 // accumulation in TMEM): ~22 mantissa bits per operand, fp32-class accuracy (3.8e-7 max relative error
 // measured), far inside the 1e-4 bar.  ysq / musq are fp32 FMAs on the CUDA cores.

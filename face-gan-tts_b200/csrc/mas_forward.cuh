@@ -460,7 +460,8 @@ __device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, i
 // token each tile is entered with, then one thread per tile emits the start frames tok[x] of its tokens.
 template <int XP, int NTHREADS, int G0, int G1>
 __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsigned char *nj_s, int *tok, int *xin,
-                                                   int jt_owed, int ntiles, int t_x, int t_y, int tid) {
+                                                   int jt_owed, int ntiles, int t_x, int t_y, int tid,
+                                                   long long *dbg = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     if constexpr (G0 < G1) {
         constexpr int nwarps = NTHREADS / 32;
@@ -476,6 +477,7 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
             x -= n;
         }
         tok[0] = 0;
+        if (dbg) dbg[10] = clock64();
     }
     __syncthreads();
     for (int jt = tid; jt < ntiles; jt += NTHREADS) {                     // one thread per tile: start frames
@@ -498,7 +500,7 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
 //   hd   scratch in shared memory: [(Ty + 3) & ~3] heads + [32] warp totals
 template <int NTHREADS>
 __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b, const int *tok, int *hd, int t_x, int t_y,
-                                                      int tid) {
+                                                      int tid, long long *dbg = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     int *start_b = P.start + (size_t)b * P.Tx;
     int *dur_b = P.dur + (size_t)b * P.Tx;
@@ -522,6 +524,7 @@ __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b,
             if (e > s) hd[s] = x;
         }
         __syncthreads();
+        if (dbg && tid == 0) dbg[11] = clock64();
         const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
         constexpr int nw = NTHREADS >> 5;
         int carry = -1;
