@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 
 #include "mas_host.h"
 
@@ -33,6 +34,8 @@ Opt g_opts[] = {
     {"upload_impl", {0}},            // 0/1 SM zero-copy pull kernel, 2 copy engine (one 2-D copy per utterance and tensor), 3 TMA bulk copies for y
     {"upload_l2_256b", {0}},         // 1: zero-copy loads carry the L2::256B fetch hint
     {"upload_ctas", {0}},            // CTAs of the zero-copy upload kernel (0 = one per SM)
+    {"fused_dump_ptr_lo", {0}},      // tests only: [B,Tx,Ty] float buffer receiving the fused kernel's value tiles (device pointer halves)
+    {"fused_dump_ptr_hi", {0}},
     {"fused_impl", {0}},             // 0 auto (fused kernel when the shape is covered), 1 force the serial form
 };
 }  // namespace
@@ -92,6 +95,23 @@ int mas_b200_set_option(const char *key, int value) {
 }
 
 int mas_b200_get_option(const char *key) { return key ? option(key) : INT_MIN; }
+
+int mas_b200_set_pointer_option(const char *key, void *ptr) {
+    if (!key) return MAS_B200_ERR_ARG;
+    const std::string lo = std::string(key) + "_lo", hi = std::string(key) + "_hi";
+    if (option(lo.c_str()) == INT_MIN && option(hi.c_str()) == INT_MIN) {
+        // INT_MIN is also a legal half of a pointer: look the keys up instead of trusting the value
+        bool found = false;
+        for (auto &o : g_opts) found = found || lo == o.key;
+        if (!found) return MAS_B200_ERR_ARG;
+    }
+    const unsigned long long v = reinterpret_cast<unsigned long long>(ptr);
+    for (auto &o : g_opts) {
+        if (lo == o.key) o.value.store((int)(unsigned)(v & 0xffffffffu), std::memory_order_relaxed);
+        if (hi == o.key) o.value.store((int)(unsigned)(v >> 32), std::memory_order_relaxed);
+    }
+    return MAS_B200_OK;
+}
 
 size_t mas_b200_workspace_bytes(int B, int Tx, int Ty) {
     if (B <= 0 || Tx <= 0 || Ty <= 0) return 0;

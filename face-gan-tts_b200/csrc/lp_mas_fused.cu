@@ -6,11 +6,14 @@
 // tcgen05.mma with A = mu_x parked in TENSOR MEMORY, lp_tc_frontend.cuh) produces the value matrix one 32-frame
 // tile at a time; its epilogue writes every tile STRAIGHT INTO THE SHARED-MEMORY RING the alignment search reads
 // (mas_forward.cuh: register-resident column, SHFL halo, 1 direction bit per cell in shared memory, per-token
-// backtrack).  Values and paths are bit-identical to the serial form (log_prior_tc_kernel -> HBM -> mas_forward_kernel):
-// same K order, same ((ysq + dot) + musq) + const association, same DP.
+// backtrack).  The y^2 / mu^2 / constant terms ride along in the contraction as one extra K step,
+//   A_extra[x] = (1, 1, mc_hi, mc_lo, 0, 0, 0, 0),  B_extra[t] = (ysq_hi, ysq_lo, 1, 1, 0, 0, 0, 0),   mc = musq[x] + const,
+// (exact tf32 pairs again), so the accumulator leaves TMEM as the finished log-prior value and the epilogue is a pure
+// TMEM -> shared-memory copy: it shares its scheduler partition with a DP warp and must stay out of its way.
+// The path is the bit-exact MAS of exactly these values (tests dump them through the fused_dump_ptr option).
 //
 // Warp roles (15 warps; warp % 4 = scheduler partition, the arbiter favours the higher warp id):
-//    0..3   epilogue: prologue (mu_x -> hi/lo -> TMEM), then per tile TMEM -> registers -> + ysq/musq/const -> ring
+//    0..3   epilogue: per tile TMEM -> registers -> ring (in the prologue: musq + const)
 //    6, 7   operand split: raw y tile [F][32] -> hi/lo K-major core matrices + ysq
 //    10     TMA loads (mu_x block, y tiles) + tcgen05.mma issue
 //    11, 14 backtrack helpers: per-tile transfer tables in the shadow of the DP
@@ -47,16 +50,16 @@ constexpr int kWarpMma = 10;
 constexpr int kWarpHelpA = 11;
 constexpr int kWarpDp = 12;                  // 12, 13
 constexpr int kWarpHelpB = 14;
-constexpr int kYsqRing = 8;                  // ysq ring entries (the split warps run at most ~4 tiles ahead of the epilogue)
 
 struct FusedParams {
     MasParams mas;       // t_x, t_y, B, Tx, Ty, neg, ring_stages, start, dur, frame_token, status, path, path_dtype, dbg
     const float *mu;     // [B,F,Tx]
     float cst;           // -0.5 * F * log(2 pi)
+    float *value_dump;   // tests only: [B,Tx,Ty], receives the value tiles the search consumed (null normally)
 };
 
 // Shared-memory carve-up (bytes from a 1024-aligned base):
-//   [ring: NS value tiles][halo rings][raw y: 2][hi: 2][lo: 2][ysq partials][ysq ring][mbarriers][flags][direction words + transfer tables]
+//   [ring: NS value tiles][halo rings][raw y: 2][hi: 2][lo: 2][ysq partials][mbarriers][flags][direction words + transfer tables]
 // The [F][Tx] staging of mu_x for the prologue aliases the front (ring, halo, possibly raw).
 template <int KS, int W>
 struct FusedSmem {
@@ -64,14 +67,14 @@ struct FusedSmem {
     static constexpr int XP = 32 * kFR * W;
     using M = MasSmem<kFR, W>;
     static constexpr uint32_t kRaw = (uint32_t)F * 32u * 4u;      // one raw y tile [F][32 frames]
-    static constexpr uint32_t kOp = (uint32_t)F * 32u * 4u;       // one hi (or lo) operand tile
+    static constexpr int FE = F + 8;                              // K extent of an operand tile: F mel bins + the extra K step
+    static constexpr uint32_t kOp = (uint32_t)FE * 32u * 4u;      // one hi (or lo) operand tile
     __host__ __device__ static constexpr size_t off_halo(int ns) { return M::ring_bytes(ns); }
     __host__ __device__ static constexpr size_t off_raw(int ns) { return off_halo(ns) + M::halo_bytes(ns); }
     __host__ __device__ static constexpr size_t off_hi(int ns) { return off_raw(ns) + 2 * kRaw; }
     __host__ __device__ static constexpr size_t off_lo(int ns) { return off_hi(ns) + 2 * kOp; }
     __host__ __device__ static constexpr size_t off_part(int ns) { return off_lo(ns) + 2 * kOp; }             // [2][2][32] f32
-    __host__ __device__ static constexpr size_t off_ysq(int ns) { return off_part(ns) + 2 * 2 * 32 * 4; }     // [8][32] f32
-    __host__ __device__ static constexpr size_t off_bars(int ns) { return off_ysq(ns) + kYsqRing * 32 * 4; }  // 16 + 2*ns mbarriers (room for 4*ns)
+    __host__ __device__ static constexpr size_t off_bars(int ns) { return off_part(ns) + 2 * 2 * 32 * 4; }    // 16 + 2*ns mbarriers (room for 4*ns)
     __host__ __device__ static constexpr size_t off_flags(int ns) { return off_bars(ns) + 8 * (size_t)(16 + 4 * ns); }
     __host__ __device__ static constexpr size_t off_bits(int ns) { return ((off_flags(ns) + 128 + 127) / 128) * 128; }
     // direction words (4 B) + transfer table (1 B) per row and tile
@@ -112,7 +115,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     constexpr int NT = kTileFrames;
     constexpr int kTileFloats = XP * kTilePitch;
     constexpr int kG = XP / 32, kGH = kG / 2;                 // row groups of a tile: [0,kGH) helper A, [kGH,kG) helper B
-    constexpr uint32_t kSbo = (uint32_t)F * 32u;              // 8 frames x F mel bins x 4 B per row group of an operand tile
+    constexpr uint32_t kSbo = (uint32_t)FS::FE * 32u;         // 8 frames x (F + 8) K values x 4 B per row group of an operand tile
     const MasParams &P = FP.mas;
     const int NS = P.ring_stages;
     const int HS = NS + 1;
@@ -124,9 +127,8 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     unsigned char *ophi = smem_raw + FS::off_hi(NS);
     unsigned char *oplo = smem_raw + FS::off_lo(NS);
     float *part = reinterpret_cast<float *>(smem_raw + FS::off_part(NS));
-    float *ysq = reinterpret_cast<float *>(smem_raw + FS::off_ysq(NS));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + FS::off_bars(NS));
-    uint64_t *bar_aready = bars /*[M-tile]*/, *bar_raw = bars + 2, *bar_split = bars + 4, *bar_bfree = bars + 6;
+    uint64_t *bar_aready = bars /*[M-tile]*/, *bar_xready = bars + 14 /*[M-tile]*/, *bar_raw = bars + 2, *bar_split = bars + 4, *bar_bfree = bars + 6;
     uint64_t *bar_dfull = bars + 8;              // [D stage][M-tile]
     uint64_t *bar_dempty = bars + 12;            // [D stage]
     uint64_t *ring_empty = bars + 16;            // [ring stage][M-tile]
@@ -185,7 +187,8 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     }
 
     if (tid == 0) {
-        mbar_init(&bar_aready[0], 12 * 32); mbar_init(&bar_aready[1], 12 * 32);
+        mbar_init(&bar_aready[0], 8 * 32); mbar_init(&bar_aready[1], 8 * 32);
+        mbar_init(&bar_xready[0], 4 * 32); mbar_init(&bar_xready[1], 4 * 32);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_raw[i], 1); mbar_init(&bar_split[i], 64); mbar_init(&bar_bfree[i], 1); mbar_init(&bar_dempty[i], 128);
         }
@@ -219,8 +222,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(kFullMask, *tmem_slot, 0);
     if (dbg && tid == 0) dbg[8] = clock64();
-    // TMEM columns: A hi/lo of M-tile mt at (2*mt + lo) * F; D of (stage p, M-tile mt) behind them
-    auto col_d = [](int p, int mt) { return (uint32_t)(2 * W * F + (p * W + mt) * 32); };
+    // TMEM columns: M-tile mt: A hi at mt*(2F+8), A lo at +F, the extra K step at +2F; D of (stage p, M-tile mt) behind them
+    auto col_a = [](int mt, int part) { return (uint32_t)(mt * (2 * F + 8) + part * F); };
+    auto col_d = [](int p, int mt) { return (uint32_t)(W * (2 * F + 8) + (p * W + mt) * 32); };
+    static_assert(W * (2 * F + 8) + 2 * W * 32 <= kLpTmemCols, "A (hi, lo, extra) + two D stages must fit the 512 TMEM columns");
 
     if (warp == kWarpMma && !late_start) {
         // the first two y tiles are on their way while the A operand is being parked
@@ -236,23 +241,29 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     // ---- prologue (warps 0..11; warp % 4 = TMEM lane quadrant): mu_x rows -> exact tf32 hi/lo -> TMEM, the A operand
     // for the whole CTA.  Warps 4..7 take the lower half of the mel bins, warps 8..11 the upper half; warps 0..3 (the
     // epilogue warps) compute musq[x] = -0.5 sum_f mu^2 in the serial kernel's order.
-    float mc[W];                                              // epilogue warps: musq + const per M-tile
     if (warp < 12) {
         const int q = warp & 3, grp = warp >> 2;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
 #pragma unroll
         for (int mt = 0; mt < W; ++mt) {
-            if (grp == 0) mc[mt] = 0.f;
             if (mt < w_act) {
                 const float *src = mu_s + (mt * 4 + q) * 32 + (lane ^ (8 * q));       // + f * W * 128
                 if (grp == 0) {
-                    float sq = 0.f;
-#pragma unroll 8
-                    for (int f = 0; f < F; ++f) {
-                        const float v = src[f * W * 128];
-                        sq = fmaf(-0.5f * v, v, sq);
+                    // musq = -0.5 sum_f mu^2 over four interleaved partial sums (a single chain of F dependent FMAs
+                    // was the longest thing in the prologue)
+                    float sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int f = 0; f < F; f += 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float v = src[(f + k) * W * 128];
+                            sq[k] = fmaf(-0.5f * v, v, sq[k]);
+                        }
                     }
-                    mc[mt] = sq + FP.cst;
+                    // the extra K step of this row: (1, 1, mc_hi, mc_lo, 0, 0, 0, 0),  mc = musq + const
+                    uint32_t ex[8] = {0x3f800000u, 0x3f800000u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    tf32_split(((sq[0] + sq[1]) + (sq[2] + sq[3])) + FP.cst, ex[2], ex[3]);
+                    tmem_st8(tmem + lane_base + col_a(mt, 2), ex);
                 } else {
                     constexpr int KH = KS / 2;
                     const int fbase = (grp - 1) * KH * 8;
@@ -262,14 +273,15 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) tf32_split(src[(f0 + k) * W * 128], hi[k], lo[k]);
-                        tmem_st8(tmem + lane_base + lp_col_a(F, mt, 0) + f0, hi);
-                        tmem_st8(tmem + lane_base + lp_col_a(F, mt, 1) + f0, lo);
+                        tmem_st8(tmem + lane_base + col_a(mt, 0) + f0, hi);
+                        tmem_st8(tmem + lane_base + col_a(mt, 1) + f0, lo);
                     }
                 }
             }
             // M-tile by M-tile: the first tile's MMAs on M-tile 0 start while M-tile 1 is still being parked
-            if (grp != 0) { tmem_wait_st(); tc_fence_before(); }
-            mbar_arrive(&bar_aready[mt]);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(grp == 0 ? &bar_xready[mt] : &bar_aready[mt]);
         }
     }
     if (dbg && tid == 0) dbg[9] = clock64();
@@ -278,6 +290,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         // ======================= TMA loads + MMA issue (warp-uniform; one elected lane acts) =======================
         if (late_start) {
             mbar_wait_warp(&bar_aready[W - 1], 0);
+            mbar_wait_warp(&bar_xready[W - 1], 0);
             if (elect_one()) {
                 for (int q = 0; q < 2 && q < ntiles; ++q) {
                     mbar_arrive_expect_tx(&bar_raw[q], FS::kRaw);
@@ -315,7 +328,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                         if (dbg && lane == 0 && mt == 0) dbg[1] = clock64();
                     }
                     const uint32_t dcol = tmem + col_d(p, mt);
-                    const uint32_t ah = tmem + lp_col_a(F, mt, 0), al = tmem + lp_col_a(F, mt, 1);
+                    const uint32_t ah = tmem + col_a(mt, 0), al = tmem + col_a(mt, 1);
                     // a compact loop (two K steps per iteration), not 6*KS unrolled instructions: the code of all
                     // roles has to share the instruction cache with the latency-critical DP warps
                     const uint64_t dh0 = umma_smem_desc_k_nosw(bh, 128u, kSbo);
@@ -328,6 +341,9 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                         umma_tf32_ts_elect(dcol, ah + 8u * ks, dl, idesc, 1u);                    // hi * lo
                         umma_tf32_ts_elect(dcol, al + 8u * ks, dh, idesc, 1u);                    // lo * hi
                     }
+                    // + ysq[t] + (musq[x] + const): the extra K step (operand chunks 2KS, 2KS + 1 of the hi tile)
+                    if (g == 0) { mbar_wait_warp(&bar_xready[mt], 0); tc_fence_after(); }
+                    umma_tf32_ts_elect(dcol, tmem + col_a(mt, 2), dh0 + (uint64_t)(KS * 16), idesc, 1u);
                     umma_commit_elect(&bar_dfull[p * 2 + mt]);     // D of (tile g, M-tile mt) complete -> epilogue warps
                 }
             }
@@ -338,11 +354,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         if (dbg && lane == 0) { dbg[16] = w_split; dbg[17] = w_dempty; }
 #endif
     } else if (warp == kWarpSplit || warp == kWarpSplit + 1) {
-        // ======================= operand split: raw [F][32] -> hi/lo K-major core matrices, ysq =======================
+        // ======================= operand split: raw [F][32] -> hi/lo K-major core matrices + the ysq K step =======================
         // thread = (frame n = lane, mel-bin chunks kc = sw, sw + 2, ...): 4 conflict-free LDS.32 down a column of the raw
         // tile, one STS.128 per operand into core matrix (n / 8, kc), row n % 8.
         const int sw = warp - kWarpSplit;
-        if (late_start) mbar_wait(&bar_aready[W - 1], 0);
+        if (late_start) { mbar_wait(&bar_aready[W - 1], 0); mbar_wait(&bar_xready[W - 1], 0); }
         const int n = lane;
         const uint32_t row_off = (uint32_t)(n >> 3) * kSbo + (uint32_t)(n & 7) * 16u;
         PROF_DECL(w_bfree = 0, w_raw = 0);
@@ -383,9 +399,16 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             }
             float *pd = part + p * 64;
             pd[sw * 32 + n] = q;
-            fence_proxy_async_smem();              // hi/lo stores -> visible to the tensor core's smem reads
             asm volatile("bar.sync 1, 64;" ::: "memory");
-            if (sw == 0) ysq[(g & (kYsqRing - 1)) * 32 + n] = pd[n] + pd[32 + n];
+            // the extra K step of frame n: (ysq_hi, ysq_lo, 1, 1 | 0, 0, 0, 0), ysq = -0.5 sum_f y^2
+            if (sw == 0) {
+                uint4 e = make_uint4(0u, 0u, 0x3f800000u, 0x3f800000u);
+                tf32_split(pd[n] + pd[32 + n], e.x, e.y);
+                *reinterpret_cast<uint4 *>(hb + row_off + (uint32_t)(2 * KS) * 128u) = e;
+            } else {
+                *reinterpret_cast<uint4 *>(hb + row_off + (uint32_t)(2 * KS + 1) * 128u) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            fence_proxy_async_smem();              // operand stores -> visible to the tensor core's smem reads
             mbar_arrive(&bar_split[p]);            // also: raw buffer p may be refilled
         }
 #if MASB200_FUSED_PROF
@@ -393,7 +416,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 #endif
     } else if (warp < 4) {
         // ======================= epilogue warps: TMEM lane quadrant = warp =======================
-        // per tile: D (TMEM) -> (ysq + dot) + (musq + const) -> ring slot of this lane's text row, as packed fp32x2 adds
+        // per tile: D (TMEM) = the finished log-prior values -> ring slot of this lane's text row
         const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
         int stage = 0;
         uint32_t sphase = 0;                                       // parity of the ring stage's CURRENT use
@@ -401,7 +424,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         for (int g = 0; g < ntiles; ++g) {
             const int p = g & 1;
             const uint32_t par = (uint32_t)(g >> 1) & 1u;
-            const float *yq_row = ysq + (g & (kYsqRing - 1)) * 32;
 #pragma unroll
             for (int mt = 0; mt < W; ++mt) {
                 if (mt < w_act) {
@@ -417,16 +439,16 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                     if (g >= NS) mbar_wait(&ring_empty[stage * 2 + mt], sphase ^ 1u);     // DP warp mt released the stage
                     PROF_ADD(w_rempty, c1);
                     float *rowp = ring + (size_t)stage * kTileFloats + (size_t)(warp * (32 * W) + 32 * mt + lane) * kTilePitch;
-                    const float ms = mc[mt];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 yq = *reinterpret_cast<const float4 *>(yq_row + 4 * c);
-                        float4 o;
-                        add_f32x2(o.x, o.y, yq.x, yq.y, __uint_as_float(d[4 * c + 0]), __uint_as_float(d[4 * c + 1]));
-                        add_f32x2(o.z, o.w, yq.z, yq.w, __uint_as_float(d[4 * c + 2]), __uint_as_float(d[4 * c + 3]));
-                        add_f32x2(o.x, o.y, o.x, o.y, ms, ms);
-                        add_f32x2(o.z, o.w, o.z, o.w, ms, ms);
-                        *reinterpret_cast<float4 *>(rowp + ((c ^ (lane & 7)) << 2)) = o;
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4 *>(rowp + ((c ^ (lane & 7)) << 2)) = make_uint4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
+                    if (FP.value_dump != nullptr) {                // tests only
+                        const int x = 128 * mt + 4 * lane + warp;
+                        float *dst = FP.value_dump + ((size_t)b * P.Tx + x) * P.Ty + g * NT;
+                        if (x < P.Tx)
+                            for (int c = 0; c < 8; ++c)
+                                if (g * NT + 4 * c < P.Ty)
+                                    *reinterpret_cast<uint4 *>(dst + 4 * c) = make_uint4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
                     }
                     __syncwarp();
                     if (lane == 0) flag_release(&eprog[mt * 4 + warp], g + 1);      // this warp's rows of (tile g, M-tile mt) are in the ring
@@ -459,11 +481,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         const uint32_t lane0_mask = (lane == 0) ? 0xffffffffu : 0u;
         const bool has_consumer = (w + 1 < w_act);
         float *hconst = hbuf + (size_t)W * HS * NT;              // warp 0's halo input (one constant row)
-        float *hdump = hconst + (size_t)HS * NT;                 // [W][32] where lanes without a consumer store
+        float *hdump = hconst + (size_t)HS * NT;                 // [W][160] where lanes without a consumer store
         const float *hb_in = (w > 0) ? hbuf + (size_t)(w - 1) * HS * NT : hconst;
         const int hin_step = (w > 0) ? NT : 0;
         float *hb_out = hbuf + (size_t)w * HS * NT;
-        const uint32_t hout_base = (has_consumer && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * NT);
+        const uint32_t hout_base = (has_consumer && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * FS::M::kDumpFloats + 4 * lane);
         const uint32_t hout_step = (has_consumer && lane == 31) ? NT * 4u : 0u;
         int *flag_out = hprog + w;
         // what tile j needs, one word per lane: lanes 0..3 the four epilogue warps' progress on this warp's M-tile
@@ -488,6 +510,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             __syncwarp();
             if (dbg && lane == 0) dbg[2] = clock64();
         }
+        // the first two value / halo groups of a tile are loaded as soon as the tile is known to be in the ring --
+        // for tile j + 1 that is before the tail work of tile j
+        float4 va[R], ha;
+        dp_tile_prefetch<R, XP>(va, ha, ring + lane_cta * kTilePitch, hb_in, lane7);
         for (int j = 0; j < ntiles; ++j) {
             const int t0 = j * NT;
             const int sync_next = flag_acquire(sync_word);       // consumed after the body
@@ -500,9 +526,18 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
             const int dl0 = lane_cta - t0 / R;
             PROF_T(cb0);
-            if (diag) dp_tile<R, XP, true>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
-            else dp_tile<R, XP, false>(q, acc, up, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+            if (diag) dp_tile_pre<R, XP, true>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+            else dp_tile_pre<R, XP, false>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             PROF_ADD(w_body, cb0);
+            // tile j + 1 ready?  (normally yes: the flags were read before the body) -> its first groups are on their
+            // way while this tile's direction words are stored and the tile is released
+            PROF_T(cw0);
+            if (j + 1 < ntiles) {
+                if (!__all_sync(kFullMask, sync_next >= j + 2)) flag_wait_ge_warp(sync_word, j + 2);
+                dp_tile_prefetch<R, XP>(va, ha, ring + (size_t)next_stage * kTileFloats + lane_cta * kTilePitch,
+                                        hb_in + next_hs * hin_step, lane7);
+            }
+            PROF_ADD(w_full, cw0);
 
             // direction words of this tile, walk-ready (see mas_forward_kernel)
             if (diag) {
@@ -524,9 +559,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             }
             stage = next_stage;
             hs = next_hs;
-            PROF_T(cw0);
-            if (j + 1 < ntiles && !__all_sync(kFullMask, sync_next >= j + 2)) flag_wait_ge_warp(sync_word, j + 2);
-            PROF_ADD(w_full, cw0);
         }
 #if MASB200_FUSED_PROF
         if (dbg && lane == 0) { dbg[22 + 2 * w] = w_full; dbg[26 + w] = w_body; }
@@ -541,10 +573,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     // ================================ backtrack + outputs (the ring is idle now) ================================
     int *tok = reinterpret_cast<int *>(ring);
     int *xin = tok + XP;
-    mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg);
-    if (dbg && tid == 0) dbg[5] = clock64();
     int *hd = xin + ((ntiles + 3) & ~3);
-    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg);
+    const bool heads = P.frame_token != nullptr;
+    mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg, heads ? hd : nullptr);
+    if (dbg && tid == 0) dbg[5] = clock64();
+    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg, heads);
     write_path_any(P, b, start_b, dur_b, tid, kFusedThreads);
     if (dbg && tid == 0) {
         dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y;
@@ -590,16 +623,14 @@ int fused_launch(FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, 
     return MAS_B200_OK;
 }
 
-template <int KS>
-int fused_dispatch_w(FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
-    return FP.mas.Tx <= 128 ? fused_launch<KS, 1>(FP, ymap, stream, dry_run) : fused_launch<KS, 2>(FP, ymap, stream, dry_run);
-}
-
+// TMEM budget: W M-tiles of A (hi, lo, extra K step: 2F + 8 columns each) + two D stages of W x 32 columns <= 512
 int fused_dispatch(int F, FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
+    const bool one = FP.mas.Tx <= 128;
     switch (F) {
-        case 64: return fused_dispatch_w<8>(FP, ymap, stream, dry_run);
-        case 80: return fused_dispatch_w<10>(FP, ymap, stream, dry_run);
-        case 96: return fused_dispatch_w<12>(FP, ymap, stream, dry_run);
+        case 64: return one ? fused_launch<8, 1>(FP, ymap, stream, dry_run) : fused_launch<8, 2>(FP, ymap, stream, dry_run);
+        case 80: return one ? fused_launch<10, 1>(FP, ymap, stream, dry_run) : fused_launch<10, 2>(FP, ymap, stream, dry_run);
+        case 96: return one ? fused_launch<12, 1>(FP, ymap, stream, dry_run) : MAS_B200_ERR_UNSUPPORTED;
+        case 128: return one ? fused_launch<16, 1>(FP, ymap, stream, dry_run) : MAS_B200_ERR_UNSUPPORTED;
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
 }
@@ -607,11 +638,12 @@ int fused_dispatch(int F, FusedParams &FP, const CUtensorMap &ymap, cudaStream_t
 }  // namespace
 
 // Shapes the fused kernel covers (everything else runs the serial form: log-prior kernel -> HBM -> MAS kernel):
-// F in {64, 80, 96} (A = mu_x hi/lo of two M-tiles + two D stages within the 512 TMEM columns), Tx <= 256 (two
-// M-tiles / two DP warps), Ty % 4 == 0 and 16-byte aligned operands (TMA), direction words + a >= 2-stage ring within
-// 227 KB of shared memory (Ty <= ~2900 frames at Tx <= 128, ~1500 at Tx <= 256).
+// F in {64, 80} with Tx <= 256 (two M-tiles / two DP warps) or F in {64, 80, 96, 128} with Tx <= 128 (one M-tile) -- the
+// A operand (mu_x hi/lo + the extra K step) and two D stages have to fit the 512 TMEM columns --, Ty % 4 == 0 and
+// 16-byte aligned operands (TMA), direction words + a >= 2-stage ring within 227 KB of shared memory (Ty up to ~2900
+// frames at Tx <= 128, ~1500 at Tx <= 256).
 bool lp_mas_fused_supported(const float *mu_x, const float *y, int B, int F, int Tx, int Ty) {
-    if (!(F == 64 || F == 80 || F == 96) || Tx > 256 || Ty % 4 != 0 || B <= 0) return false;
+    if (!(F == 64 || F == 80 || F == 96 || F == 128) || Tx > 256 || Ty % 4 != 0 || B <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(mu_x) & 15)) return false;
     FusedParams FP{};
     FP.mas.Tx = Tx; FP.mas.Ty = Ty;
@@ -660,6 +692,10 @@ int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const
     P.path_dtype = (want_path && fuse) ? path_dtype : MAS_B200_PATH_NONE;
     FP.mu = mu_x;
     FP.cst = log_prior_const(F);
+    {   // tests only: device pointer to a [B,Tx,Ty] buffer that receives the value tiles (two int options)
+        const unsigned lo = (unsigned)option("fused_dump_ptr_lo"), hi = (unsigned)option("fused_dump_ptr_hi");
+        FP.value_dump = reinterpret_cast<float *>(((unsigned long long)hi << 32) | lo);
+    }
     rc = fused_dispatch(F, FP, ymap, stream, false);
     if (rc != MAS_B200_OK) return rc;
     if (want_path && !fuse) return launch_path_expand(P.start, P.dur, B, Tx, Ty, path, path_dtype, stream);

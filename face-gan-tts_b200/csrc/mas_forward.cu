@@ -31,7 +31,7 @@ constexpr size_t kStaticSmem = 64;           // bt_state + slack
 size_t fixed_bytes_rw(int R, int W, int ns) {
     const int XP = 32 * R * W;
     const size_t ring = sizeof(float) * (size_t)ns * XP * kTilePitch;
-    const size_t halo = sizeof(float) * ((size_t)(W + 1) * (ns + 1) + W) * kTileFrames;
+    const size_t halo = sizeof(float) * (((size_t)(W + 1) * (ns + 1)) * kTileFrames + (size_t)W * 160);   // MasSmem::halo_bytes
     const size_t ctrl = 8 * (size_t)(2 * ns) + 4 * (size_t)(W + 2) + 64;
     return ((ring + halo + ctrl + 127) / 128) * 128;
 }

@@ -206,21 +206,28 @@ __device__ __forceinline__ void dp_group(float (&q)[R], uint32_t (&acc)[R], floa
     dp_frame<R, 4 * H + 3, DIAG>(q, acc, up, v, h4.w, lane0_mask, dlb, neg, hout_addr);
 }
 
-// A whole 32-frame tile: a loop of four 8-frame blocks (value and halo groups register double-buffered across the
-// loop).  The block body is ~2.7 KB of code and stays in the instruction cache of the scheduler partition; the
-// fully unrolled tile (11 KB per variant, beside the other roles' loops) did not -- the DP warps ran at 50-67
-// cycles/frame instead of the ~30 the instruction stream costs, varying from SM pair to SM pair.
-//   hin   32 floats in shared memory: Q of the row above the warp at the tile's frames
-//   acc   must be zero on entry; on exit bit k of acc[r] is the direction bit of frame k
+// A whole 32-frame tile as a loop of four 8-frame blocks (value and halo groups register double-buffered across the
+// loop).  The block body is ~2.7 KB of code and stays in the instruction cache; the fully unrolled tile (11 KB per
+// variant, beside the other roles' loops) did not.
+//   va, ha   group 0 of THIS tile, already loaded (dp_tile_prefetch: for tile j + 1 that happens before the tail work
+//            of tile j, so the tile starts without a shared-memory round trip); garbage on exit
+//   hin      32 floats in shared memory: Q of the row above the warp at the tile's frames
+//   acc      must be zero on entry; on exit bit k of acc[r] is the direction bit of frame k
+template <int R, int XP>
+__device__ __forceinline__ void dp_tile_prefetch(float4 (&va)[R], float4 &ha, const float *lane_tile, const float *hin,
+                                                 int lane7) {
+    load_group<R, XP>(va, lane_tile, lane7, 0);
+    ha = *reinterpret_cast<const float4 *>(hin);
+}
+
 template <int R, int XP, bool DIAG>
-__device__ __forceinline__ void dp_tile(float (&q)[R], uint32_t (&acc)[R], float &up, const float *lane_tile,
-                                        const float *hin, int lane7, uint32_t lane0_mask, int dl0, float neg,
-                                        uint32_t hout_addr) {
+__device__ __forceinline__ void dp_tile_pre(float (&q)[R], uint32_t (&acc)[R], float &up, float4 (&va)[R], float4 &ha,
+                                            const float *lane_tile, const float *hin, int lane7, uint32_t lane0_mask,
+                                            int dl0, float neg, uint32_t hout_addr) {
     static_assert(8 % R == 0, "rows per lane must divide the 8-frame block");
-    float4 va[R], vb[R];
-    float4 ha, hb;
+    float4 vb[R];
+    float4 hb;
     const float4 *h4 = reinterpret_cast<const float4 *>(hin);
-    load_group<R, XP>(va, lane_tile, lane7, 0); ha = h4[0];
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         load_group<R, XP>(vb, lane_tile, lane7, 2 * i + 1); hb = h4[2 * i + 1];
@@ -233,6 +240,16 @@ __device__ __forceinline__ void dp_tile(float (&q)[R], uint32_t (&acc)[R], float
         dl0 -= 8 / R;
         hout_addr += 32u;
     }
+}
+
+template <int R, int XP, bool DIAG>
+__device__ __forceinline__ void dp_tile(float (&q)[R], uint32_t (&acc)[R], float &up, const float *lane_tile,
+                                        const float *hin, int lane7, uint32_t lane0_mask, int dl0, float neg,
+                                        uint32_t hout_addr) {
+    float4 va[R];
+    float4 ha;
+    dp_tile_prefetch<R, XP>(va, ha, lane_tile, hin, lane7);
+    dp_tile_pre<R, XP, DIAG>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, neg, hout_addr);
 }
 
 template <int R>
@@ -251,7 +268,7 @@ __device__ __forceinline__ void store_words(uint32_t *dst, const uint32_t (&acc)
 }
 
 // Shared-memory carve-up; host (launcher) and device agree through these functions.
-//   [ring: NS value tiles][halo: (W+1) rings of NS+1 slots x 32 floats, W dump rows][ctrl][direction bits]
+//   [ring: NS value tiles][halo: (W+1) rings of NS+1 slots x 32 floats, W dump areas][ctrl][direction bits]
 // halo ring i < W is written by DP warp i; ring W holds the constant / carried-line input of warp 0.
 template <int R, int W>
 struct MasSmem {
@@ -259,8 +276,12 @@ struct MasSmem {
     static constexpr int kTileFloats = XP * kTilePitch;
     __host__ __device__ static constexpr size_t ring_bytes(int ns) { return sizeof(float) * (size_t)ns * kTileFloats; }
     __host__ __device__ static constexpr int halo_slots(int ns) { return ns + 1; }
+    // halo rings + per DP warp a 640-byte dump area: lanes without a consumer store their (unused) halo value to the
+    // 16-byte slot (lane + 4-frame group) of it -- 32 distinct slots per store instruction.  (All lanes storing to ONE
+    // address serialised into 32 shared-memory passes per STS.128: 2-8 cycles per frame of write-after-read stalls.)
+    static constexpr int kDumpFloats = 160;
     __host__ __device__ static constexpr size_t halo_bytes(int ns) {
-        return sizeof(float) * ((size_t)(W + 1) * halo_slots(ns) + W) * kTileFrames;
+        return sizeof(float) * (((size_t)(W + 1) * halo_slots(ns)) * kTileFrames + (size_t)W * kDumpFloats);
     }
     __host__ __device__ static constexpr size_t ctrl_bytes(int ns) { return 8 * (size_t)(2 * ns) + 4 * (size_t)(W + 2) + 64; }
     __host__ __device__ static constexpr size_t fixed_bytes(int ns) {
@@ -458,10 +479,13 @@ __device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, i
 // Backtrack over walk-ready direction words in shared memory: the transfer tables of row groups [G0, G1) still owed
 // for tiles [jt_owed, ntiles) are shared by all warps, then one dependent shared-memory load per TILE gives the
 // token each tile is entered with, then one thread per tile emits the start frames tok[x] of its tokens.
+//   hd   optional [t_y] frame "head" marks for mas_emit_outputs_scan (hd[start frame of token x] = x, -1 elsewhere):
+//        cleared by the idle threads while thread 0 walks the tile chain, set by the per-tile walkers -- saves the
+//        output stage two passes and two block barriers.
 template <int XP, int NTHREADS, int G0, int G1>
 __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsigned char *nj_s, int *tok, int *xin,
                                                    int jt_owed, int ntiles, int t_x, int t_y, int tid,
-                                                   long long *dbg = nullptr) {
+                                                   long long *dbg = nullptr, int *hd = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     if constexpr (G0 < G1) {
         constexpr int nwarps = NTHREADS / 32;
@@ -478,6 +502,8 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
         }
         tok[0] = 0;
         if (dbg) dbg[10] = clock64();
+    } else if (hd != nullptr) {
+        for (int t = tid - 1; t < t_y; t += NTHREADS - 1) hd[t] = -1;
     }
     __syncthreads();
     for (int jt = tid; jt < ntiles; jt += NTHREADS) {                     // one thread per tile: start frames
@@ -486,9 +512,12 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
         uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
         for (int x = xin[jt]; x > lo; --x) {
             const uint32_t m = bj[x] & mk;
-            tok[x] = (jt << 5) + 32 - __ffs((int)m);
+            const int st = (jt << 5) + 32 - __ffs((int)m);
+            tok[x] = st;
+            if (hd != nullptr) hd[st] = x;
             mk = m ^ (0u - m);
         }
+        if (jt == 0 && hd != nullptr) hd[0] = 0;                           // token 0 starts at frame 0
     }
     __syncthreads();
 }
@@ -498,9 +527,10 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
 // (hd[start frame of x] = x): one thread per 8 frames, warp shuffle scan, 16-byte stores -- instead of one thread
 // per token walking its frames (a 200-frame silence token was the whole tail).
 //   hd   scratch in shared memory: [(Ty + 3) & ~3] heads + [32] warp totals
+//   heads_ready   hd[] was already filled by mas_backtrack_smem
 template <int NTHREADS>
 __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b, const int *tok, int *hd, int t_x, int t_y,
-                                                      int tid, long long *dbg = nullptr) {
+                                                      int tid, long long *dbg = nullptr, bool heads_ready = false) {
     const int warp = tid >> 5, lane = tid & 31;
     int *start_b = P.start + (size_t)b * P.Tx;
     int *dur_b = P.dur + (size_t)b * P.Tx;
@@ -516,14 +546,16 @@ __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b,
     }
     if (ft) {
         int *wt = hd + ((P.Ty + 3) & ~3);
-        for (int t = tid; t < t_y; t += NTHREADS) hd[t] = -1;
-        __syncthreads();
-        for (int x = tid; x < t_x; x += NTHREADS) {
-            const int s = tok[x];
-            const int e = (x + 1 < t_x) ? tok[x + 1] : t_y;
-            if (e > s) hd[s] = x;
+        if (!heads_ready) {
+            for (int t = tid; t < t_y; t += NTHREADS) hd[t] = -1;
+            __syncthreads();
+            for (int x = tid; x < t_x; x += NTHREADS) {
+                const int s = tok[x];
+                const int e = (x + 1 < t_x) ? tok[x + 1] : t_y;
+                if (e > s) hd[s] = x;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (dbg && tid == 0) dbg[11] = clock64();
         const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
         constexpr int nw = NTHREADS >> 5;
@@ -634,7 +666,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     float *gline_b = P.gline ? P.gline + (size_t)b * 2 * P.line_pitch : nullptr;
     const float *vb = P.value + (size_t)b * P.stride_b;
     float *hconst = hbuf + (size_t)W * HS * NT;              // warp 0's halo input ring
-    float *hdump = hconst + (size_t)HS * NT;                 // [W][32] where lanes without a consumer store
+    float *hdump = hconst + (size_t)HS * NT;                 // [W][160] where lanes without a consumer store
 
     for (int pass = 0; pass < npass; ++pass) {
         const int rows_base = pass * XP;
@@ -751,7 +783,7 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
             const float *hb_in = (w > 0) ? hbuf + (size_t)(w - 1) * HS * NT : hconst;
             const int hin_step = (w > 0 || line_in) ? NT : 0;        // warp 0 of pass 0 re-reads one constant row
             float *hb_out = hbuf + (size_t)w * HS * NT;
-            const uint32_t hout_base = ((has_consumer || line_out) && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * NT);
+            const uint32_t hout_base = ((has_consumer || line_out) && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * S::kDumpFloats + 4 * lane);
             const uint32_t hout_step = ((has_consumer || line_out) && lane == 31) ? NT * 4u : 0u;
             const int *flag_in = (w > 0) ? hprog + (w - 1) : hprog + W;           // hprog[W] is pre-satisfied
             int *flag_out = hprog + w;                                            // also read by the backtrack helper
@@ -839,9 +871,14 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     // (4*(Tx + tiles) bytes always fit below two value tiles there), else global (start table, carry line)
     int *tok = SMEM_BITS ? reinterpret_cast<int *>(ring) : start_b;
     int *xin = SMEM_BITS ? tok + XP : reinterpret_cast<int *>(gline_b);
+    // scratch of the output scan, in the (idle) ring behind tok / xin: heads [Ty], warp totals [32]
+    int *hd = xin + ((ntiles + 3) & ~3);
+    const bool scan_ft = SMEM_BITS && (mas_tail_scratch_ints(XP, ntiles, P.Ty) * sizeof(int) <= S::ring_bytes(NS));
+    const bool heads = scan_ft && P.frame_token != nullptr;
     if constexpr (SMEM_BITS) {
         // transfer tables (upper row groups) the producer warp did not get to, tile entry tokens, start frames
-        mas_backtrack_smem<XP, nthreads, kGH, kG>(bits_s, nj_s, tok, xin, bt_state[3], ntiles, t_x, t_y, tid);
+        mas_backtrack_smem<XP, nthreads, kGH, kG>(bits_s, nj_s, tok, xin, bt_state[3], ntiles, t_x, t_y, tid, nullptr,
+                                                  heads ? hd : nullptr);
     } else {
         const int rows_pitch = P.gbits_rows_pitch;
         uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
@@ -891,11 +928,8 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     // ================================= outputs =================================
     // [start, duration] per token from the start frames; frame -> token index; dense path
     int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
-    // scratch of the scan below, in the (idle) ring behind tok / xin: heads [Ty], warp totals [32]
-    int *hd = xin + ((ntiles + 3) & ~3);
-    const bool scan_ft = SMEM_BITS && (mas_tail_scratch_ints(XP, ntiles, P.Ty) * sizeof(int) <= S::ring_bytes(NS));
     if (scan_ft) {
-        mas_emit_outputs_scan<nthreads>(P, b, tok, hd, t_x, t_y, tid);
+        mas_emit_outputs_scan<nthreads>(P, b, tok, hd, t_x, t_y, tid, nullptr, heads);
     } else {
         for (int x = tid; x < P.Tx; x += nthreads) {
             int s = 0, d = 0;

@@ -33,6 +33,7 @@ SIGNATURES = {
     "mas_b200_maximum_path": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mas_b200_log_prior": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mas_b200_set_pointer_option": (c_int, [c_char_p, c_void_p]),
     "mas_b200_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mas_b200_fused_workspace_prepare": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "mas_b200_log_prior_maximum_path": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -105,6 +106,12 @@ def set_option(key: str, value: int) -> int:
     if prev == -2 ** 31:
         raise KeyError(key)
     return prev
+
+
+def set_pointer_option(key: str, tensor) -> None:
+    """Diagnostics / tests: hand a device buffer (torch tensor, or None to switch off) to the library."""
+    check(lib().mas_b200_set_pointer_option(key.encode(), None if tensor is None else tensor.data_ptr()),
+          "mas_b200_set_pointer_option")
 
 
 def get_option(key: str) -> int:

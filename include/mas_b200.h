@@ -294,6 +294,12 @@ int mas_b200_log_prior_maximum_path_host(const float *mu_x, const float *y,
  * INT32_MIN for an unknown key.  Process-wide, read at launch time. */
 int mas_b200_set_option(const char *key, int value);
 int mas_b200_get_option(const char *key);
+/* Diagnostics / tests only: a device pointer option (stored as the two int options key_lo / key_hi).
+ *   "mas_debug_ptr"   [B][32] int64  phase stamps of the MAS / fused kernels
+ *   "lp_debug_ptr"    [ctas][32] int64 stamps of the unfused tcgen05 log-prior kernel
+ *   "fused_dump_ptr"  [B,Tx,Ty] float32: the fused kernel also writes the value tiles its search consumed
+ * NULL switches the option off.  Returns MAS_B200_OK or MAS_B200_ERR_ARG for an unknown key. */
+int mas_b200_set_pointer_option(const char *key, void *device_ptr);
 
 #ifdef __cplusplus
 }

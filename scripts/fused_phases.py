@@ -18,13 +18,10 @@ def run(B, F, Tx, Ty, full=False):
     for _ in range(3):
         plan(mu, y, tx, ty)
     dbg = torch.zeros((B, 32), dtype=torch.int64, device="cuda")
-    p = dbg.data_ptr()
-    lo, hi = p & 0xFFFFFFFF, p >> 32
-    _lib.set_option("mas_debug_ptr_lo", lo - (1 << 32) if lo >= (1 << 31) else lo)
-    _lib.set_option("mas_debug_ptr_hi", hi)
+    _lib.set_pointer_option("mas_debug_ptr", dbg)
     plan(mu, y, tx, ty)
     torch.cuda.synchronize()
-    _lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0)
+    _lib.set_pointer_option("mas_debug_ptr", None)
     d = dbg.cpu()
     print(f"--- fused B={B} F={F} Tx={Tx} Ty={Ty} full={full}")
     print("  b  t_x   t_y | (setup mu_load park_A) prologue first_tile   dp_total  cyc/frame |  join backtrack (chain) outputs (heads) | total cyc   wall us")
