@@ -36,6 +36,7 @@ Opt g_opts[] = {
     {"upload_ctas", {0}},            // CTAs of the zero-copy upload kernel (0 = one per SM)
     {"fused_dump_ptr_lo", {0}},      // tests only: [B,Tx,Ty] float buffer receiving the fused kernel's value tiles (device pointer halves)
     {"fused_dump_ptr_hi", {0}},
+    {"pdl", {1}},                    // 1: fused kernel / path expansion launch with programmatic stream serialization
     {"fused_impl", {0}},             // 0 auto (fused kernel when the shape is covered), 1 force the serial form
 };
 }  // namespace
@@ -116,6 +117,10 @@ int mas_b200_set_pointer_option(const char *key, void *ptr) {
 size_t mas_b200_workspace_bytes(int B, int Tx, int Ty) {
     if (B <= 0 || Tx <= 0 || Ty <= 0) return 0;
     return workspace_layout(B, Tx, Ty).total;
+}
+
+int mas_b200_debug_occupy_sms(int ctas, long long cycles, void *stream) {
+    return launch_debug_spin(ctas, cycles, static_cast<cudaStream_t>(stream));
 }
 
 int mas_b200_lengths_from_mask(const float *mask_dev, int B, int Tx, int Ty, int *t_x_dev, int *t_y_dev,

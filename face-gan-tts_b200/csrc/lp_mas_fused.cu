@@ -144,6 +144,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);     // provably warp-uniform for ptxas
     const int lane = tid & 31;
+    // Programmatic dependent launch: this grid may have been placed while the previous kernel of the stream was
+    // still running (its launch latency is hidden); nothing it wrote is touched before this wait returns.  The next
+    // kernel of the stream may be placed as soon as every CTA of this grid is past the trigger.
+    pdl_wait();
+    pdl_launch_dependents();
     const int t_x = __shfl_sync(kFullMask, P.t_x[b], 0);
     const int t_y = __shfl_sync(kFullMask, P.t_y[b], 0);
     int *start_b = P.start + (size_t)b * P.Tx;
@@ -618,8 +623,17 @@ int fused_launch(FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, 
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedMaxSmem));
         if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
     }
-    kern<<<FP.mas.B, kFusedThreads, smem, stream>>>(FP, ymap);
-    MASB200_CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)FP.mas.B);
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = option("pdl") != 0 ? 1 : 0;
+    MASB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, FP, ymap));
     return MAS_B200_OK;
 }
 

@@ -25,6 +25,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 }
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch (griddepcontrol): see lp_mas_fused.cu / path_ops.cu
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // mbarrier (shared::cta).  arrive = release.cta, try_wait = acquire.cta.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

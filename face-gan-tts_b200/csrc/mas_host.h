@@ -65,6 +65,7 @@ int launch_mas(const MasLaunch &L);
 
 int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, void *path, int path_dtype,
                        cudaStream_t stream);
+int launch_debug_spin(int ctas, long long cycles, cudaStream_t stream);   // tests only (path_ops.cu)
 int launch_lengths_from_mask(const float *mask, int B, int Tx, int Ty, int *t_x, int *t_y, cudaStream_t stream);
 int launch_generate_path(const void *durations, int dur_is_float, const int *t_x, const int *t_y, int B, int Tx, int Ty,
                          void *path, int path_dtype, int *frame_token, cudaStream_t stream);

@@ -2,6 +2,8 @@
 //   path_expand       [start,dur] table -> dense [B,Tx,Ty] path (pure streaming write, all SMs)
 //   lengths_from_mask dense prefix mask -> t_x, t_y   (reference monotonic_align/__init__.py:20-21)
 //   generate_path     integer durations -> dense path (reference model/utils.py:27-40)
+#include <atomic>
+
 #include "mas_forward.cuh"
 #include "mas_host.h"
 
@@ -16,6 +18,8 @@ template <typename T>
 __global__ void __launch_bounds__(kExpandThreads) path_expand_kernel(const int *__restrict__ start,
                                                                      const int *__restrict__ dur, int Tx, int Ty,
                                                                      T *__restrict__ path) {
+    pdl_wait();                   // launched programmatically behind the kernel that produces the table
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int x0 = blockIdx.x * kExpandRows;
     const int rows = min(kExpandRows, Tx - x0);
@@ -100,13 +104,45 @@ __global__ void __launch_bounds__(256) generate_path_kernel(const D *__restrict_
 int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, void *path, int path_dtype,
                        cudaStream_t stream) {
     if (!start || !dur || !path || B <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
-    dim3 grid((Tx + kExpandRows - 1) / kExpandRows, B);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((Tx + kExpandRows - 1) / kExpandRows, B);
+    cfg.blockDim = dim3(kExpandThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = option("pdl") != 0 ? 1 : 0;
     if (path_dtype == MAS_B200_PATH_F32)
-        path_expand_kernel<float><<<grid, kExpandThreads, 0, stream>>>(start, dur, Tx, Ty, static_cast<float *>(path));
+        MASB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, path_expand_kernel<float>, start, dur, Tx, Ty, static_cast<float *>(path)));
     else if (path_dtype == MAS_B200_PATH_I32)
-        path_expand_kernel<int><<<grid, kExpandThreads, 0, stream>>>(start, dur, Tx, Ty, static_cast<int *>(path));
+        MASB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, path_expand_kernel<int>, start, dur, Tx, Ty, static_cast<int *>(path)));
     else
         return MAS_B200_ERR_ARG;
+    return MAS_B200_OK;
+}
+
+// tests only: `ctas` CTAs that each hold a whole SM (max dynamic shared memory) for `cycles` clock cycles
+__global__ void __launch_bounds__(32, 1) debug_spin_kernel(long long cycles) {
+    extern __shared__ unsigned char hog[];
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) __nanosleep(200);
+    if (cycles < 0) hog[threadIdx.x] = 0;
+}
+
+int launch_debug_spin(int ctas, long long cycles, cudaStream_t stream) {
+    if (ctas <= 0 || cycles < 0) return MAS_B200_ERR_ARG;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != MAS_B200_OK) return rc;
+    static std::atomic<int> configured[16];
+    int dev = 0;
+    MASB200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
+        MASB200_CUDA_TRY(cudaFuncSetAttribute(debug_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
+    }
+    debug_spin_kernel<<<ctas, 32, di.max_smem_optin, stream>>>(cycles);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

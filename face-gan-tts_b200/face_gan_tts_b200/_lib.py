@@ -34,6 +34,7 @@ SIGNATURES = {
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mas_b200_log_prior": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mas_b200_set_pointer_option": (c_int, [c_char_p, c_void_p]),
+    "mas_b200_debug_occupy_sms": (c_int, [c_int, c_ll, c_void_p]),
     "mas_b200_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mas_b200_fused_workspace_prepare": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "mas_b200_log_prior_maximum_path": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -300,6 +300,9 @@ int mas_b200_get_option(const char *key);
  *   "fused_dump_ptr"  [B,Tx,Ty] float32: the fused kernel also writes the value tiles its search consumed
  * NULL switches the option off.  Returns MAS_B200_OK or MAS_B200_ERR_ARG for an unknown key. */
 int mas_b200_set_pointer_option(const char *key, void *device_ptr);
+/* Tests only: launches `ctas` CTAs on `stream` that each hold one whole SM (maximum dynamic shared memory) for `cycles`
+ * SM clock cycles -- a foreign kernel that keeps SMs away from the library's kernels (tests/test_gpu_logprior.py). */
+int mas_b200_debug_occupy_sms(int ctas, long long cycles, void *stream);
 
 #ifdef __cplusplus
 }

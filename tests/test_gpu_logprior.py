@@ -58,73 +58,119 @@ def test_log_prior_odd_shapes(impl):
         assert rel_err(fgt.log_prior(mu, y, impl=impl), oracle.log_prior_direct(mu, y)) < REL_TOL
 
 
-@pytest.mark.parametrize("impl", IMPLS)
-def test_fused_call_bit_exact_on_its_own_value_and_agrees_with_reference_pipeline(impl):
-    """log_prior_maximum_path(mu_x, y, lengths): (1) its path is the bit-exact MAS of the value matrix the
-    library's log-prior produces; (2) agreement with torch-fp32 log-prior -> oracle MAS is reported and high."""
-    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=8, F=80, Tx=190, Ty=1000, seed=1234)
+def _reference_mas(value_np, t_x_np, t_y_np):
+    """int32 paths of the reference MAS: the reference's own compiled core.pyx when it travelled to this box
+    (oracle/_ref), else the C restatement that is pinned to it (tests/test_oracle.py)."""
+    paths = np.zeros(value_np.shape, np.int32)
+    core = oracle.reference_core("asis")
+    if core is not None:
+        core.maximum_path_c(paths, np.ascontiguousarray(value_np, dtype=np.float32).copy(), t_x_np.astype(np.int32), t_y_np.astype(np.int32))
+    else:
+        oracle.maximum_path_c(paths, value_np.copy(), t_x_np, t_y_np)
+    return paths
+
+
+def _fused_with_value_dump(mu_d, y_d, t_x, t_y, **kw):
+    """The fused call with the tests-only `fused_dump_ptr` hook: also returns the value tiles the in-kernel search
+    consumed (NaN where the kernel wrote nothing: beyond the last 32-frame tile of an utterance)."""
+    from face_gan_tts_b200 import _lib
+
+    B, _, Tx = mu_d.shape
+    dump = torch.full((B, Tx, y_d.shape[2]), float("nan"), device=DEV)
+    _lib.set_pointer_option("fused_dump_ptr", dump)
+    try:
+        res = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, **kw)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_pointer_option("fused_dump_ptr", None)
+    return res, dump
+
+
+def _agreement(ft, ref_ft):
+    valid = ref_ft >= 0
+    return float((ft[valid] == ref_ft[valid]).mean())
+
+
+# (B, F, Tx, Ty): the LRS2 bench shape, the reference default n_feats = 128 with short texts (one M-tile), F = 64 / 96
+FUSED_SHAPES = [(8, 80, 190, 1000), (32, 80, 190, 1000), (32, 128, 128, 1000), (5, 64, 256, 512), (6, 96, 100, 600),
+                (3, 80, 31, 64), (4, 80, 129, 1400)]
+
+
+@pytest.mark.parametrize("B,F,Tx,Ty", FUSED_SHAPES)
+def test_fused_kernel_path_is_bit_exact_mas_of_its_own_values(B, F, Tx, Ty):
+    """The fused kernel (one CTA per utterance, value tiles handed over in shared memory): (1) the values its search
+    consumed are the log-prior within 1e-4 relative of torch fp32; (2) path / durations / frame_token are the BIT-EXACT
+    reference MAS of exactly those values; (3) frame-level agreement with torch-fp32 log-prior -> reference MAS."""
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=1234, tx_lo=max(1, Tx // 3), ty_lo=max(Tx, Ty // 3))
     mu_d, y_d = mu_x.to(DEV), y.to(DEV)
-    res = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, path_dtype=torch.int32, impl=impl, check=True)
-    lp = fgt.log_prior(mu_d, y_d, impl=impl)
-    own = np.zeros(lp.shape, np.int32)
-    oracle.maximum_path_c(own, lp.cpu().numpy().copy(), t_x.numpy(), t_y.numpy())
+    res, dump = _fused_with_value_dump(mu_d, y_d, t_x, t_y, path_dtype=torch.int32, check=True)
+    assert not torch.isnan(dump[0, 0, 0]), "the fused kernel did not run (shape fell back to the serial form)"
+    ref_lp = oracle.log_prior_reference(mu_d, y_d)
+    txn, tyn = t_x.numpy(), t_y.numpy()
+    for b in range(B):
+        a, c = dump[b, :txn[b], :tyn[b]], ref_lp[b, :txn[b], :tyn[b]]
+        assert rel_err(a, c) < REL_TOL
+    own = _reference_mas(torch.nan_to_num(dump).cpu().numpy(), txn, tyn)
     np.testing.assert_array_equal(res.path.cpu().numpy(), own)
     dur, ft = oracle.durations_and_frame_token(own)
     np.testing.assert_array_equal(res.durations.cpu().numpy(), dur)
     np.testing.assert_array_equal(res.frame_token.cpu().numpy(), ft)
-
-    ref_lp = oracle.log_prior_reference(mu_d, y_d).cpu().numpy()
-    ref = np.zeros(lp.shape, np.int32)
-    oracle.maximum_path_c(ref, ref_lp.copy(), t_x.numpy(), t_y.numpy())
+    ref = _reference_mas(ref_lp.cpu().numpy(), txn, tyn)
     _, ref_ft = oracle.durations_and_frame_token(ref)
-    valid = ref_ft >= 0
-    agree = (ft[valid] == ref_ft[valid]).mean()
-    print(f"\n[{impl}] frame-level path agreement with torch-fp32 log-prior -> reference MAS: {agree * 100:.4f}%")
+    agree = _agreement(ft, ref_ft)
+    print(f"\n[fused B={B} F={F} {Tx}x{Ty}] frame-level path agreement with torch-fp32 log-prior -> reference MAS: {agree * 100:.4f}%")
     assert agree > 0.999
 
 
-def test_prepared_workspace_nonce_flags_survive_reuse_and_stale_contents():
-    """MAS_B200_WS_PREPARED: the flag area is cleared once and never again; stale flags of earlier calls (older
-    nonces) must never read as set -- also when the SAME workspace serves different inputs back to back, with and
-    without the dense path, interleaved with unprepared calls on it."""
+@pytest.mark.parametrize("impl,F", [("ffma", 80), ("auto", 128), ("ffma", 128)])
+def test_serial_form_bit_exact_on_its_own_value_and_agrees_with_reference_pipeline(impl, F):
+    """Shapes / implementations the fused kernel does not take (n_feats = 128 with two M-tiles, the FFMA log-prior):
+    log-prior kernel -> [B,Tx,Ty] -> MAS kernel.  Same three checks, at the bench batch size."""
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=32, F=F, Tx=190, Ty=1000, seed=1234)
+    mu_d, y_d = mu_x.to(DEV), y.to(DEV)
+    res = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, path_dtype=torch.int32, impl=impl, check=True)
+    lp = fgt.log_prior(mu_d, y_d, impl=impl)
+    own = _reference_mas(lp.cpu().numpy(), t_x.numpy(), t_y.numpy())
+    np.testing.assert_array_equal(res.path.cpu().numpy(), own)
+    dur, ft = oracle.durations_and_frame_token(own)
+    np.testing.assert_array_equal(res.durations.cpu().numpy(), dur)
+    np.testing.assert_array_equal(res.frame_token.cpu().numpy(), ft)
+    ref = _reference_mas(oracle.log_prior_reference(mu_d, y_d).cpu().numpy(), t_x.numpy(), t_y.numpy())
+    _, ref_ft = oracle.durations_and_frame_token(ref)
+    agree = _agreement(ft, ref_ft)
+    print(f"\n[{impl} F={F}] frame-level path agreement with torch-fp32 log-prior -> reference MAS: {agree * 100:.4f}%")
+    assert agree > 0.999
+
+
+def test_prepared_workspace_flag_is_still_accepted():
+    """mas_b200_fused_workspace_prepare / MAS_B200_WS_PREPARED were the protocol of the removed two-kernel pipeline; they
+    stay in the ABI as no-ops: garbage in the workspace, prepared or not, dense path or not -- same results."""
     from face_gan_tts_b200 import _lib
 
     L = _lib.lib()
     B, F, Tx, Ty = 32, 80, 190, 1000
-    sets = []
-    for k in range(3):
-        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=300 + k)
-        sets.append((mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV)))
-    prev = _lib.set_option("fused_impl", 1)
-    try:
-        want = [fgt.log_prior_maximum_path(*s_, path_dtype=torch.float32) for s_ in sets]
-        torch.cuda.synchronize()
-    finally:
-        _lib.set_option("fused_impl", prev)
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=300)
+    mu, yy, tx, ty = mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV)
+    want = fgt.log_prior_maximum_path(mu, yy, tx, ty, path_dtype=torch.float32)
     ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, Tx, Ty)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=DEV)
-    ws.fill_(0xAB)                                             # garbage everywhere, then prepare
+    ws.fill_(0xAB)
     assert L.mas_b200_fused_workspace_prepare(ws.data_ptr(), ws_bytes, B, F, Tx, Ty, None) == 0
     path = torch.empty((B, Tx, Ty), device=DEV)
     dur = torch.empty((B, Tx), dtype=torch.int32, device=DEV)
     ft = torch.empty((B, Ty), dtype=torch.int32, device=DEV)
     st = torch.empty((B,), dtype=torch.int32, device=DEV)
     sp = torch.cuda.current_stream().cuda_stream
-    bad = torch.zeros((), dtype=torch.int64, device=DEV)
-    for i in range(120):
-        mu, yy, tx, ty = sets[i % 3]
+    for i in range(8):
         dense = (i % 4) != 3
-        impl = _lib.LP_AUTO | (_lib.WS_PREPARED if (i % 7) != 5 else 0)
+        impl = _lib.LP_AUTO | (_lib.WS_PREPARED if i % 2 else 0)
         rc = L.mas_b200_log_prior_maximum_path(mu.data_ptr(), yy.data_ptr(), tx.data_ptr(), ty.data_ptr(), B, F, Tx, Ty, -1e9,
                                                path.data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
                                                dur.data_ptr(), ft.data_ptr(), st.data_ptr(), ws.data_ptr(), ws_bytes, impl, sp)
         assert rc == 0
-        w = want[i % 3]
-        bad += (dur != w.durations).sum() + (ft != w.frame_token).sum()
+        assert torch.equal(dur, want.durations) and torch.equal(ft, want.frame_token)
         if dense:
-            bad += (path != w.path).sum()
-    torch.cuda.synchronize()
-    assert int(bad) == 0
+            assert torch.equal(path, want.path)
 
 
 def test_alignment_plan_equals_functional_api_and_reuses_buffers():
@@ -211,35 +257,42 @@ def test_tcgen05_kernel_is_the_one_running_and_matches_ffma():
         fgt.log_prior(mu_x.to(DEV), y.to(DEV), impl="tcgen05")          # n_feats not instantiated: raises, no fallback
 
 
-@pytest.mark.parametrize("B,F", [(3, 80), (32, 80), (80, 80), (3, 128), (32, 128), (49, 128), (50, 128)])
-def test_overlapped_pipeline_equals_serial_pipeline(B, F):
-    """mas_b200_log_prior_maximum_path: the overlapped log-prior || MAS pipeline (device flags, dense path written
-    by the log-prior CTAs; taken for 2*B <= SM count) and the serial one (fused_impl=1; also what B=80 gets) must
-    produce identical outputs -- same kernels, same arithmetic, only the scheduling differs."""
+@pytest.mark.parametrize("B,F,Tx", [(3, 80, 190), (32, 80, 190), (80, 80, 190), (300, 80, 190), (32, 128, 128), (3, 128, 190), (50, 128, 190)])
+def test_fused_kernel_vs_serial_form(B, F, Tx):
+    """mas_b200_log_prior_maximum_path: the fused kernel (default where the shape is covered) and the serial form
+    (fused_impl=1: log-prior kernel -> HBM -> MAS kernel -> path expansion) are two schedules of the same computation.
+    Their log-priors differ in the last bits (the fused kernel folds the y^2 / mu^2 terms into the contraction), so the
+    paths may differ at near-ties: status and structure must be identical, frames must agree > 99.9 %.  Shapes the fused
+    kernel does not cover (F = 128 with two M-tiles) take the serial form in both modes: identical outputs."""
     from face_gan_tts_b200 import _lib
 
-    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=190, Ty=1000, seed=11)      # F = 128: split-M, counting flags
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=1000, seed=11)
     mu_d, y_d = mu_x.to(DEV), y.to(DEV)
     outs = []
     for mode in (0, 1):
         prev = _lib.set_option("fused_impl", mode)
         try:
             r = None
-            for _ in range(4):                      # back to back, no host sync in between: flag reuse across calls
+            for _ in range(4):                      # back to back, no host sync in between
                 r = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, path_dtype=torch.float32)
             torch.cuda.synchronize()
             outs.append(r)
         finally:
             _lib.set_option("fused_impl", prev)
     a, b = outs
-    assert torch.equal(a.path, b.path) and torch.equal(a.durations, b.durations)
-    assert torch.equal(a.frame_token, b.frame_token) and torch.equal(a.status, b.status)
-    assert torch.equal(a.path.sum(-1).int(), a.durations)
-    assert int(a.status.abs().sum()) == 0
+    assert torch.equal(a.status, b.status) and int(a.status.abs().sum()) == 0
+    assert torch.equal(a.path.sum(-1).int(), a.durations) and torch.equal(b.path.sum(-1).int(), b.durations)
+    assert torch.equal(a.durations.sum(-1), t_y.to(DEV)) and torch.equal(b.durations.sum(-1), t_y.to(DEV))
+    valid = b.frame_token >= 0
+    assert torch.equal(valid, a.frame_token >= 0)
+    agree = float((a.frame_token[valid] == b.frame_token[valid]).float().mean())
+    assert agree > 0.999
+    if F == 128 and Tx > 128:
+        assert torch.equal(a.path, b.path) and torch.equal(a.frame_token, b.frame_token)
 
 
-def test_overlapped_pipeline_long_text_split_m():
-    """Tx = 300 (three M-tile CTAs per utterance, flags count to 3) through the overlapped pipeline == serial."""
+def test_long_text_takes_the_serial_form():
+    """Tx = 300 (three M-tiles: split-M log-prior kernel + MAS kernel): fused_impl = 0 and 1 are the same code path."""
     from face_gan_tts_b200 import _lib
 
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=8, F=80, Tx=300, Ty=1000, seed=21, tx_lo=100, ty_lo=400)
@@ -259,36 +312,52 @@ def test_overlapped_pipeline_long_text_split_m():
     assert int(a.status.abs().sum()) == 0 and torch.equal(a.path.sum(-1).int(), a.durations)
 
 
-@pytest.mark.parametrize("F", [80, 128])
-def test_overlapped_pipeline_soak(F):
-    """300 back-to-back overlapped calls over rotating inputs and workspaces, no host sync in between: every result
-    must equal the serial pipeline's.  Guards the cross-kernel protocol (bulk-store completion -> proxy fence ->
-    release flag -> acquire -> TMA load; flag reset by the next call's memset; done flags -> path writers)."""
-    from face_gan_tts_b200 import _lib
-
+@pytest.mark.parametrize("F,Tx", [(80, 190), (128, 128)])
+def test_fused_kernel_soak(F, Tx):
+    """300 back-to-back fused calls over rotating inputs, no host sync in between (programmatic dependent launch lets
+    call i + 1 be placed while call i is still running): every result must equal the first, checked result of its input."""
     B, nset = 32, 3
-    sets = []
+    sets, want = [], []
     for k in range(nset):
-        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=190, Ty=1000, seed=100 + k)
-        sets.append((mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV)))
-    prev = _lib.set_option("fused_impl", 1)
-    try:
-        want = [fgt.log_prior_maximum_path(*s_, path_dtype=torch.float32) for s_ in sets]
-        torch.cuda.synchronize()
-    finally:
-        _lib.set_option("fused_impl", prev)
+        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=1000, seed=100 + k)
+        s_ = (mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV))
+        res, dump = _fused_with_value_dump(*s_, path_dtype=torch.float32)
+        own = _reference_mas(torch.nan_to_num(dump).cpu().numpy(), t_x.numpy(), t_y.numpy())
+        np.testing.assert_array_equal(res.path.cpu().numpy().astype(np.int32), own)
+        sets.append(s_)
+        want.append((res.durations.clone(), res.frame_token.clone(), res.path.clone()))
     bad = torch.zeros((), dtype=torch.int64, device=DEV)
     for i in range(300):
         r = fgt.log_prior_maximum_path(*sets[i % nset], path_dtype=torch.float32)
         w = want[i % nset]
-        bad += (r.durations != w.durations).sum() + (r.frame_token != w.frame_token).sum() + (r.path != w.path).sum()
+        bad += (r.durations != w[0]).sum() + (r.frame_token != w[1]).sum() + (r.path != w[2]).sum()
     torch.cuda.synchronize()
     assert int(bad) == 0
 
 
-def test_overlapped_pipeline_rejects_bad_items_without_hanging():
-    """t_x > t_y is undefined in the reference (core.pyx:34); here the item is rejected, its outputs are zero, and the
-    producer/consumer flag protocol of the overlapped pipeline still terminates."""
+@pytest.mark.parametrize("n_sms", [1, 32, 116, 148])
+def test_fused_call_completes_beside_a_foreign_kernel_holding_sms(n_sms):
+    """The alignment is ONE kernel whose CTAs wait only for each other's warps (never for another launch), so a foreign
+    kernel that keeps SMs busy on another stream (NCCL, the decoder of a real training step) can delay it but not
+    starve it: with 1 / 32 / 116 / all 148 SMs held for ~2 ms the call still completes with the right answer."""
+    from face_gan_tts_b200 import _lib
+
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=32, F=80, Tx=190, Ty=1000, seed=9)
+    args = (mu_x.to(DEV), y.to(DEV), t_x.to(DEV), t_y.to(DEV))
+    want = fgt.log_prior_maximum_path(*args, path_dtype=torch.float32)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(DEV)
+    with torch.cuda.stream(side):
+        _lib.check(_lib.lib().mas_b200_debug_occupy_sms(n_sms, 4_000_000, side.cuda_stream), "mas_b200_debug_occupy_sms")
+    for _ in range(3):
+        got = fgt.log_prior_maximum_path(*args, path_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert torch.equal(got.path, want.path) and torch.equal(got.durations, want.durations)
+    assert torch.equal(got.frame_token, want.frame_token) and int(got.status.abs().sum()) == 0
+
+
+def test_fused_call_rejects_bad_items():
+    """t_x > t_y is undefined in the reference (core.pyx:34); here the item is rejected and its outputs are zero."""
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=4, F=80, Tx=61, Ty=200, seed=5, tx_lo=21, ty_lo=90)
     t_x = t_x.clone(); t_y = t_y.clone()
     t_x[1] = 61; t_y[1] = 40                       # t_x > t_y

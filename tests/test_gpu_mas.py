@@ -41,10 +41,15 @@ class options:
             _lib.set_option(k, v)
 
 
+_REF_CORE = oracle.reference_core("asis")      # the reference's own core.pyx, compiled by oracle/build_ref.py (travels in oracle/_ref)
+
+
 def oracle_paths(value_np, t_x, t_y):
+    """Paths of the reference MAS: the compiled reference itself when it is on this box, else the C restatement that
+    tests/test_oracle.py pins to it."""
     p = np.zeros(value_np.shape, np.int32)
-    oracle.maximum_path_c(p, np.ascontiguousarray(value_np, np.float32).copy(), np.asarray(t_x, np.int32),
-                          np.asarray(t_y, np.int32))
+    fn = _REF_CORE.maximum_path_c if _REF_CORE is not None else oracle.maximum_path_c
+    fn(p, np.ascontiguousarray(value_np, np.float32).copy(), np.asarray(t_x, np.int32), np.asarray(t_y, np.int32))
     return p
 
 
@@ -161,12 +166,20 @@ def test_rejected_items_are_reported_not_undefined():
         fgt.align(v, torch.tensor([6, 5, 4], dtype=torch.int32), torch.tensor([8, 3, 8], dtype=torch.int32), check=True)
 
 
-@pytest.mark.parametrize("seed", range(6))
+_EDGE_TX = [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257]      # lane / warp / M-tile / CTA-pass edges
+_EDGE_TY = [1, 2, 31, 32, 33, 63, 64, 65, 255, 256, 257]          # 32-frame tile edges
+
+
+@pytest.mark.parametrize("seed", range(120))
 def test_random_fuzz_vs_oracle(seed):
     rng = np.random.default_rng(100 + seed)
     B = int(rng.integers(1, 9))
-    Tx = int(rng.integers(1, 300))
-    Ty = int(rng.integers(Tx, 700))
+    if seed % 2:                                                    # sizes on tile edges
+        Tx = _EDGE_TX[(seed // 2) % len(_EDGE_TX)]
+        Ty = max(Tx, _EDGE_TY[(seed // 2 + seed // 22) % len(_EDGE_TY)]) + int(rng.integers(0, 2)) * 32 * int(rng.integers(0, 8))
+    else:
+        Tx = int(rng.integers(1, 300))
+        Ty = int(rng.integers(Tx, 700))
     kind = seed % 3
     if kind == 0:
         v = rng.standard_normal((B, Tx, Ty)).astype(np.float32)
