@@ -18,7 +18,9 @@
 //    10     TMA loads (mu_x block, y tiles) + tcgen05.mma issue
 //    11, 14 backtrack helpers: per-tile transfer tables in the shadow of the DP
 //    12, 13 DP warps (text rows 0..127 / 128..255): alone with one epilogue warp on partitions 0 / 1, highest ids there
-//    4, 5, 8, 9  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
+//    9      dense path (when requested): streams the all-zero [Tx,Ty] block out with bulk copies from an 8 KB zero
+//           buffer while the search runs -- the result only adds ~t_y ones to it (written by all warps in the tail)
+//    4, 5, 8  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
 // TMEM lane m of M-tile mt holds text row x = 128*mt + 4*(m & 31) + (m >> 5): the epilogue thread of that lane then owns
 // ring slot (m >> 5) * 32W + 32*mt + (m & 31) -- the lane-major permuted layout of mas_common.cuh -- so its eight 16-byte
 // stores are bank-conflict free, M-tile mt is exactly DP warp mt's rows, and each (stage, M-tile) has its own
@@ -50,6 +52,8 @@ constexpr int kWarpMma = 10;
 constexpr int kWarpHelpA = 11;
 constexpr int kWarpDp = 12;                  // 12, 13
 constexpr int kWarpHelpB = 14;
+constexpr int kWarpZero = 9;                 // dense-path zero fill
+constexpr uint32_t kZeroBytes = 8192;        // zero buffer = size of one bulk store
 
 struct FusedParams {
     MasParams mas;       // t_x, t_y, B, Tx, Ty, neg, ring_stages, start, dur, frame_token, status, path, path_dtype, dbg
@@ -59,7 +63,7 @@ struct FusedParams {
 };
 
 // Shared-memory carve-up (bytes from a 1024-aligned base):
-//   [ring: NS value tiles][halo rings][raw y: 2][hi: 2][lo: 2][ysq partials][mbarriers][flags][direction words + transfer tables]
+//   [ring: NS value tiles][halo rings][raw y: 2][hi: 2][lo: 2][ysq partials][mbarriers][flags][zero buffer][direction words + transfer tables]
 // The [F][Tx] staging of mu_x for the prologue aliases the front (ring, halo, possibly raw).
 template <int KS, int W>
 struct FusedSmem {
@@ -76,7 +80,8 @@ struct FusedSmem {
     __host__ __device__ static constexpr size_t off_part(int ns) { return off_lo(ns) + 2 * kOp; }             // [2][2][32] f32
     __host__ __device__ static constexpr size_t off_bars(int ns) { return off_part(ns) + 2 * 2 * 32 * 4; }    // 16 + 2*ns mbarriers (room for 4*ns)
     __host__ __device__ static constexpr size_t off_flags(int ns) { return off_bars(ns) + 8 * (size_t)(16 + 4 * ns); }
-    __host__ __device__ static constexpr size_t off_bits(int ns) { return ((off_flags(ns) + 128 + 127) / 128) * 128; }
+    __host__ __device__ static constexpr size_t off_zero(int ns) { return ((off_flags(ns) + 128 + 127) / 128) * 128; }
+    __host__ __device__ static constexpr size_t off_bits(int ns) { return off_zero(ns) + kZeroBytes; }
     // direction words (4 B) + transfer table (1 B) per row and tile
     __host__ __device__ static constexpr size_t total(int ns, int ntiles) { return off_bits(ns) + (size_t)5 * ntiles * XP; }
 };
@@ -136,6 +141,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hprog + 8);
     int *eprog = hprog + 12;                                                              // [W][4] epilogue progress flags
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem_raw + FS::off_bits(NS));
+    unsigned char *zbuf = smem_raw + FS::off_zero(NS);
     // prologue staging of mu_x, transposed for the TMEM lane order: element (f, x) with x = 128*mt + 4*l + q at
     //   ((f*W + mt)*4 + q)*32 + (l ^ 8q)      -- coalesced global reads land conflict-free, and so do the readers
     float *mu_s = reinterpret_cast<float *>(smem_raw);
@@ -206,6 +212,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         mbar_fence_init();
     }
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
+    if (P.path != nullptr) {
+        for (uint32_t i = tid; i < kZeroBytes / 16; i += kFusedThreads) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();                            // generic-proxy zeros -> visible to the bulk stores reading them
+    }
     {
         // x = 32j + lane = 128*mt + 4*l + q with mt = j >> 2, l = 8*(j & 3) + (lane >> 2), q = lane & 3:
         //   position ((f*W + mt)*4 + q)*32 + (l ^ 8q) = f*W*128 + mt*128 + [q*32 + (lane >> 2) + ((8*(j & 3)) ^ 8q)]
@@ -464,6 +474,22 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 #if MASB200_FUSED_PROF
         if (dbg && tid == 0) { dbg[20] = w_dfull; dbg[21] = w_rempty; }
 #endif
+    } else if (warp == kWarpZero) {
+        // ======================= dense path, part 1: the all-zero [Tx,Ty] block, in the shadow of the search =======================
+        if (P.path != nullptr) {
+            unsigned char *dst = reinterpret_cast<unsigned char *>(P.path) + (size_t)b * P.Tx * P.Ty * 4;
+            const size_t total = (size_t)P.Tx * P.Ty * 4;                      // Ty % 4 == 0: a multiple of 16 bytes
+            if (elect_one()) {
+                for (size_t off = 0; off < total; off += kZeroBytes) {
+                    const uint32_t n = (uint32_t)(total - off < kZeroBytes ? total - off : kZeroBytes);
+                    tma_bulk_store_1d(dst + off, zbuf, n);
+                    tma_store_commit();
+                }
+                tma_store_wait_all();                                          // the zeros are in memory ...
+                asm volatile("fence.proxy.async;" ::: "memory");               // ... and ordered before the generic-proxy ones
+            }
+            __syncwarp();
+        }
     } else if (warp == kWarpHelpA || warp == kWarpHelpB) {
         // ======================= backtrack helpers: transfer tables behind the LAST active DP warp =======================
         const int *flag_last = hprog + (w_act - 1);
@@ -583,7 +609,15 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg, heads ? hd : nullptr);
     if (dbg && tid == 0) dbg[5] = clock64();
     mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg, heads);
-    write_path_any(P, b, start_b, dur_b, tid, kFusedThreads);
+    if (P.path != nullptr) {
+        // dense path, part 2: token x owns frames [tok[x], tok[x+1]) of row x -- one warp per token, a contiguous run of ones
+        uint32_t *pb = reinterpret_cast<uint32_t *>(P.path) + (size_t)b * P.Tx * P.Ty;
+        const uint32_t one = P.path_dtype == MAS_B200_PATH_F32 ? 0x3f800000u : 1u;
+        for (int x = warp; x < t_x; x += kFusedWarps) {
+            const int s0 = tok[x], e0 = (x + 1 < t_x) ? tok[x + 1] : t_y;
+            for (int t = s0 + lane; t < e0; t += 32) pb[(size_t)x * P.Ty + t] = one;
+        }
+    }
     if (dbg && tid == 0) {
         dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y;
         long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[13] = t;
@@ -697,10 +731,10 @@ int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const
         const unsigned lo = (unsigned)option("mas_debug_ptr_lo"), hi = (unsigned)option("mas_debug_ptr_hi");
         P.dbg = reinterpret_cast<long long *>(((unsigned long long)hi << 32) | lo);
     }
-    // dense path: in-kernel for batches of several waves (the writes of finished CTAs overlap the others' search),
-    // a separate streaming kernel on all SMs otherwise
+    // dense path: written by the kernel itself (zeros streamed out in the shadow of the search, ones in the tail) unless
+    // the buffer is not 16-byte aligned or option mas_fused_path_write = 0 asks for the separate expansion kernel
     int fuse = option("mas_fused_path_write");
-    if (fuse < 0) fuse = (B >= 2 * di.sm_count) ? 1 : 0;
+    fuse = (fuse != 0 && (reinterpret_cast<uintptr_t>(path) & 15) == 0) ? 1 : 0;
     const bool want_path = path_dtype != MAS_B200_PATH_NONE;
     P.path = (want_path && fuse) ? path : nullptr;
     P.path_dtype = (want_path && fuse) ? path_dtype : MAS_B200_PATH_NONE;
