@@ -10,14 +10,18 @@ path over one batch: mu_x, y, lengths -> dense fp32 path + durations + frame->to
 Metric: alignment cells/s = B*T_text*T_mel / time (padded cells), whole job over all GPUs.
 
   value     inputs already resident in HBM; K steps back to back on one stream between two
-            CUDA events; the steps rotate over NSETS independent buffer sets whose footprint
-            exceeds L2, so no step finds its inputs in cache.
-  e2e       the same step through the public API with HOST buffers: every step copies
-            mu_x, y and the lengths from pinned host memory, runs the fused call, and reads
-            durations + frame->token index back to pinned host memory (`e2e`), or additionally
-            the whole dense path (`e2e_dense_path`).
-  roofline  dominant kernel (by measured time), algorithmic bytes / its CUDA-event time
-            against MEASURED_PEAKS.json hbm_gbs.
+            CUDA events; a step is ONE kernel (lp_mas_fused_kernel: tcgen05 log-prior -> shared-memory
+            ring -> MAS -> backtrack -> dense path); the steps rotate over NSETS independent buffer
+            sets whose footprint exceeds L2, so no step finds its inputs in cache.
+  e2e       the same step through the public API with HOST buffers: every step moves the batch from
+            pinned host memory (packed ragged form, one copy-engine transfer + device unpack), runs
+            the fused call, and reads durations + frame->token index back to pinned host memory
+            (`e2e`); `e2e_padded_copy` = padded tensors with plain copies, `e2e_dense_path` = also
+            the whole dense path back.
+  roofline  the step's kernel: algorithmic bytes / its CUDA-event time against MEASURED_PEAKS.json
+            hbm_gbs, on padded and on valid bytes, `traffic` from the committed ncu capture.
+  sweep     the throughput-regime workloads (configs[3] B=64 512x4096, configs[4] B=1024), each with
+            its own roofline.       path_agreement   % of frames agreeing with torch fp32 -> core.pyx.
   cpu_baseline  the reference's own implementation (oracle/_ref: core.pyx as shipped, serial)
             + the torch log-prior expression on this box's host cores, same batch.
   --impl reference  times that CPU path as its own arm (rank 0 only under torchrun).
@@ -25,7 +29,8 @@ Metric: alignment cells/s = B*T_text*T_mel / time (padded cells), whole job over
 Multi-GPU (torchrun, one rank per GPU): utterances are independent, so each rank aligns its
 own 32-utterance shard (weak scaling, no data-path collective); the per-token durations are
 returned to every rank with one asynchronous NCCL all-gather per step (loss bookkeeping),
-overlapped with the next step and completed inside the timed region.
+overlapped with the next step and completed inside the timed region.  `strong_scaling_configs4`
+adds BASELINE configs[4]: a fixed total batch (64..1024) split over the ranks.
 """
 import argparse
 import json
@@ -56,24 +61,6 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of the same shape (profiles/r1_ncu_full_*.json); None if there is none."""
-    name = {"mas_forward_backtrack": "r1_ncu_full_mas_forward_B32.json"}.get(kernel)
-    if not name:
-        return None
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", name)))
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            v, u = d[k]
-            tot += float(v.replace(",", "")) * scale[u]
-        return tot
-    except Exception:
-        return None
 
 
 class ClockSampler:
@@ -242,6 +229,162 @@ def time_compute_loss_block(dev, out_size=128):
 
 
 # ----------------------------------------------------------------------------- CUDA arm
+def bind_rank_to_cores(local_rank, local_world):
+    """Give every rank of the node its own slice of the host cores BEFORE it allocates pinned memory / starts copy
+    threads: 8 ranks x pinned H2D on one host otherwise share (and migrate between) the same cores."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, local_world))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, len(mine)))
+        return len(mine)
+    except Exception:
+        return None
+
+
+def cuda_time(stream, dev, fn, reps, warm=3):
+    """ms per call of fn(i): CUDA events on the launching stream, synchronised on both sides."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize(dev)
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for i in range(reps):
+        fn(warm + i)
+    b_.record(stream)
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b_) / reps
+
+
+def ncu_dram_bytes(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed `ncu --set full` summary
+    (profiles/<name>.json, written by scripts/tools/ncu_summary.py); None if it is not there."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[k]
+            tot += float(str(v).replace(",", "")) * scale[u]
+        return tot
+    except Exception:
+        return None
+
+
+def path_agreement(dev, n_feats):
+    """north_star: 'end-to-end path agreement is reported against the reference on the same synthetic mu_x/y' --
+    % of valid frames of the bench batch whose token agrees with (torch fp32 log-prior -> the reference's compiled
+    core.pyx MAS); the C restatement stands in when the compiled reference is not on the box."""
+    import oracle
+    import face_gan_tts_b200 as fgt
+    from face_gan_tts_b200 import synthetic
+
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, n_feats, TX, TY, seed=1234)
+    mu_d, y_d = mu_x.to(dev), y.to(dev)
+    res = fgt.log_prior_maximum_path(mu_d, y_d, t_x, t_y, dense_path=False)
+    ref_lp = oracle.log_prior_reference(mu_d, y_d).cpu().numpy()
+    core = oracle.reference_core("asis")
+    paths = np.zeros(ref_lp.shape, np.int32)
+    (core or oracle).maximum_path_c(paths, ref_lp.copy(), t_x.numpy(), t_y.numpy())
+    _, ref_ft = oracle.durations_and_frame_token(paths)
+    ft = res.frame_token.cpu().numpy()
+    valid = ref_ft >= 0
+    return {"n_feats": n_feats, "frames": int(valid.sum()), "agree_pct": float((ft[valid] == ref_ft[valid]).mean() * 100.0),
+            "against": "torch fp32 log-prior -> " + ("reference core.pyx (compiled)" if core is not None else "C restatement of core.pyx")}
+
+
+def run_sweep(dev, peak, K):
+    """Throughput-regime workloads of BASELINE.json (configs[3], configs[4] at one GPU), each CUDA-event timed on buffers
+    larger than L2, with the roofline on padded cells, on VALID cells, and -- where a capture is committed -- on the
+    DRAM bytes ncu saw."""
+    import face_gan_tts_b200 as fgt
+    from face_gan_tts_b200 import _lib, synthetic
+
+    L = _lib.lib()
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+    out = []
+
+    def entry(name, form, Bn, Fn, Tx, Ty, ms, bytes_padded, bytes_valid, valid_cells, ncu=None, note=None):
+        cells = Bn * Tx * Ty
+        e = {"workload": name, "form": form, "B": Bn, "n_feats": Fn, "T_text": Tx, "T_mel": Ty, "ms": ms,
+             "cells_per_s": cells / (ms * 1e-3), "valid_cells_per_s": valid_cells / (ms * 1e-3),
+             "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s",
+                          "achieved": bytes_padded / (ms * 1e-3) / 1e9, "frac": bytes_padded / (ms * 1e-3) / 1e9 / peak,
+                          "achieved_valid": bytes_valid / (ms * 1e-3) / 1e9,
+                          "frac_valid": bytes_valid / (ms * 1e-3) / 1e9 / peak}}
+        tr = ncu_dram_bytes(ncu) if ncu else None
+        e["roofline"]["traffic"] = tr
+        if tr:
+            e["roofline"]["frac_dram"] = tr / (ms * 1e-3) / 1e9 / peak
+        if note:
+            e["note"] = note
+        out.append(e)
+
+    reps = max(5, min(K, 20))
+    # ---- configs[4] at one GPU: B = 1024 of the LRS2 shape
+    Bn, Fn, Tx, Ty = 1024, F, TX, TY
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(Bn, Fn, Tx, Ty, seed=99)
+    mu_d, y_d, tx_d, ty_d = mu_x.to(dev), y.to(dev), t_x.to(dev), t_y.to(dev)
+    vc = int((t_x.long() * t_y.long()).sum())
+    in_pad = 4 * Fn * Bn * (Tx + Ty)
+    in_val = 4 * Fn * int((t_x.long() + t_y.long()).sum())
+    io_small = 4 * Bn * (Tx + Ty)
+    for dense in (True, False):
+        plan = fgt.AlignmentPlan(Bn, Fn, Tx, Ty, device=dev, dense_path=dense)
+        ms = cuda_time(stream, dev, lambda i: plan(mu_d, y_d, tx_d, ty_d), reps)
+        pathb = 4 * Bn * Tx * Ty if dense else 0
+        entry("configs[4] @1 GPU: LRS2 shape, B=1024", "fused kernel, " + ("dense fp32 path" if dense else "index outputs only"),
+              Bn, Fn, Tx, Ty, ms, in_pad + pathb + io_small, in_val + pathb + io_small, vc,
+              ncu="r2_ncu_fused_B1024.json" if dense else None,
+              note="algorithmic bytes = 4F(Tx+Ty) inputs + durations/frame_token" + (" + 4 B/cell dense path" if dense else "") +
+                   "; the [Tx,Ty] value matrix never exists in memory")
+        del plan
+    value = fgt.log_prior(mu_d, y_d)
+    ws_bytes = L.mas_b200_workspace_bytes(Bn, Tx, Ty)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    dur = torch.empty((Bn, Tx), dtype=torch.int32, device=dev)
+    ft = torch.empty((Bn, Ty), dtype=torch.int32, device=dev)
+    st = torch.empty((Bn,), dtype=torch.int32, device=dev)
+
+    def mas_only(i):
+        _lib.check(L.mas_b200_maximum_path(value.data_ptr(), Tx * Ty, Ty, tx_d.data_ptr(), ty_d.data_ptr(), Bn, Tx, Ty, -1e9,
+                                           None, _lib.PATH_NONE, dur.data_ptr(), ft.data_ptr(), st.data_ptr(), ws.data_ptr(),
+                                           ws_bytes, sp), "maximum_path")
+
+    ms = cuda_time(stream, dev, mas_only, reps)
+    entry("configs[4] @1 GPU: LRS2 shape, B=1024", "maximum_path alone (value matrix resident in HBM), index outputs", Bn, Fn, Tx, Ty,
+          ms, 4 * Bn * Tx * Ty + io_small, 4 * vc + io_small, vc, ncu="r2_ncu_mas_forward_B1024.json",
+          note="algorithmic bytes = 4 B per value cell read; cells outside [0,t_x)x[0,t_y) are never read")
+    del value, ws, mu_d, y_d
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: long-utterance stress, value matrix streamed (B=64, 512 x 4096)
+    Bn, Tx, Ty = 64, 512, 4096
+    v, t_x, t_y = synthetic.mas_value(Bn, Tx, Ty, seed=5, tx_lo=256, ty_lo=2048)
+    v_d, tx_d, ty_d = v.to(dev), t_x.to(dev), t_y.to(dev)
+    vc = int((t_x.long() * t_y.long()).sum())
+    for dense in (True, False):
+        ms = cuda_time(stream, dev, lambda i: fgt.align(v_d, tx_d, ty_d, dense_path=dense), reps)
+        pathb = 4 * Bn * Tx * Ty if dense else 0
+        entry("configs[3]: long-utterance stress", "maximum_path(value) streamed, " + ("dense fp32 path" if dense else "index outputs only"),
+              Bn, 0, Tx, Ty, ms, 4 * Bn * Tx * Ty + pathb, 4 * vc + pathb, vc,
+              note="direction bits (262 KB/utterance) in L2-resident global scratch; host time of the functional API included")
+    del v_d
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(Bn, F, Tx, Ty, seed=6, tx_lo=256, ty_lo=2048)
+    mu_d, y_d, tx_d, ty_d = mu_x.to(dev), y.to(dev), t_x.to(dev), t_y.to(dev)
+    vc = int((t_x.long() * t_y.long()).sum())
+    plan = fgt.AlignmentPlan(Bn, F, Tx, Ty, device=dev, dense_path=True)
+    ms = cuda_time(stream, dev, lambda i: plan(mu_d, y_d, tx_d, ty_d), reps)
+    entry("configs[3]: long-utterance stress", "log-prior + MAS, serial form (Tx > 256: split-M tcgen05 log-prior -> HBM -> MAS -> expand), dense",
+          Bn, F, Tx, Ty, ms, 4 * F * Bn * (Tx + Ty) + 4 * Bn * Tx * Ty, 4 * F * int((t_x.long() + t_y.long()).sum()) + 4 * Bn * Tx * Ty, vc,
+          note="algorithmic bytes as for the fused form (6.0 B/cell class); the serial form really moves 3 x 4 B/cell")
+    del plan, mu_d, y_d
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_cuda(args):
     import face_gan_tts_b200 as fgt
     from face_gan_tts_b200 import _lib, sharding, synthetic
@@ -249,14 +392,15 @@ def run_cuda(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_cores = bind_rank_to_cores(local_rank, local_world) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the only collective is a 24 KB all-gather that runs beside the next step's kernels: one channel (one CTA)
-        # is plenty and keeps NCCL off the SMs the two co-resident alignment kernels need
+        # the only collective is a 24 KB all-gather that runs beside the next step's kernel: one channel (one CTA) is plenty
         os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("MAS_B200_NCCL_CHANNELS", "1"))
         os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
@@ -264,7 +408,7 @@ def run_cuda(args):
     dev = torch.device("cuda", local_rank)
     L = _lib.lib()
     K, W = args.steps, max(args.warmup, 3)
-    NSETS = 6      # ~61 MB per set (inputs, value scratch, dense path): 6 sets = 366 MB >> 126 MB L2
+    NSETS = 6      # ~37 MB per set (inputs + dense path): 6 sets = 220 MB > 126 MB L2
 
     # ---- device-resident buffer sets (each rank its own utterances: independent shards)
     sets = []
@@ -278,8 +422,6 @@ def run_cuda(args):
         sets.append(d)
     ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, TX, TY)
     wss = [torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) for _ in range(NSETS)]
-    for w_ in wss:      # persistent workspaces, cleared once: the fused calls then skip their per-call flag memset
-        _lib.check(L.mas_b200_fused_workspace_prepare(w_.data_ptr(), ws_bytes, B, F, TX, TY, None), "workspace_prepare")
     torch.cuda.synchronize(dev)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
@@ -289,14 +431,12 @@ def run_cuda(args):
             d["mu"].data_ptr(), d["y"].data_ptr(), d["tx"].data_ptr(), d["ty"].data_ptr(), B, F, TX, TY, -1e9,
             d["path"].data_ptr() if dense else None, _lib.PATH_F32 if dense else _lib.PATH_NONE,
             d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), ws.data_ptr(), ws_bytes,
-            _lib.LP_AUTO | _lib.WS_PREPARED, sp if on is None else on.cuda_stream)
+            _lib.LP_AUTO, sp if on is None else on.cuda_stream)
         _lib.check(rc, "mas_b200_log_prior_maximum_path")
 
     graphs = [None]      # multi-GPU: CUDA graphs of the fused call, one per buffer set (see below)
-
     gathered = [torch.empty((world * B, TX), dtype=torch.int32, device=dev) for _ in range(2)] if dist else None
     comm_stream = torch.cuda.Stream(dev) if dist else None
-
     step_done = [torch.cuda.Event() for _ in range(4)] if dist else None
 
     def step(i):
@@ -322,9 +462,8 @@ def run_cuda(args):
         step(i)
     barrier()
     if dist and not args.no_graph:
-        # With the NCCL enqueue beside it, one step costs ~56 us of host time per rank -- as long as the step itself --
-        # so the fused call (memset, fork, two kernels, join: captured as-is, scripts/graph_probe.py) is replayed
-        # from a CUDA graph per buffer set (5 us of host time); the all-gather stays an eager NCCL call.
+        # With the NCCL enqueue beside it a step costs more host time than GPU time, so the fused call (ONE kernel node)
+        # is replayed from a CUDA graph per buffer set; the all-gather stays an eager NCCL call on its own stream.
         try:
             cap = torch.cuda.Stream(dev)
             cap.wait_stream(stream)
@@ -366,56 +505,90 @@ def run_cuda(args):
     ms_step = ms_total / K
     value = world * CELLS / (ms_step * 1e-3)
 
-    # ---- per-kernel breakdown (rank 0): CUDA events around each piece on its own stream
-    def time_piece(fn, reps=K):
-        for i in range(3):
-            fn(i)
-        torch.cuda.synchronize(dev)
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for i in range(reps):
-            fn(3 + i)
-        b_.record(stream)
-        torch.cuda.synchronize(dev)
-        return a.elapsed_time(b_) / reps
+    # ---- configs[4]: strong scaling of a fixed total batch over the ranks (every rank: B_total / world utterances of the
+    # LRS2 shape + the asynchronous all-gather of the durations), device-timed, max over ranks
+    strong = None
+    if dist:
+        strong = []
+        for b_total in (64, 128, 256, 512, 1024):
+            if b_total % world:
+                continue
+            bl = b_total // world
+            mu_x, y, t_x, t_y = synthetic.lrs2_batch(bl, F, TX, TY, seed=777 + rank)
+            args_d = (mu_x.to(dev), y.to(dev), t_x.to(dev), t_y.to(dev))
+            plan = fgt.AlignmentPlan(bl, F, TX, TY, device=dev, dense_path=True)
+            gat = torch.empty((b_total, TX), dtype=torch.int32, device=dev)
 
-    # ---- e2e (every rank): pinned HOST buffers in, results back to pinned host memory, every step, inside the
-    # timed region.  Software-pipelined like a training loop: the H2D of step i+1 runs on a copy stream while
-    # step i computes, and the host consumes the result of step i-1 (event sync) while step i is in flight.
+            def sstep(i):
+                r = plan(*args_d)
+                comm_stream.wait_stream(stream)
+                with torch.cuda.stream(comm_stream):
+                    sharding.all_gather_durations_into(gat, r.durations)
+                stream.wait_stream(comm_stream)      # the next step overwrites plan.durations
+
+            for i in range(3):
+                sstep(i)
+            barrier()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a_.record(stream)
+            for i in range(reps):
+                sstep(i)
+            b_.record(stream)
+            barrier()
+            t = torch.tensor([a_.elapsed_time(b_) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            strong.append({"B_total": b_total, "B_per_gpu": bl, "ms_per_step": float(t.item()),
+                           "cells_per_s": b_total * TX * TY / (float(t.item()) * 1e-3)})
+            del plan, gat, args_d
+        torch.cuda.empty_cache()
+
+    # ---- e2e (every rank): HOST buffers in, results back to pinned host memory, every step, inside the timed region.
+    # Software-pipelined like a training loop: the H2D of step i+1 runs on a copy stream while step i computes, and the
+    # host consumes the result of step i-1 (event sync) while step i is in flight.
+    #   packed   the batch arrives as a collate that does not pad produces it (fgt.pack_batch layout: lengths + the valid
+    #            part of every row, one pinned buffer): ONE copy-engine transfer + the device unpack kernel
+    #   padded   the padded pinned tensors, four cudaMemcpyAsync
     NH = 3
     host_in = [[t.pin_memory() for t in synthetic.lrs2_batch(B, F, TX, TY, seed=4321 + 100 * rank + k)] for k in range(NH)]
+    host_packed = [fgt.pack_batch(*h) for h in host_in]          # outside the timed region: this IS the input format
+    staging = [torch.empty((max(p.numel() for p in host_packed),), dtype=torch.uint8, device=dev) for _ in range(2)]
     dur_h = [torch.empty((B, TX), dtype=torch.int32).pin_memory() for _ in range(2)]
     ft_h = [torch.empty((B, TY), dtype=torch.int32).pin_memory() for _ in range(2)]
     path_h = [torch.empty((B, TX, TY), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(dev)
     plans = [fgt.AlignmentPlan(B, F, TX, TY, device=dev, dense_path=True) for _ in range(2)]
+    plans_idx = [fgt.AlignmentPlan(B, F, TX, TY, device=dev, dense_path=False) for _ in range(2)]
 
-    def run_e2e(nsteps, dense_d2h, ragged=True):
+    def run_e2e(nsteps, dense_d2h, mode):
         h2d_done = [torch.cuda.Event() for _ in range(nsteps)]
         res_done = [torch.cuda.Event() for _ in range(2)]
         checksum = 0
 
         def enqueue_h2d(i):
             d = sets[i % NSETS]
-            mu_h, y_h, tx_h, ty_h = host_in[i % NH]
             with torch.cuda.stream(copy_stream):
-                if ragged:
-                    # only the valid [0,t_x) / [0,t_y) part of every row crosses PCIe (zero-copy pull kernel)
-                    fgt.upload_batch(mu_h, y_h, tx_h, ty_h, out=(d["mu"], d["y"], d["tx"], d["ty"]))
+                if mode == "packed":
+                    fgt.upload_packed_batch(host_packed[i % NH], B, F, TX, TY, device=dev, out=(d["mu"], d["y"], d["tx"], d["ty"]),
+                                            staging=staging[i & 1])
                 else:
+                    mu_h, y_h, tx_h, ty_h = host_in[i % NH]
                     d["mu"].copy_(mu_h, non_blocking=True)
                     d["y"].copy_(y_h, non_blocking=True)
                     d["tx"].copy_(tx_h, non_blocking=True)
                     d["ty"].copy_(ty_h, non_blocking=True)
                 h2d_done[i].record(copy_stream)
 
+        pl = plans if dense_d2h else plans_idx
         enqueue_h2d(0)
         for i in range(nsteps):
             if i + 1 < nsteps:
+                if i >= 1:
+                    copy_stream.wait_event(res_done[(i - 1) & 1])      # staging / input set reuse: step i-1 is done with them
                 enqueue_h2d(i + 1)
             d = sets[i % NSETS]
             stream.wait_event(h2d_done[i])
-            res = plans[i & 1](d["mu"], d["y"], d["tx"], d["ty"])          # AlignmentPlan: reusable outputs + workspace
+            res = pl[i & 1](d["mu"], d["y"], d["tx"], d["ty"])          # AlignmentPlan: reusable outputs + workspace
             dur_h[i & 1].copy_(res.durations, non_blocking=True)
             ft_h[i & 1].copy_(res.frame_token, non_blocking=True)
             if dense_d2h:
@@ -427,11 +600,11 @@ def run_cuda(args):
         res_done[(nsteps - 1) & 1].synchronize()
         return checksum
 
-    def time_e2e(dense_d2h, ragged=True):
-        run_e2e(4, dense_d2h, ragged)
+    def time_e2e(dense_d2h, mode):
+        run_e2e(4, dense_d2h, mode)
         barrier()
         t0 = time.perf_counter()
-        run_e2e(K, dense_d2h, ragged)
+        run_e2e(K, dense_d2h, mode)
         torch.cuda.synchronize(dev)
         sec = (time.perf_counter() - t0) / K
         if dist:
@@ -441,26 +614,24 @@ def run_cuda(args):
         return sec
 
     h2d_padded = 4 * F * B * (TX + TY) + 8 * B
-    # bytes the ragged upload actually reads over PCIe, counted from the host batches it copies (mean over the NH sets;
-    # 16-byte granularity along y rows)
-    h2d = int(sum(4 * F * int((t[2].long() + ((t[3].long() + 3) // 4) * 4).sum()) + 8 * B for t in host_in) / NH)
-    # The headline e2e moves the padded tensors with the copy engine (50.6 GB/s, within 1 % run to run).  The ragged
-    # zero-copy upload moves a third fewer bytes but SM-issued PCIe reads reach only 36-41 GB/s and vary box to box
-    # (228-260 us per step measured), so it is reported beside it, not instead of it.
-    sec_e2e = time_e2e(False, ragged=False)
-    sec_e2e_ragged = time_e2e(False, ragged=True)
-    sec_e2e_dense = time_e2e(True, ragged=False)
-    e2e = {"value": world * CELLS / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
-           "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e * 1e3,
-           "result": "durations [B,Tx] + frame->token index [B,Ty] (dense path stays in HBM for mu_y)",
-           "h2d": "cudaMemcpyAsync of the padded pinned tensors (copy engine)",
-           "pipelining": "H2D of step i+1 on a copy stream under step i; host consumes result i-1 while step i runs"}
-    e2e_ragged = {"value": world * CELLS / sec_e2e_ragged, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                  "d2h_bytes_per_step": 4 * B * (TX + TY), "ms_per_step": sec_e2e_ragged * 1e3,
-                  "h2d": "mas_b200_upload_batch: only the valid rows' [0,t_x)/[0,t_y) cross PCIe (zero-copy pull kernel, "
-                         "padding zero-filled on the device)"}
-    e2e_dense = {"value": world * CELLS / sec_e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
-                 "d2h_bytes_per_step": 4 * B * (TX + TY) + 4 * CELLS, "ms_per_step": sec_e2e_dense * 1e3}
+    h2d_packed = int(sum(p.numel() for p in host_packed) / NH)
+    sec_e2e = time_e2e(False, "packed")
+    sec_e2e_padded = time_e2e(False, "padded")
+    sec_e2e_dense = time_e2e(True, "packed")
+    d2h_idx = 4 * B * (TX + TY)
+    e2e = {"value": world * CELLS / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_packed,
+           "d2h_bytes_per_step": d2h_idx, "ms_per_step": sec_e2e * 1e3,
+           "input": "packed ragged batch in pinned host memory (lengths + valid part of every mu_x / y row: what a collate "
+                    "that does not pad produces, fgt.pack_batch layout)",
+           "h2d": "ONE cudaMemcpyAsync (copy engine) + mas_b200_unpack_batch on the device (zero-padded tensors)",
+           "result": "durations [B,Tx] + frame->token index [B,Ty] to pinned host memory (the dense path stays in HBM for mu_y)",
+           "pipelining": "H2D + unpack of step i+1 on a copy stream under step i; host consumes result i-1 while step i runs"}
+    e2e_padded = {"value": world * CELLS / sec_e2e_padded, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
+                  "d2h_bytes_per_step": d2h_idx, "ms_per_step": sec_e2e_padded * 1e3,
+                  "h2d": "cudaMemcpyAsync of the padded pinned tensors (what relocate_input does, face_tts.py:85-89)"}
+    e2e_dense = {"value": world * CELLS / sec_e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d_packed,
+                 "d2h_bytes_per_step": d2h_idx + 4 * CELLS, "ms_per_step": sec_e2e_dense * 1e3,
+                 "result": "as e2e + the dense fp32 path [B,Tx,Ty] copied back (what maximum_path literally returns)"}
 
     out = None
     if rank == 0:
@@ -480,30 +651,47 @@ def run_cuda(args):
                 d["dur"].data_ptr(), d["ft"].data_ptr(), d["status"].data_ptr(), wss[i % NSETS].data_ptr(), mas_ws,
                 sp), "maximum_path")
 
+        def serial_form(i):
+            prev = _lib.set_option("fused_impl", 1)
+            try:
+                fused(sets[i % NSETS], wss[i % NSETS])
+            finally:
+                _lib.set_option("fused_impl", prev)
+
         for i in range(NSETS):
             lp_only(i)
-        t_lp = time_piece(lp_only)
-        t_mas = time_piece(lambda i: mas_only(i, False))
-        t_mas_dense = time_piece(lambda i: mas_only(i, True))
-        t_expand = max(t_mas_dense - t_mas, 0.0)
+        t_fused = cuda_time(stream, dev, lambda i: fused(sets[i % NSETS], wss[i % NSETS], True), K)
+        t_fused_idx = cuda_time(stream, dev, lambda i: fused(sets[i % NSETS], wss[i % NSETS], False), K)
+        t_serial = cuda_time(stream, dev, serial_form, K)
+        t_lp = cuda_time(stream, dev, lp_only, K)
+        t_mas = cuda_time(stream, dev, lambda i: mas_only(i, False), K)
+        t_mas_dense = cuda_time(stream, dev, lambda i: mas_only(i, True), K)
         valid_cells = int(sum((d["tx"].long() * d["ty"].long()).sum().item() for d in sets) / NSETS)
-        kernels = {
-            "log_prior": {"ms": t_lp, "algorithmic_bytes": 4 * F * B * (TX + TY) + 4 * CELLS},
-            "mas_forward_backtrack": {"ms": t_mas, "algorithmic_bytes": 4 * CELLS},
-            "path_expand": {"ms": t_expand, "algorithmic_bytes": 4 * CELLS},
-        }
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        valid_in = int(sum((d["tx"].long() + d["ty"].long()).sum().item() for d in sets) / NSETS) * 4 * F
         peak, peak_src = load_peaks()
-        achieved = kernels[dom]["algorithmic_bytes"] / (kernels[dom]["ms"] * 1e-3) / 1e9
-        step_bytes = 4 * F * B * (TX + TY) + 4 * CELLS        # fused algorithmic traffic: inputs + dense path
+        # dominant (only) kernel of the step: lp_mas_fused_kernel.  Algorithmic bytes (fused form):
+        # 4F(Tx+Ty) per utterance in + 4 B/cell dense path out (+ the two index outputs); the value matrix costs nothing.
+        step_bytes = 4 * F * B * (TX + TY) + 4 * CELLS + 4 * B * (TX + TY)
+        step_bytes_valid = valid_in + 4 * CELLS + 4 * B * (TX + TY)
+        achieved = step_bytes / (t_fused * 1e-3) / 1e9
+        traffic = ncu_dram_bytes("r2_ncu_fused_B32.json")
         roofline = {
-            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
-            "kernels_ms": {k: v["ms"] for k, v in kernels.items()},
-            "step_algorithmic_bytes": step_bytes,
-            "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
-            "note": "B=32 CTAs on 148 SMs: bounded by the T_mel-long dependency chain of the DP, not by HBM",
+            "bound": "hbm", "kernel": "lp_mas_fused_kernel<10,2> (log-prior + MAS + dense path, one CTA per utterance)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "achieved_valid": step_bytes_valid / (t_fused * 1e-3) / 1e9,
+            "frac_valid": step_bytes_valid / (t_fused * 1e-3) / 1e9 / peak,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": step_bytes,
+            "kernel_ms": t_fused,
+            "kernels_ms": {"lp_mas_fused (dense path)": t_fused, "lp_mas_fused (index outputs only)": t_fused_idx,
+                           "serial form: log_prior + mas_forward + path_expand": t_serial,
+                           "log_prior alone (tcgen05, -> HBM)": t_lp, "mas_forward alone (index outputs)": t_mas,
+                           "mas_forward + path_expand": t_mas_dense},
+            "tensor_pipe": "3xTF32 tcgen05.mma, A in TMEM: 62 MMAs (M=128,N=32,K=8) per 32-frame tile of an utterance",
+            "note": "B=32 CTAs on 148 SMs: the step is bound by the T_mel-long dependency chain of the DP "
+                    "(~50 cycles/frame in one warp per 128 text rows), not by HBM; the throughput regime is in `sweep`",
         }
+        if traffic:
+            roofline["frac_dram"] = traffic / (t_fused * 1e-3) / 1e9 / peak
 
         # ---- CPU baseline on this box's host cores (bounded sample: a few full-batch steps)
         try:
@@ -522,35 +710,45 @@ def run_cuda(args):
         except Exception as ex:  # the oracle is a reported baseline, never a dependency of the product
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
+        # ---- end-to-end path agreement with the reference on the bench batch (north_star), F = 80 and the reference
+        # default n_feats = 128
+        try:
+            agreement = [path_agreement(dev, 80), path_agreement(dev, 128)]
+        except Exception as ex:
+            agreement = {"error": repr(ex)[:200]}
+
         # ---- configs[2] at the bench shape: the whole alignment block of compute_loss (face_tts.py:159-218,233-234),
         # forward + backward w.r.t. mu_x / logw.  "reference" = the reference's formulation on the SAME GPU tensors
         # (torch log-prior GEMMs on the device, its maximum_path wrapper bouncing value/mask to the host for the
         # compiled core.pyx and back, dense attn consumers) -- what a training step pays today.
-        block = None
+        block, sweep = None, None
         if world == 1:
             try:
                 block = time_compute_loss_block(dev)
             except Exception as ex:
                 block = {"error": repr(ex)[:200]}
+            try:
+                sweep = run_sweep(dev, peak, K)
+            except Exception as ex:
+                sweep = {"error": repr(ex)[:300]}
 
-        # overlapped pipeline (B <= SMs/2, no profiler attached): tcgen05 log-prior kernel (which also expands the
-        # dense path) + MAS kernel; serial pipeline: log-prior, MAS, path_expand
-        overlapped = os.environ.get("MAS_B200_PIPELINE", "") != "serial" and 2 * B <= 148 and \
-            _lib.get_option("fused_impl") != 1
-        launches_per_step = 2 if overlapped else 3
-        roofline["pipeline"] = ("overlapped: log_prior_tc || mas_forward on two streams, flags through L2"
-                                if overlapped else "serial: log_prior -> mas_forward -> path_expand")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: fused log_prior+MAS, LRS2 train batch shape", "B_per_gpu": B,
                        "n_feats": F, "T_text": TX, "T_mel": TY, "valid_cells_per_step": valid_cells,
-                       "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 61} MB) larger than the 126 MB L2",
+                       "outputs": "dense fp32 path [B,Tx,Ty] + durations [B,Tx] + frame->token index [B,Ty]",
+                       "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 37} MB) larger than the 126 MB L2",
                        "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
                        else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "compute_loss_block": block, "e2e": e2e, "e2e_ragged_upload": e2e_ragged, "e2e_dense_path": e2e_dense,
-            "gpu_launches": launches_per_step * K, "host_enqueue_us_per_step": host_enqueue_us,
+            "roofline": roofline, "cpu_baseline": cpu, "path_agreement": agreement, "sweep": sweep,
+            "strong_scaling_configs4": strong, "compute_loss_block": block,
+            "e2e": e2e, "e2e_padded_copy": e2e_padded, "e2e_dense_path": e2e_dense,
+            "gpu_launches": K, "launches_per_step": 1,
+            "pipeline": "ONE kernel per step: lp_mas_fused_kernel (tcgen05 log-prior -> shared-memory ring -> MAS -> backtrack "
+                        "-> dense path), programmatic dependent launch",
+            "host_enqueue_us_per_step": host_enqueue_us, "host_cores_per_rank": host_cores,
             "launch": "CUDA graph replay of the fused call + eager NCCL all-gather" if graphs[0] is not None else "eager",
             "clocks": clocks,
         }

@@ -264,6 +264,41 @@ int mas_b200_upload_batch(const float *mu_x_pinned, const float *y_pinned, const
                                t_y_dev, static_cast<cudaStream_t>(stream));
 }
 
+size_t mas_b200_packed_batch_bytes(const int *t_xs, const int *t_ys, int B, int F) {
+    if (!t_xs || !t_ys || B <= 0 || F <= 0) return 0;
+    size_t n = 0;
+    for (int b = 0; b < B; ++b) n += (size_t)(t_xs[b] > 0 ? t_xs[b] : 0) + (size_t)(t_ys[b] > 0 ? t_ys[b] : 0);
+    return packed_batch_header_bytes(B) + sizeof(float) * (size_t)F * n;
+}
+
+int mas_b200_pack_batch_host(const float *mu_x, const float *y, const int *t_xs, const int *t_ys, int B, int F, int Tx,
+                             int Ty, void *packed, size_t packed_bytes) {
+    if (!mu_x || !y || !t_xs || !t_ys || !packed || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
+    for (int b = 0; b < B; ++b)
+        if (t_xs[b] < 0 || t_xs[b] > Tx || t_ys[b] < 0 || t_ys[b] > Ty) return MAS_B200_ERR_ARG;
+    if (packed_bytes < mas_b200_packed_batch_bytes(t_xs, t_ys, B, F)) return MAS_B200_ERR_WORKSPACE;
+    int *hdr = static_cast<int *>(packed);
+    std::memcpy(hdr, t_xs, sizeof(int) * (size_t)B);
+    std::memcpy(hdr + B, t_ys, sizeof(int) * (size_t)B);
+    float *dst = reinterpret_cast<float *>(static_cast<char *>(packed) + packed_batch_header_bytes(B));
+    for (int b = 0; b < B; ++b)
+        for (int f = 0; f < F; ++f) {
+            std::memcpy(dst, mu_x + ((size_t)b * F + f) * Tx, sizeof(float) * (size_t)t_xs[b]);
+            dst += t_xs[b];
+        }
+    for (int b = 0; b < B; ++b)
+        for (int f = 0; f < F; ++f) {
+            std::memcpy(dst, y + ((size_t)b * F + f) * Ty, sizeof(float) * (size_t)t_ys[b]);
+            dst += t_ys[b];
+        }
+    return MAS_B200_OK;
+}
+
+int mas_b200_unpack_batch(const void *packed_dev, int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev,
+                          int *t_x_dev, int *t_y_dev, void *stream) {
+    return launch_unpack_batch(packed_dev, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev, static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------- host-buffer drop-ins
 namespace {
 struct DevBuf {

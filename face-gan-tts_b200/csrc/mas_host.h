@@ -91,6 +91,10 @@ int launch_duration_loss(const float *logw, const int *durations, const int *x_l
 int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const int *t_xs_pinned, const int *t_ys_pinned,
                         int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev, int *t_x_dev, int *t_y_dev,
                         cudaStream_t stream);
+// packed (ragged) batch -> zero-padded device tensors (upload.cu)
+size_t packed_batch_header_bytes(int B);
+int launch_unpack_batch(const void *packed_dev, int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev, int *t_x_dev,
+                        int *t_y_dev, cudaStream_t stream);
 int launch_log_prior_ffma(const float *mu_x, const float *y, int B, int F, int Tx, int Ty, float *out,
                           cudaStream_t stream);
 // tcgen05 implementation; returns MAS_B200_ERR_UNSUPPORTED when the shape is not covered.

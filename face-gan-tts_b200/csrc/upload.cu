@@ -238,4 +238,67 @@ int launch_upload_batch(const float *mu_x_pinned, const float *y_pinned, const i
     return MAS_B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Packed (ragged) batch: what a collate function that does NOT pad would hand over -- one contiguous buffer
+//   [t_x: B int32][t_y: B int32][pad to 16 bytes][mu: for b: F rows of t_x[b] floats][y: for b: F rows of t_y[b] floats]
+// It crosses PCIe with ONE copy-engine cudaMemcpyAsync (only valid data: ~8.1 of the 12.2 MB of a padded LRS2 batch),
+// and this kernel expands it on the device into the zero-padded tensors the reference contract describes
+// (mu_x [B,F,Tx] zero beyond t_x: text_encoder.py:417; y [B,F,Ty] zero-padded: lrs2_dataset.py:256,265).
+// HBM-bound: reads 4F*sum(t_x + t_y), writes 4FB(Tx + Ty) bytes.  One CTA per (mel bin, utterance) row pair.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) unpack_batch_kernel(const int *__restrict__ hdr, const float *__restrict__ body, int B,
+                                                           int F, int Tx, int Ty, float *__restrict__ mu_x,
+                                                           float *__restrict__ y, int *__restrict__ t_x_out,
+                                                           int *__restrict__ t_y_out) {
+    const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    __shared__ long long red[2][8];
+    // exclusive prefix sums of the lengths up to utterance b, and the total of t_x (start of the y section)
+    long long sx = 0, sy = 0, totx = 0;
+    for (int i = tid; i < B; i += 256) {
+        const long long a = max(0, min(hdr[i], Tx)), c = max(0, min(hdr[B + i], Ty));
+        totx += a;
+        if (i < b) { sx += a; sy += c; }
+    }
+    long long v[3] = {sx, sy, totx};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(kFullMask, v[k], o);
+    }
+    __shared__ long long part[3][8];
+    if ((tid & 31) == 0) { part[0][tid >> 5] = v[0]; part[1][tid >> 5] = v[1]; part[2][tid >> 5] = v[2]; }
+    __syncthreads();
+    sx = sy = totx = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sx += part[0][w]; sy += part[1][w]; totx += part[2][w]; }
+    (void)red;
+    const int tx = max(0, min(hdr[b], Tx)), ty = max(0, min(hdr[B + b], Ty));
+    if (f == 0 && tid == 0) { t_x_out[b] = hdr[b]; t_y_out[b] = hdr[B + b]; }      // unclamped: bad lengths are reported downstream
+    const float *mu_src = body + (size_t)F * sx + (size_t)f * tx;
+    const float *y_src = body + (size_t)F * totx + (size_t)F * sy + (size_t)f * ty;
+    float *mu_dst = mu_x + ((size_t)b * F + f) * Tx;
+    float *y_dst = y + ((size_t)b * F + f) * Ty;
+    for (int x = tid; x < Tx; x += 256) mu_dst[x] = x < tx ? __ldcs(mu_src + x) : 0.f;
+    for (int t = tid; t < Ty; t += 256) y_dst[t] = t < ty ? __ldcs(y_src + t) : 0.f;
+}
+
+}  // namespace
+
+size_t packed_batch_header_bytes(int B) { return (((size_t)8 * B + 15) / 16) * 16; }
+
+int launch_unpack_batch(const void *packed_dev, int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev, int *t_x_dev,
+                        int *t_y_dev, cudaStream_t stream) {
+    if (!packed_dev || !mu_x_dev || !y_dev || !t_x_dev || !t_y_dev || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0 || B > 65535)
+        return MAS_B200_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(packed_dev) & 15) return MAS_B200_ERR_ALIGN;
+    const int *hdr = static_cast<const int *>(packed_dev);
+    const float *body = reinterpret_cast<const float *>(static_cast<const char *>(packed_dev) + packed_batch_header_bytes(B));
+    unpack_batch_kernel<<<dim3(F, B), 256, 0, stream>>>(hdr, body, B, F, Tx, Ty, mu_x_dev, y_dev, t_x_dev, t_y_dev);
+    MASB200_CUDA_TRY(cudaGetLastError());
+    return MAS_B200_OK;
+}
+
 }  // namespace masb200

@@ -33,6 +33,9 @@ SIGNATURES = {
     "mas_b200_maximum_path": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mas_b200_log_prior": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mas_b200_packed_batch_bytes": (c_size_t, [c_void_p, c_void_p, c_int, c_int]),
+    "mas_b200_pack_batch_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
+    "mas_b200_unpack_batch": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_b200_set_pointer_option": (c_int, [c_char_p, c_void_p]),
     "mas_b200_debug_occupy_sms": (c_int, [c_int, c_ll, c_void_p]),
     "mas_b200_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -197,10 +197,6 @@ class AlignmentPlan:
             self.status = torch.empty((B,), dtype=torch.int32, device=dev)
             self.ws_bytes = L.mas_b200_fused_workspace_bytes(B, F, Tx, Ty)
             self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
-            # cleared once; the per-call nonce flags make every later clearing unnecessary (MAS_B200_WS_PREPARED)
-            _lib.check(L.mas_b200_fused_workspace_prepare(self.ws.data_ptr(), self.ws_bytes, B, F, Tx, Ty, _stream_ptr(dev)),
-                       "mas_b200_fused_workspace_prepare")
-            self.impl |= _lib.WS_PREPARED
         self._fn = L.mas_b200_log_prior_maximum_path
         self._result = AlignmentResult(self.path, self.durations, self.frame_token, self.status)
 
@@ -210,11 +206,14 @@ class AlignmentPlan:
         are done here -- that is the point)."""
         B, F, Tx, Ty = self.shape
         if mu_x.shape != (B, F, Tx) or y.shape != (B, F, Ty) or mu_x.dtype != torch.float32 or y.dtype != torch.float32 \
-                or not mu_x.is_contiguous() or not y.is_contiguous() or mu_x.device != self.device:
-            raise ValueError("AlignmentPlan: mu_x / y must be contiguous float32 CUDA tensors of the planned shape")
+                or not mu_x.is_contiguous() or not y.is_contiguous() or mu_x.device != self.device or y.device != self.device:
+            raise ValueError("AlignmentPlan: mu_x / y must be contiguous float32 CUDA tensors of the planned shape on the plan's device")
         if x_lengths.dtype != torch.int32 or y_lengths.dtype != torch.int32 or x_lengths.device != self.device \
                 or y_lengths.device != self.device or x_lengths.shape != (B,) or y_lengths.shape != (B,):
             raise ValueError("AlignmentPlan: lengths must be int32 [B] tensors on the plan's device")
+        if torch.cuda.current_device() != self.device.index:       # the library works on the CURRENT device
+            with torch.cuda.device(self.device):
+                return self.__call__(mu_x, y, x_lengths, y_lengths, check)
         rc = self._fn(mu_x.data_ptr(), y.data_ptr(), x_lengths.data_ptr(), y_lengths.data_ptr(), B, F, Tx, Ty, self.neg,
                       self.path.data_ptr() if self.path is not None else None, self.path_code,
                       self.durations.data_ptr(), self.frame_token.data_ptr(), self.status.data_ptr(),
@@ -322,6 +321,58 @@ def upload_batch(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor, y
         _lib.check(rc, "mas_b200_upload_batch")
         if mu_on_copy_engine:
             cur.wait_stream(side)
+    return out
+
+
+def pack_batch(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *, out=None,
+               pin: bool = True) -> torch.Tensor:
+    """Host-side collate WITHOUT padding (mas_b200_pack_batch_host): padded HOST tensors mu_x [B,F,Tx], y [B,F,Ty]
+    (float32) + int32 lengths -> one contiguous uint8 buffer
+        [t_x: B int32][t_y: B int32][pad to 16 B][mu: for b, for f: t_x[b] floats][y: for b, for f: t_y[b] floats]
+    holding only the valid data (what a dataset collate that never pads would produce directly).  Pinned by default
+    so that `upload_packed_batch` moves it with one asynchronous copy."""
+    for t, name in ((mu_x, "mu_x"), (y, "y"), (x_lengths, "x_lengths"), (y_lengths, "y_lengths")):
+        if t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous host tensor")
+    if mu_x.dtype != torch.float32 or y.dtype != torch.float32 or x_lengths.dtype != torch.int32 or \
+            y_lengths.dtype != torch.int32:
+        raise ValueError("mu_x / y must be float32 and the lengths int32")
+    B, F, Tx = mu_x.shape
+    Ty = y.shape[2]
+    L = _lib.lib()
+    nbytes = L.mas_b200_packed_batch_bytes(x_lengths.data_ptr(), y_lengths.data_ptr(), B, F)
+    if out is None:
+        out = torch.empty((nbytes,), dtype=torch.uint8)
+        if pin:
+            out = out.pin_memory()
+    elif out.numel() < nbytes or out.dtype != torch.uint8 or out.is_cuda:
+        raise ValueError("pack_batch: `out` must be a host uint8 tensor of at least packed_batch_bytes")
+    _lib.check(L.mas_b200_pack_batch_host(mu_x.data_ptr(), y.data_ptr(), x_lengths.data_ptr(), y_lengths.data_ptr(),
+                                          B, F, Tx, Ty, out.data_ptr(), out.numel()), "mas_b200_pack_batch_host")
+    return out[:nbytes]
+
+
+def upload_packed_batch(packed: torch.Tensor, B: int, F: int, Tx: int, Ty: int, *, device=None, out=None, staging=None):
+    """Packed ragged batch (pack_batch layout, pinned host memory) -> zero-padded device tensors
+    (mu_x [B,F,Tx], y [B,F,Ty], t_x [B], t_y [B]): ONE copy-engine transfer of the valid bytes + one device kernel
+    (mas_b200_unpack_batch).  Asynchronous on the current stream.  `out` / `staging` (a CUDA uint8 buffer of at least
+    packed.numel() bytes) let a training loop reuse its buffers."""
+    if packed.is_cuda or packed.dtype != torch.uint8 or not packed.is_contiguous():
+        raise ValueError("packed must be a contiguous uint8 host tensor (pack_batch)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        if staging is None:
+            staging = torch.empty((packed.numel(),), dtype=torch.uint8, device=dev)
+        elif staging.numel() < packed.numel() or not staging.is_cuda:
+            raise ValueError("staging must be a CUDA uint8 buffer of at least packed.numel() bytes")
+        if out is None:
+            out = (torch.empty((B, F, Tx), dtype=torch.float32, device=dev),
+                   torch.empty((B, F, Ty), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
+        staging[:packed.numel()].copy_(packed, non_blocking=True)
+        _lib.check(_lib.lib().mas_b200_unpack_batch(staging.data_ptr(), B, F, Tx, Ty, out[0].data_ptr(), out[1].data_ptr(),
+                                                    out[2].data_ptr(), out[3].data_ptr(), _stream_ptr(dev)),
+                   "mas_b200_unpack_batch")
     return out
 
 

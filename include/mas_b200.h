@@ -289,6 +289,22 @@ int mas_b200_log_prior_maximum_path_host(const float *mu_x, const float *y,
                                          int B, int F, int Tx, int Ty, float max_neg_val,
                                          int *paths, int *durations, int *frame_token);
 
+/*
+ * Packed (ragged) batch -- what a collate function that does not pad hands over; replaces the padded H2D copies of
+ * relocate_input (model/face_tts.py:85-89) on the host -> device path.  One contiguous buffer
+ *   [t_x: B int32][t_y: B int32][pad to 16 bytes][mu: for b, for f: t_x[b] floats][y: for b, for f: t_y[b] floats]
+ * crosses PCIe with ONE cudaMemcpyAsync (valid data only); mas_b200_unpack_batch expands it on the device into the
+ * zero-padded mu_x [B,F,Tx] / y [B,F,Ty] / length tensors every other entry point takes.
+ *   mas_b200_packed_batch_bytes   size of the packed buffer for the given (host) lengths
+ *   mas_b200_pack_batch_host      host-side packer for callers that hold padded host tensors (plain memcpy per row)
+ *   mas_b200_unpack_batch         device kernel, stream-ordered; packed_dev 16-byte aligned
+ */
+size_t mas_b200_packed_batch_bytes(const int *t_xs, const int *t_ys, int B, int F);
+int mas_b200_pack_batch_host(const float *mu_x, const float *y, const int *t_xs, const int *t_ys, int B, int F, int Tx,
+                             int Ty, void *packed, size_t packed_bytes);
+int mas_b200_unpack_batch(const void *packed_dev, int B, int F, int Tx, int Ty, float *mu_x_dev, float *y_dev,
+                          int *t_x_dev, int *t_y_dev, void *stream);
+
 /* Tuning/diagnostic knobs (not part of the reference interface).
  * mas_b200_set_option("mas_rows_per_lane", R) etc.; returns previous value or
  * INT32_MIN for an unknown key.  Process-wide, read at launch time. */

@@ -116,3 +116,26 @@ def test_install_shim_registers_reference_import_names():
     finally:
         f.uninstall()
     assert "model.monotonic_align" not in sys.modules
+
+
+def test_pack_batch_host_layout_matches_numpy():
+    """mas_b200_pack_batch_host (no GPU needed): [t_x][t_y][pad16][mu rows, valid part][y rows, valid part]."""
+    import numpy as np
+    import torch
+    import face_gan_tts_b200 as fgt
+
+    B, F, Tx, Ty = 5, 7, 13, 29
+    g = torch.Generator().manual_seed(0)
+    mu_x = torch.randn(B, F, Tx, generator=g)
+    y = torch.randn(B, F, Ty, generator=g)
+    t_x = torch.tensor([13, 1, 7, 4, 12], dtype=torch.int32)
+    t_y = torch.tensor([29, 5, 17, 4, 28], dtype=torch.int32)
+    packed = fgt.pack_batch(mu_x, y, t_x, t_y, pin=False).numpy()
+    hdr = (8 * B + 15) // 16 * 16
+    assert packed.size == hdr + 4 * F * int(t_x.sum() + t_y.sum())
+    ints = packed[:8 * B].view(np.int32)
+    assert ints[:B].tolist() == t_x.tolist() and ints[B:].tolist() == t_y.tolist()
+    body = packed[hdr:].view(np.float32)
+    want = np.concatenate([mu_x[b, f, :t_x[b]].numpy() for b in range(B) for f in range(F)] +
+                          [y[b, f, :t_y[b]].numpy() for b in range(B) for f in range(F)])
+    np.testing.assert_array_equal(body, want)

@@ -400,6 +400,31 @@ def test_upload_batch_equals_a_plain_copy_of_padded_inputs(B, F, Tx, Ty, upload_
     assert torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token)
 
 
+@pytest.mark.parametrize("B,F,Tx,Ty", [(32, 80, 190, 1000), (5, 128, 64, 256), (3, 7, 33, 101), (2, 80, 1, 4), (300, 8, 21, 40)])
+def test_packed_batch_unpacks_to_the_padded_tensors(B, F, Tx, Ty):
+    """pack_batch (host collate without padding) -> ONE H2D copy -> mas_b200_unpack_batch: the device tensors are the
+    zero-padded tensors of the reference contract, whatever garbage the padded host tensors held beyond the lengths."""
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B, F, Tx, Ty, seed=78, tx_lo=1, ty_lo=max(1, Ty // 3))
+    g = torch.Generator().manual_seed(1)
+    junk_x = torch.randn(B, F, Tx, generator=g) * (torch.arange(Tx)[None, None] >= t_x[:, None, None])
+    junk_y = torch.randn(B, F, Ty, generator=g) * (torch.arange(Ty)[None, None] >= t_y[:, None, None])
+    packed = fgt.pack_batch(mu_x + junk_x, y + junk_y, t_x, t_y)
+    assert packed.is_pinned() and packed.numel() == 16 * ((8 * B + 15) // 16) + 4 * F * int(t_x.sum() + t_y.sum())
+    out = fgt.upload_packed_batch(packed, B, F, Tx, Ty)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0].cpu(), mu_x) and torch.equal(out[1].cpu(), y)
+    assert torch.equal(out[2].cpu(), t_x) and torch.equal(out[3].cpu(), t_y)
+    # buffers reused, alignment from them == alignment from plain copies
+    staging = torch.empty((packed.numel() + 64,), dtype=torch.uint8, device=DEV)
+    out2 = fgt.upload_packed_batch(packed, B, F, Tx, Ty, out=out, staging=staging)
+    torch.cuda.synchronize()
+    assert torch.equal(out2[1].cpu(), y)
+    if F in (80, 128):
+        a = fgt.log_prior_maximum_path(out2[0], out2[1], out2[2], out2[3], dense_path=False)
+        b = fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, dense_path=False)
+        assert torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token)
+
+
 def test_upload_batch_rejects_pageable_memory():
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(2, 80, 21, 64, seed=3, tx_lo=5, ty_lo=30)
     with pytest.raises(ValueError):
