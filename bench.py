@@ -461,7 +461,24 @@ def run_cuda(args):
     for i in range(W):
         step(i)
     barrier()
+    # eager launches keep the programmatic dependent launch between consecutive steps (~2 us per step); a CUDA graph per
+    # step does not, but costs almost no host time.  Replay graphs only when the host cannot enqueue a step (fused call +
+    # NCCL all-gather) in less time than the GPU needs for it.
+    use_graph = False
     if dist and not args.no_graph:
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record(stream)
+        t0 = time.perf_counter()
+        for i in range(24):
+            step(W + i)
+        host_us = (time.perf_counter() - t0) / 24 * 1e6
+        e_b.record(stream)
+        barrier()
+        dev_us = e_a.elapsed_time(e_b) / 24 * 1e3
+        flag = torch.tensor([1.0 if host_us > 0.85 * dev_us else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)          # every rank takes the same decision
+        use_graph = bool(flag.item() > 0) or args.graph
+    if dist and use_graph:
         # With the NCCL enqueue beside it a step costs more host time than GPU time, so the fused call (ONE kernel node)
         # is replayed from a CUDA graph per buffer set; the all-gather stays an eager NCCL call on its own stream.
         try:
@@ -765,7 +782,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: always eager launches")
+    ap.add_argument("--graph", action="store_true", help="multi-GPU: always replay the fused call from a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

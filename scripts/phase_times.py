@@ -16,21 +16,18 @@ def run(B, Tx, Ty, opts, dense=False):
     dbg = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
     for _ in range(3):
         fgt.align(v, t_x, t_y, dense_path=dense)
-    p = dbg.data_ptr()
-    lo, hi = p & 0xFFFFFFFF, p >> 32
-    _lib.set_option("mas_debug_ptr_lo", lo - (1 << 32) if lo >= (1 << 31) else lo)
-    _lib.set_option("mas_debug_ptr_hi", hi)
+    _lib.set_pointer_option("mas_debug_ptr", dbg)
     fgt.align(v, t_x, t_y, dense_path=dense)
     torch.cuda.synchronize()
-    _lib.set_option("mas_debug_ptr_lo", 0); _lib.set_option("mas_debug_ptr_hi", 0)
+    _lib.set_pointer_option("mas_debug_ptr", None)
     d = dbg.cpu()
     print(f"--- B={B} Tx={Tx} Ty={Ty} opts={opts}")
-    print(" b   t_x  t_y | first_tile  dp_total  ring_wait  (dp-wait)/frame | warps_done backtrack  tail  | total cyc")
+    print(" b   t_x  t_y |  dp_total  cyc/frame | warps_done backtrack outputs | total cyc")
     for b in list(range(min(B, 6))) + ([B - 1] if B > 6 else []):
         s = d[b].tolist()
         tx, ty = s[7] >> 32, s[7] & 0xFFFFFFFF
-        print(f"{b:3d} {tx:5d} {ty:5d} | {s[1]-s[0]:9d} {s[2]-s[0]:9d} {s[3]:9d} {(s[2]-s[1]-s[3])/max(ty,1):10.1f}      | "
-              f"{s[4]-s[2]:9d} {s[5]-s[4]:9d} {s[6]-s[5]:6d} | {s[6]-s[0]:9d}")
+        print(f"{b:3d} {tx:5d} {ty:5d} | {s[2]-s[0]:9d} {(s[2]-s[0])/max(ty,1):10.1f} | "
+              f"{s[4]-s[2]:9d} {s[5]-s[4]:9d} {s[6]-s[5]:7d} | {s[6]-s[0]:9d}")
     for k in opts:
         _lib.set_option(k, 0)
 
