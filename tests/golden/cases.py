@@ -180,3 +180,25 @@ CASES = {
     "cfg1": case_cfg1,
     "wide_513x1030": case_wide_513x1030,
 }
+
+
+def compute_loss_inputs(B, Tx, Ty, out_size, seed, n_vocab, n_feats=128):
+    """Inputs of one FaceTTS.compute_loss fixture case (tests/golden/make_compute_loss_golden.py), drawn from ONE seeded
+    CPU generator in a fixed order -- shared by the generator script and by the tests, which regenerate `y` for the
+    LRS2-sized case instead of storing 8 MB of noise in the fixture.
+    Returns x_len, y_len (int64), x [B,Tx] int64, y [B,n_feats,Ty] float32, face [B,3,224,224] float32."""
+    g = torch.Generator().manual_seed(seed)
+    x_len = torch.randint(max(3, Tx // 3), Tx + 1, (B,), generator=g)
+    x_len = x_len - (1 - x_len % 2)
+    x_len[0] = Tx
+    y_len = torch.stack([torch.randint(max(int(x_len[b]), Ty // 4), Ty + 1, (1,), generator=g)[0] for b in range(B)])
+    y_len[0] = Ty
+    if out_size is not None:
+        y_len[1] = min(out_size - 20, Ty)            # one utterance shorter than the crop window
+        x_len[1] = min(int(x_len[1]), int(y_len[1]))
+    x = torch.randint(0, n_vocab - 1, (B, Tx), generator=g)
+    x = x * (torch.arange(Tx)[None] < x_len[:, None])
+    y = (torch.randn(B, n_feats, Ty, generator=g) * 2.0 - 5.0).clamp_(-11.512925, 2.0)
+    y = y * (torch.arange(Ty)[None, None] < y_len[:, None, None])
+    face = torch.rand(B, 3, 224, 224, generator=g) * 255.0
+    return x_len, y_len, x, y, face

@@ -19,7 +19,9 @@ Hooks record what crosses the boundary of the alignment block (face_tts.py:159-2
     out:  log_prior + attn_mask as handed to maximum_path (:173), attn, the (y, y_mask, mu_y) handed to
           decoder.compute_loss (:222), dur_loss, prior_loss, and the gradients of
           dur_loss + prior_loss w.r.t. mu_x and logw.
-Two cases: cropped (out_size=128, some utterances longer, some shorter than the window) and uncropped.
+Two small cases: cropped (out_size=128, some utterances longer, some shorter than the window) and uncropped; plus one
+at the LRS2 training shape (B=16, T_text=190, T_mel=1000, out_size=128) in compute_loss_block_lrs2.npz, stored without
+the tensors the tests can regenerate (y from the seed, log_prior / attn_mask from the oracle).
 """
 import os
 import random
@@ -88,22 +90,13 @@ def config():
     )
 
 
-def run_case(model, face_tts_mod, B, Tx, Ty, out_size, seed):
-    g = torch.Generator().manual_seed(seed)
-    x_len = torch.randint(max(3, Tx // 3), Tx + 1, (B,), generator=g)
-    x_len = x_len - (1 - x_len % 2)
-    x_len[0] = Tx
-    y_len = torch.stack([torch.randint(max(int(x_len[b]), Ty // 4), Ty + 1, (1,), generator=g)[0] for b in range(B)])
-    y_len[0] = Ty
-    if out_size is not None:
-        y_len[1] = min(out_size - 20, Ty)            # one utterance shorter than the crop window
-        x_len[1] = min(int(x_len[1]), int(y_len[1]))
+def run_case(model, face_tts_mod, B, Tx, Ty, out_size, seed, slim=False):
+    import time
+
+    import cases
+
     n_vocab = model.n_vocab
-    x = torch.randint(0, n_vocab - 1, (B, Tx), generator=g)
-    x = x * (torch.arange(Tx)[None] < x_len[:, None])
-    y = (torch.randn(B, 128, Ty, generator=g) * 2.0 - 5.0).clamp_(-11.512925, 2.0)
-    y = y * (torch.arange(Ty)[None, None] < y_len[:, None, None])
-    face = torch.rand(B, 3, 224, 224, generator=g) * 255.0
+    x_len, y_len, x, y, face = cases.compute_loss_inputs(B, Tx, Ty, out_size, seed, n_vocab)
 
     rec = {}
     enc_hook = model.encoder.register_forward_hook(lambda m, i, o: rec.update(enc=o))
@@ -112,8 +105,12 @@ def run_case(model, face_tts_mod, B, Tx, Ty, out_size, seed):
     real_dec = model.decoder.compute_loss
     offsets = []
 
+    t_mp = [0.0]
+
     def mp(value, mask):
+        t0 = time.perf_counter()
         out = real_mp(value, mask)
+        t_mp[0] += time.perf_counter() - t0
         rec.update(log_prior=value.detach().clone(), attn_mask=mask.detach().clone(), attn=out.detach().clone())
         return out
 
@@ -133,7 +130,9 @@ def run_case(model, face_tts_mod, B, Tx, Ty, out_size, seed):
         random.seed(seed)
         torch.manual_seed(seed)
         model.zero_grad()
+        t_step0 = time.perf_counter()
         dur_loss, prior_loss, diff_loss, spk_loss = model.compute_loss(x, x_len, y, y_len, spk=face, out_size=out_size)
+        t_step = time.perf_counter() - t_step0
         mu_x, logw, x_mask = rec["enc"]
         g_mu, g_lw = torch.autograd.grad(dur_loss + prior_loss, [mu_x, logw])
     finally:
@@ -147,6 +146,25 @@ def run_case(model, face_tts_mod, B, Tx, Ty, out_size, seed):
         it = iter(offsets)
         full_off = [next(it) if int(n) - out_size > 0 else 0 for n in y_len]
     assert all(torch.isfinite(v) for v in (dur_loss, prior_loss, diff_loss, spk_loss))
+    print(f"  case B={B} Tx={Tx} Ty={Ty}: reference compute_loss forward {t_step * 1e3:.1f} ms on this container's CPU, "
+          f"of which maximum_path (wrapper + Cython) {t_mp[0] * 1e3:.1f} ms; losses dur {dur_loss.item():.6f} "
+          f"prior {prior_loss.item():.6f} diff {diff_loss.item():.6f} spk {spk_loss.item():.6f}")
+    if slim:
+        # LRS2-sized case: y / log_prior / attn_mask / dec_y are regenerated by the tests (cases.compute_loss_inputs and
+        # the oracle's log-prior), not stored
+        return dict(
+            mu_x=mu_x.detach().numpy(), logw=logw.detach().numpy(), x_mask=x_mask.detach().numpy(),
+            x_lengths=x_len.numpy().astype(np.int32), y_lengths=y_len.numpy().astype(np.int32),
+            out_size=np.int32(-1 if out_size is None else out_size), shape=np.asarray([B, Tx, Ty], np.int32),
+            n_vocab=np.int32(n_vocab),
+            offsets=np.asarray(full_off if full_off is not None else [], np.int32), seed=np.int32(seed),
+            attn=np.packbits(rec["attn"].numpy().astype(np.uint8), axis=-1), attn_shape=np.asarray(rec["attn"].shape, np.int32),
+            dec_y_mask=rec["dec_y_mask"].numpy(), dec_mu_y=rec["dec_mu_y"].numpy(),
+            dur_loss=np.float32(dur_loss.item()), prior_loss=np.float32(prior_loss.item()),
+            diff_loss=np.float32(diff_loss.item()), spk_loss=np.float32(spk_loss.item()),
+            ref_step_ms_cpu=np.float32(t_step * 1e3), ref_maximum_path_ms_cpu=np.float32(t_mp[0] * 1e3),
+            grad_mu_x=g_mu.numpy(), grad_logw=g_lw.numpy(),
+        )
     return dict(
         mu_x=mu_x.detach().numpy(), logw=logw.detach().numpy(), x_mask=x_mask.detach().numpy(), y=y.numpy(),
         x_lengths=x_len.numpy().astype(np.int32), y_lengths=y_len.numpy().astype(np.int32),
@@ -173,6 +191,12 @@ def main():
     path = os.path.join(HERE, "compute_loss_block.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+    # BASELINE configs[2] at the bench shape: B=16 (the GAN micro-batch, config.py:112), T_text=190, T_mel=1000, n_feats=128,
+    # out_size=128
+    big = {f"lrs2/{k}": v for k, v in run_case(model, face_tts_mod, 16, 190, 1000, 128, 303, slim=True).items()}
+    path2 = os.path.join(HERE, "compute_loss_block_lrs2.npz")
+    np.savez_compressed(path2, **big)
+    print("wrote", path2, os.path.getsize(path2), "bytes")
     for k in ("cropped/dur_loss", "cropped/prior_loss", "full/dur_loss", "full/prior_loss", "cropped/offsets"):
         print(k, out[k])
 
