@@ -13,7 +13,9 @@
  *   - every `*_dev` pointer is DEVICE memory owned by the caller; `stream` is
  *     a cudaStream_t passed as void* (NULL = default stream).  Calls are
  *     asynchronous and stream-ordered; nothing synchronises the host.
- *   - the library keeps no global mutable state: calls are thread-safe.
+ *   - process-wide state: only the table of tuning knobs (mas_b200_set_option, read at launch time) and
+ *     per-device caches of device properties; calls from different host threads / on different streams do not
+ *     interact.  Every launch is self-contained: no kernel of this library waits for another launch.
  *   - return value: MAS_B200_OK or a negative MAS_B200_ERR_* code (argument
  *     errors are detected on the host before anything is launched).  Per-item
  *     data errors that only the device can see (t_x > t_y, t_x < 1: undefined
@@ -55,9 +57,7 @@ extern "C" {
 #define MAS_B200_LP_AUTO   0
 #define MAS_B200_LP_FFMA   1   /* fp32 CUDA-core contraction                     */
 #define MAS_B200_LP_TCGEN05 2  /* tcgen05/TMEM 3xTF32 contraction (sm_100a)       */
-/* OR-ed into `impl` of mas_b200_log_prior_maximum_path: the workspace was cleared once with
- * mas_b200_fused_workspace_prepare and has only been used for fused calls since (a training loop's persistent
- * workspace), so the call does not clear its flag area again -- one launch less per step. */
+/* OR-ed into `impl` of mas_b200_log_prior_maximum_path: accepted and ignored (ABI compatibility with round 1). */
 #define MAS_B200_WS_PREPARED 0x100
 
 /* default of core.pyx:40 */
@@ -118,7 +118,7 @@ int mas_b200_maximum_path(const float *value_dev, long long stride_b, long long 
  * Replaces: model/face_tts.py:165-171
  *   log_prior[b,x,t] = -0.5*sum_f y[b,f,t]^2 + sum_f mu_x[b,f,x]*y[b,f,t]
  *                      - 0.5*sum_f mu_x[b,f,x]^2 - 0.5*F*log(2*pi)
- * combined in the reference's order ((y_square - y_mu_double) + mu_square) + const.
+ * combined as (y_square' + dot) + (mu_square' + const) (the primed terms carry the -0.5).
  *   mu_x_dev [B,F,Tx] float32 contiguous; y_dev [B,F,Ty] float32 contiguous;
  *   log_prior_dev [B,Tx,Ty] float32 contiguous.
  * Within 1e-4 relative of the torch fp32 expression.
@@ -130,18 +130,18 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev,
 /*
  * Fused log-prior + MAS: mu_x, y -> path / durations / frame_token in one call, entirely on the device.
  * Replaces: model/face_tts.py:165-174 (log-prior block + maximum_path call).
- * For batches that leave SMs free (B + log-prior CTAs <= SM count; the LRS2 training batch does) the tcgen05
- * log-prior kernel and the MAS kernel run CONCURRENTLY on two streams forked from / joined into `stream`: the
- * [B,Tx,Ty] value matrix is handed over through L2 in 64-frame groups guarded by device-scope release/acquire
- * flags in the workspace, the search starts a few microseconds after the log-prior, and the dense path (if
- * requested) is written by the log-prior CTAs as each utterance's backtrack completes.  Larger batches (or
- * shapes the tensor-core kernel does not take, or a profiler that serialises kernels) run
- * mas_b200_log_prior into the workspace and then mas_b200_maximum_path.  Same results either way.
+ * ONE kernel, one CTA per utterance (lp_mas_fused.cu), for n_feats in {64, 80} with Tx <= 256 or n_feats in
+ * {64, 80, 96, 128} with Tx <= 128, Ty % 4 == 0, 16-byte aligned mu_x / y: tcgen05 3xTF32 contraction with mu_x parked
+ * in tensor memory, its accumulator written tile by tile straight into the shared-memory ring the alignment search
+ * reads -- the [Tx,Ty] value matrix never exists in global memory --, then backtrack, durations, frame_token and (if
+ * requested) the dense path, whose zeros are streamed out while the search runs.  The path is the bit-exact MAS
+ * (core.pyx:9-35 semantics) of the log-prior values the kernel computed (within 1e-4 relative of torch fp32).
+ * Other shapes run the serial form: mas_b200_log_prior into the workspace, then mas_b200_maximum_path.
  * workspace: >= mas_b200_fused_workspace_bytes(B,F,Tx,Ty), 256-byte aligned.
  */
 size_t mas_b200_fused_workspace_bytes(int B, int F, int Tx, int Ty);
-/* Clears the flag area of a fused workspace (once, after allocating it); see MAS_B200_WS_PREPARED.  The cross-kernel
- * flags hold a per-call nonce, so entries left by earlier calls never read as "set". */
+/* No-op kept for ABI compatibility (round 1's two-kernel pipeline kept flags in the workspace; the fused call is ONE
+ * kernel now and keeps no state there).  Validates its arguments only. */
 int mas_b200_fused_workspace_prepare(void *workspace_dev, size_t workspace_bytes, int B, int F, int Tx, int Ty,
                                      void *stream);
 int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,
