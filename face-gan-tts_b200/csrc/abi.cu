@@ -301,20 +301,47 @@ int mas_b200_unpack_batch(const void *packed_dev, int B, int F, int Tx, int Ty, 
 
 // ---------------------------------------------------------------- host-buffer drop-ins
 namespace {
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+// One device arena + one stream per (host thread, device), grown on demand and reused: the host-buffer drop-ins are
+// called once per training step, and six cudaMalloc / cudaFree pairs per call cost more than the alignment itself.
+struct HostArena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaStream_t stream = nullptr;
+    ~HostArena() {
+        if (base) cudaFree(base);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    cudaError_t reserve(size_t bytes) {
+        used = 0;
+        if (!stream) {
+            cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+            if (e != cudaSuccess) { stream = nullptr; return e; }
+        }
+        if (bytes <= cap) return cudaSuccess;
+        if (base) { cudaFree(base); base = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&base), bytes);
+        if (e != cudaSuccess) { base = nullptr; return e; }
+        cap = bytes;
+        return cudaSuccess;
+    }
+    void *take(size_t bytes) {
+        char *p = base + used;
+        used += align_up(bytes ? bytes : 1, 256);
+        return p;
+    }
 };
-struct Stream {
-    cudaStream_t s = nullptr;
-    ~Stream() { if (s) cudaStreamDestroy(s); }
-};
+HostArena *host_arena() {
+    static thread_local HostArena cache[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    return &cache[dev];
+}
 int count_bad(const int *status, int B) {
     int bad = 0;
     for (int i = 0; i < B; ++i) bad += status[i] != MAS_B200_ITEM_OK;
     return bad;
 }
+size_t pad256(size_t n) { return align_up(n ? n : 1, 256); }
 }  // namespace
 
 int mas_b200_maximum_path_host(int *paths, const float *values, const int *t_xs, const int *t_ys, int B, int Tx,
@@ -322,26 +349,25 @@ int mas_b200_maximum_path_host(int *paths, const float *values, const int *t_xs,
     if (!paths || !values || !t_xs || !t_ys || B <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     const size_t cells = (size_t)B * Tx * Ty;
     const size_t ws_bytes = mas_b200_workspace_bytes(B, Tx, Ty);
-    DevBuf d_val, d_path, d_tx, d_ty, d_status, d_ws;
-    Stream st;
-    MASB200_CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-    MASB200_CUDA_TRY(d_val.alloc(cells * 4));
-    MASB200_CUDA_TRY(d_path.alloc(cells * 4));
-    MASB200_CUDA_TRY(d_tx.alloc((size_t)B * 4));
-    MASB200_CUDA_TRY(d_ty.alloc((size_t)B * 4));
-    MASB200_CUDA_TRY(d_status.alloc((size_t)B * 4));
-    MASB200_CUDA_TRY(d_ws.alloc(ws_bytes));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_val.p, values, cells * 4, cudaMemcpyHostToDevice, st.s));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_tx.p, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_ty.p, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
-    int rc = mas_b200_maximum_path(static_cast<float *>(d_val.p), (long long)Tx * Ty, Ty, static_cast<int *>(d_tx.p),
-                                   static_cast<int *>(d_ty.p), B, Tx, Ty, max_neg_val, d_path.p, MAS_B200_PATH_I32,
-                                   nullptr, nullptr, static_cast<int *>(d_status.p), d_ws.p, ws_bytes, st.s);
-    if (rc != MAS_B200_OK) return rc;
+    HostArena *A = host_arena();
+    if (!A) return MAS_B200_ERR_CUDA;
+    MASB200_CUDA_TRY(A->reserve(2 * pad256(cells * 4) + 3 * pad256((size_t)B * 4) + pad256(ws_bytes)));
+    void *d_ws = A->take(ws_bytes);                 // first: 256-byte aligned like the arena itself
+    float *d_val = static_cast<float *>(A->take(cells * 4));
+    void *d_path = A->take(cells * 4);
+    int *d_tx = static_cast<int *>(A->take((size_t)B * 4)), *d_ty = static_cast<int *>(A->take((size_t)B * 4));
+    int *d_status = static_cast<int *>(A->take((size_t)B * 4));
+    cudaStream_t st = A->stream;
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_val, values, cells * 4, cudaMemcpyHostToDevice, st));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_tx, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_ty, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    int rc = mas_b200_maximum_path(d_val, (long long)Tx * Ty, Ty, d_tx, d_ty, B, Tx, Ty, max_neg_val, d_path,
+                                   MAS_B200_PATH_I32, nullptr, nullptr, d_status, d_ws, ws_bytes, st);
+    if (rc != MAS_B200_OK) { cudaStreamSynchronize(st); return rc; }
     int *status = new int[B];
-    cudaError_t e = cudaMemcpyAsync(paths, d_path.p, cells * 4, cudaMemcpyDeviceToHost, st.s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st.s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st.s);
+    cudaError_t e = cudaMemcpyAsync(paths, d_path, cells * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { delete[] status; set_last_cuda_error(e); return MAS_B200_ERR_CUDA; }
     const int bad = count_bad(status, B);
     delete[] status;
@@ -354,37 +380,33 @@ int mas_b200_log_prior_maximum_path_host(const float *mu_x, const float *y, cons
     if (!mu_x || !y || !t_xs || !t_ys || B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return MAS_B200_ERR_ARG;
     const size_t cells = (size_t)B * Tx * Ty;
     const size_t ws_bytes = mas_b200_fused_workspace_bytes(B, F, Tx, Ty);
-    DevBuf d_mu, d_y, d_path, d_tx, d_ty, d_status, d_dur, d_ft, d_ws;
-    Stream st;
-    MASB200_CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-    MASB200_CUDA_TRY(d_mu.alloc((size_t)B * F * Tx * 4));
-    MASB200_CUDA_TRY(d_y.alloc((size_t)B * F * Ty * 4));
-    if (paths) MASB200_CUDA_TRY(d_path.alloc(cells * 4));
-    MASB200_CUDA_TRY(d_tx.alloc((size_t)B * 4));
-    MASB200_CUDA_TRY(d_ty.alloc((size_t)B * 4));
-    MASB200_CUDA_TRY(d_status.alloc((size_t)B * 4));
-    MASB200_CUDA_TRY(d_dur.alloc((size_t)B * Tx * 4));
-    MASB200_CUDA_TRY(d_ft.alloc((size_t)B * Ty * 4));
-    MASB200_CUDA_TRY(d_ws.alloc(ws_bytes));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_mu.p, mu_x, (size_t)B * F * Tx * 4, cudaMemcpyHostToDevice, st.s));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_y.p, y, (size_t)B * F * Ty * 4, cudaMemcpyHostToDevice, st.s));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_tx.p, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
-    MASB200_CUDA_TRY(cudaMemcpyAsync(d_ty.p, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, st.s));
-    int rc = mas_b200_log_prior_maximum_path(
-        static_cast<float *>(d_mu.p), static_cast<float *>(d_y.p), static_cast<int *>(d_tx.p),
-        static_cast<int *>(d_ty.p), B, F, Tx, Ty, max_neg_val, paths ? d_path.p : nullptr,
-        paths ? MAS_B200_PATH_I32 : MAS_B200_PATH_NONE, static_cast<int *>(d_dur.p), static_cast<int *>(d_ft.p),
-        static_cast<int *>(d_status.p), d_ws.p, ws_bytes, MAS_B200_LP_AUTO, st.s);
-    if (rc != MAS_B200_OK) return rc;
+    HostArena *A = host_arena();
+    if (!A) return MAS_B200_ERR_CUDA;
+    MASB200_CUDA_TRY(A->reserve(pad256(ws_bytes) + pad256((size_t)B * F * Tx * 4) + pad256((size_t)B * F * Ty * 4) +
+                                (paths ? pad256(cells * 4) : 0) + 3 * pad256((size_t)B * 4) + pad256((size_t)B * Tx * 4) +
+                                pad256((size_t)B * Ty * 4)));
+    void *d_ws = A->take(ws_bytes);
+    float *d_mu = static_cast<float *>(A->take((size_t)B * F * Tx * 4)), *d_y = static_cast<float *>(A->take((size_t)B * F * Ty * 4));
+    void *d_path = paths ? A->take(cells * 4) : nullptr;
+    int *d_tx = static_cast<int *>(A->take((size_t)B * 4)), *d_ty = static_cast<int *>(A->take((size_t)B * 4));
+    int *d_status = static_cast<int *>(A->take((size_t)B * 4));
+    int *d_dur = static_cast<int *>(A->take((size_t)B * Tx * 4)), *d_ft = static_cast<int *>(A->take((size_t)B * Ty * 4));
+    cudaStream_t st = A->stream;
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_mu, mu_x, (size_t)B * F * Tx * 4, cudaMemcpyHostToDevice, st));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_y, y, (size_t)B * F * Ty * 4, cudaMemcpyHostToDevice, st));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_tx, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    MASB200_CUDA_TRY(cudaMemcpyAsync(d_ty, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    int rc = mas_b200_log_prior_maximum_path(d_mu, d_y, d_tx, d_ty, B, F, Tx, Ty, max_neg_val, d_path,
+                                             paths ? MAS_B200_PATH_I32 : MAS_B200_PATH_NONE, d_dur, d_ft, d_status, d_ws,
+                                             ws_bytes, MAS_B200_LP_AUTO, st);
+    if (rc != MAS_B200_OK) { cudaStreamSynchronize(st); return rc; }
     int *status = new int[B];
     cudaError_t e = cudaSuccess;
-    if (paths) e = cudaMemcpyAsync(paths, d_path.p, cells * 4, cudaMemcpyDeviceToHost, st.s);
-    if (e == cudaSuccess && durations)
-        e = cudaMemcpyAsync(durations, d_dur.p, (size_t)B * Tx * 4, cudaMemcpyDeviceToHost, st.s);
-    if (e == cudaSuccess && frame_token)
-        e = cudaMemcpyAsync(frame_token, d_ft.p, (size_t)B * Ty * 4, cudaMemcpyDeviceToHost, st.s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st.s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st.s);
+    if (paths) e = cudaMemcpyAsync(paths, d_path, cells * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && durations) e = cudaMemcpyAsync(durations, d_dur, (size_t)B * Tx * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && frame_token) e = cudaMemcpyAsync(frame_token, d_ft, (size_t)B * Ty * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { delete[] status; set_last_cuda_error(e); return MAS_B200_ERR_CUDA; }
     const int bad = count_bad(status, B);
     delete[] status;

@@ -608,11 +608,12 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     const bool heads = P.frame_token != nullptr;
     mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg, heads ? hd : nullptr);
     if (dbg && tid == 0) dbg[5] = clock64();
-    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg, heads);
-    if (P.path != nullptr) {
-        // dense path, part 2: token x owns frames [tok[x], tok[x+1]) of row x -- one warp per token, a contiguous run of ones
-        uint32_t *pb = reinterpret_cast<uint32_t *>(P.path) + (size_t)b * P.Tx * P.Ty;
-        const uint32_t one = P.path_dtype == MAS_B200_PATH_F32 ? 0x3f800000u : 1u;
+    // dense path, part 2: the ones -- frame t belongs to token frame_token[t]; written by the thread that produces
+    // frame_token[t] (when the caller wants no frame_token the per-token form below does it)
+    uint32_t *pb = P.path != nullptr ? reinterpret_cast<uint32_t *>(P.path) + (size_t)b * P.Tx * P.Ty : nullptr;
+    const uint32_t one = P.path_dtype == MAS_B200_PATH_F32 ? 0x3f800000u : 1u;
+    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg, heads, heads ? pb : nullptr, one);
+    if (pb != nullptr && !heads) {
         for (int x = warp; x < t_x; x += kFusedWarps) {
             const int s0 = tok[x], e0 = (x + 1 < t_x) ? tok[x + 1] : t_y;
             for (int t = s0 + lane; t < e0; t += 32) pb[(size_t)x * P.Ty + t] = one;

@@ -510,12 +510,22 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
         const uint32_t *bj = bits_s + (size_t)jt * XP;
         const int lo = jt > 0 ? xin[jt - 1] : 0;
         uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
-        for (int x = xin[jt]; x > lo; --x) {
-            const uint32_t m = bj[x] & mk;
-            const int st = (jt << 5) + 32 - __ffs((int)m);
-            tok[x] = st;
-            if (hd != nullptr) hd[st] = x;
-            mk = m ^ (0u - m);
+        // eight tokens per round: their words are fetched with independent loads, then each token costs two ALU ops
+        // (one dependent shared-memory load per token made a 25-token tile the whole tail)
+        for (int x = xin[jt]; x > lo; x -= 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = bj[max(x - k, 0)];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (x - k > lo) {
+                    const uint32_t m = w[k] & mk;
+                    const int st = (jt << 5) + 32 - __ffs((int)m);
+                    tok[x - k] = st;
+                    if (hd != nullptr) hd[st] = x - k;
+                    mk = m ^ (0u - m);
+                }
+            }
         }
         if (jt == 0 && hd != nullptr) hd[0] = 0;                           // token 0 starts at frame 0
     }
@@ -528,9 +538,12 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
 // per token walking its frames (a 200-frame silence token was the whole tail).
 //   hd   scratch in shared memory: [(Ty + 3) & ~3] heads + [32] warp totals
 //   heads_ready   hd[] was already filled by mas_backtrack_smem
+//   path_ones     optional: the (already zero-filled) dense path [Tx,Ty] of this utterance as 32-bit words; every frame's
+//                 thread stores `one` at (its token, its frame) -- 8 independent stores per thread, no per-token loop
 template <int NTHREADS>
 __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b, const int *tok, int *hd, int t_x, int t_y,
-                                                      int tid, long long *dbg = nullptr, bool heads_ready = false) {
+                                                      int tid, long long *dbg = nullptr, bool heads_ready = false,
+                                                      uint32_t *path_ones = nullptr, uint32_t one = 0u) {
     const int warp = tid >> 5, lane = tid & 31;
     int *start_b = P.start + (size_t)b * P.Tx;
     int *dur_b = P.dur + (size_t)b * P.Tx;
@@ -588,6 +601,11 @@ __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b,
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = (t0 + k < t_y) ? max(basev, v[k]) : -1;
+            if (path_ones != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (v[k] >= 0) path_ones[(size_t)v[k] * P.Ty + t0 + k] = one;
+            }
             if (vec && t0 + 7 < P.Ty) {
                 *reinterpret_cast<int4 *>(ft + t0) = make_int4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<int4 *>(ft + t0 + 4) = make_int4(v[4], v[5], v[6], v[7]);

@@ -14,7 +14,7 @@ def run(B, F, Tx, Ty, full=False):
     if full:
         tx[:] = Tx; ty[:] = Ty
     mu, y, tx, ty = mu.cuda(), y.cuda(), tx.cuda().int(), ty.cuda().int()
-    plan = fgt.AlignmentPlan(B, F, Tx, Ty, device="cuda:0", dense_path=False)
+    plan = fgt.AlignmentPlan(B, F, Tx, Ty, device="cuda:0", dense_path=os.environ.get("FUSED_DENSE", "0") == "1")
     for _ in range(3):
         plan(mu, y, tx, ty)
     dbg = torch.zeros((B, 32), dtype=torch.int64, device="cuda")
