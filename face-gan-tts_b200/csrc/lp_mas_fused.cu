@@ -12,7 +12,7 @@
 // TMEM -> shared-memory copy: it shares its scheduler partition with a DP warp and must stay out of its way.
 // The path is the bit-exact MAS of exactly these values (tests dump them through the fused_dump_ptr option).
 //
-// Warp roles (15 warps; warp % 4 = scheduler partition, the arbiter favours the higher warp id):
+// Warp roles (16 warps; warp % 4 = scheduler partition, the arbiter favours the higher warp id):
 //    0..3   epilogue: per tile TMEM -> registers -> ring (in the prologue: musq + const)
 //    6, 7   operand split: raw y tile [F][32] -> hi/lo K-major core matrices + ysq
 //    10     TMA loads (mu_x block, y tiles) + tcgen05.mma issue
@@ -20,7 +20,9 @@
 //    12, 13 DP warps (text rows 0..127 / 128..255): alone with one epilogue warp on partitions 0 / 1, highest ids there
 //    9      dense path (when requested): streams the all-zero [Tx,Ty] block out with bulk copies from an 8 KB zero
 //           buffer while the search runs -- the result only adds ~t_y ones to it (written by all warps in the tail)
-//    4, 5, 8  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
+//    4, 5, 8, 15  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
+//    prologue: warps 4, 5, 10, 11 / 8, 9, 14, 15 (one per TMEM lane quadrant each) park the lower / upper half of the mel
+//    bins of mu_x in tensor memory while the split warps already work on the first y tiles
 // TMEM lane m of M-tile mt holds text row x = 128*mt + 4*(m & 31) + (m >> 5): the epilogue thread of that lane then owns
 // ring slot (m >> 5) * 32W + 32*mt + (m & 31) -- the lane-major permuted layout of mas_common.cuh -- so its eight 16-byte
 // stores are bank-conflict free, M-tile mt is exactly DP warp mt's rows, and each (stage, M-tile) has its own
@@ -45,7 +47,7 @@ int make_y_tensor_map(const float *y, int B, int F, int Ty, int box_frames, CUte
 namespace {
 
 constexpr int kFR = 4;                       // text rows per DP lane
-constexpr int kFusedWarps = 15;
+constexpr int kFusedWarps = 16;
 constexpr int kFusedThreads = kFusedWarps * 32;
 constexpr int kWarpSplit = 6;                // 6, 7
 constexpr int kWarpMma = 10;
@@ -253,11 +255,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         __syncwarp();
     }
 
-    // ---- prologue (warps 0..11; warp % 4 = TMEM lane quadrant): mu_x rows -> exact tf32 hi/lo -> TMEM, the A operand
-    // for the whole CTA.  Warps 4..7 take the lower half of the mel bins, warps 8..11 the upper half; warps 0..3 (the
-    // epilogue warps) compute musq[x] = -0.5 sum_f mu^2 in the serial kernel's order.
-    if (warp < 12) {
-        const int q = warp & 3, grp = warp >> 2;
+    // ---- prologue (warp % 4 = TMEM lane quadrant): mu_x rows -> exact tf32 hi/lo -> TMEM, the A operand for the whole
+    // CTA.  Warps 4, 5, 10, 11 take the lower half of the mel bins, warps 8, 9, 14, 15 the upper half; warps 0..3 (the
+    // epilogue warps) compute musq[x] = -0.5 sum_f mu^2.  The split warps (6, 7) are NOT among them: when the staging
+    // does not reach into the y buffers they split the first y tiles meanwhile.
+    const int park_grp = warp < 4 ? 0 : ((warp == 4 || warp == 5 || warp == 10 || warp == 11) ? 1
+                                         : ((warp == 8 || warp == 9 || warp == 14 || warp == 15) ? 2 : -1));
+    if (park_grp >= 0) {
+        const int q = warp & 3, grp = park_grp;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
 #pragma unroll
         for (int mt = 0; mt < W; ++mt) {

@@ -506,7 +506,11 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
         for (int t = tid - 1; t < t_y; t += NTHREADS - 1) hd[t] = -1;
     }
     __syncthreads();
-    for (int jt = tid; jt < ntiles; jt += NTHREADS) {                     // one thread per tile: start frames
+    if (dbg && tid == 0) dbg[14] = clock64();
+    // one thread per tile: start frames.  Tile jt goes to lane jt / nwarps of warp jt % nwarps, so the (divergent,
+    // differently long) token chains of the tiles run on different warps instead of serialising inside warp 0.
+    constexpr int kNW = NTHREADS / 32;
+    for (int jt = warp + kNW * lane; jt < ntiles; jt += NTHREADS) {
         const uint32_t *bj = bits_s + (size_t)jt * XP;
         const int lo = jt > 0 ? xin[jt - 1] : 0;
         uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
@@ -529,6 +533,7 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
         }
         if (jt == 0 && hd != nullptr) hd[0] = 0;                           // token 0 starts at frame 0
     }
+    if (dbg && tid == 0) dbg[15] = clock64();
     __syncthreads();
 }
 
