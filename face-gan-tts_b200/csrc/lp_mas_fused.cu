@@ -16,11 +16,11 @@
 //    0..3   epilogue: per tile TMEM -> registers -> ring (in the prologue: musq + const)
 //    6, 7   operand split: raw y tile [F][32] -> hi/lo K-major core matrices + ysq
 //    10     TMA loads (mu_x block, y tiles) + tcgen05.mma issue
-//    11, 14 backtrack helpers: per-tile transfer tables in the shadow of the DP
+//    11, 14, 15 backtrack helpers: per-tile transfer tables in the shadow of the DP (an even share of the row groups each)
 //    12, 13 DP warps (text rows 0..127 / 128..255): alone with one epilogue warp on partitions 0 / 1, highest ids there
 //    9      dense path (when requested): streams the all-zero [Tx,Ty] block out with bulk copies from an 8 KB zero
 //           buffer while the search runs -- the result only adds ~t_y ones to it (written by all warps in the tail)
-//    4, 5, 8, 15  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
+//    4, 5, 8  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)
 //    prologue: warps 4, 5, 10, 11 / 8, 9, 14, 15 (one per TMEM lane quadrant each) park the lower / upper half of the mel
 //    bins of mu_x in tensor memory while the split warps already work on the first y tiles
 // TMEM lane m of M-tile mt holds text row x = 128*mt + 4*(m & 31) + (m >> 5): the epilogue thread of that lane then owns
@@ -47,6 +47,7 @@ int make_y_tensor_map(const float *y, int B, int F, int Ty, int box_frames, CUte
 namespace {
 
 constexpr int kFR = 4;                       // text rows per DP lane
+constexpr int kFusedCell = kCellSign;      // the search runs on the kernel's own finite log-prior values (mas_forward.cuh: mas_cell)
 constexpr int kFusedWarps = 16;
 constexpr int kFusedThreads = kFusedWarps * 32;
 constexpr int kWarpSplit = 6;                // 6, 7
@@ -54,6 +55,7 @@ constexpr int kWarpMma = 10;
 constexpr int kWarpHelpA = 11;
 constexpr int kWarpDp = 12;                  // 12, 13
 constexpr int kWarpHelpB = 14;
+constexpr int kWarpHelpC = 15;
 constexpr int kWarpZero = 9;                 // dense-path zero fill
 constexpr uint32_t kZeroBytes = 8192;        // zero buffer = size of one bulk store
 
@@ -121,7 +123,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     constexpr int XP = FS::XP;
     constexpr int NT = kTileFrames;
     constexpr int kTileFloats = XP * kTilePitch;
-    constexpr int kG = XP / 32, kGH = kG / 2;                 // row groups of a tile: [0,kGH) helper A, [kGH,kG) helper B
     constexpr uint32_t kSbo = (uint32_t)FS::FE * 32u;         // 8 frames x (F + 8) K values x 4 B per row group of an operand tile
     const MasParams &P = FP.mas;
     const int NS = P.ring_stages;
@@ -495,17 +496,33 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             }
             __syncwarp();
         }
-    } else if (warp == kWarpHelpA || warp == kWarpHelpB) {
+    } else if (warp == kWarpHelpA || warp == kWarpHelpB || warp == kWarpHelpC) {
         // ======================= backtrack helpers: transfer tables behind the LAST active DP warp =======================
+        // three warps share the row groups of every finished tile evenly (they have to keep up with the DP warps: what
+        // they have not done when the search ends is on the critical path)
         const int *flag_last = hprog + (w_act - 1);
+        const int h = warp == kWarpHelpA ? 0 : (warp == kWarpHelpB ? 1 : 2);
         int known = 0;
+#ifdef MASB200_HELP_PROF
+        long long hw = 0, hk = 0; int nwait = 0;
+#endif
         for (int jt = 0; jt < ntiles; ++jt) {
+#ifdef MASB200_HELP_PROF
+            const long long c0 = clock64();
+            if (known < jt + 1) { known = flag_wait_ge_warp(flag_last, jt + 1); ++nwait; }
+            const long long c1 = clock64();
+#else
             if (known < jt + 1) known = flag_wait_ge_warp(flag_last, jt + 1);
-            if (warp == kWarpHelpA)
-                bt_tile_transfer<0, kGH>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane);
-            else
-                bt_tile_transfer<kGH, kG>(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane);
+#endif
+            bt_tile_transfer_share(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane, h, 3);
+#ifdef MASB200_HELP_PROF
+            hw += c1 - c0; hk += clock64() - c1;
+#endif
         }
+#ifdef MASB200_HELP_PROF
+        if (dbg && lane == 0) { dbg[16 + 3 * h] = hw; dbg[17 + 3 * h] = hk; dbg[18 + 3 * h] = nwait; }
+#endif
+        if (dbg && lane == 0 && h < 2) dbg[28 + h] = clock64();
     } else if (warp >= kWarpDp && warp < kWarpDp + w_act) {
         // ======================= DP warps (see mas_forward_kernel: nothing in the tile loop may branch or predicate
         // on a loop-invariant condition; role differences are ADDRESSES) =======================
@@ -562,8 +579,8 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
             const int dl0 = lane_cta - t0 / R;
             PROF_T(cb0);
-            if (diag) dp_tile_pre<R, XP, true>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
-            else dp_tile_pre<R, XP, false>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+            if (diag) dp_tile_pre<R, XP, true, kFusedCell>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
+            else dp_tile_pre<R, XP, false, kFusedCell>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             PROF_ADD(w_body, cb0);
             // tile j + 1 ready?  (normally yes: the flags were read before the body) -> its first groups are on their
             // way while this tile's direction words are stored and the tile is released
@@ -576,17 +593,9 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             PROF_ADD(w_full, cw0);
 
             // direction words of this tile, walk-ready (see mas_forward_kernel)
-            if (diag) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (((x0 + r) >> 5) == j) acc[r] |= 1u << ((x0 + r) & 31);
-            }
-            if (x0 == 0) acc[0] = 0u;
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = __brev(acc[r]);
-            store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, acc);
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = 0u;
+            uint32_t words[R];
+            dp_finish_words<R, kFusedCell>(acc, words, x0, j, diag);
+            store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, words);
 
             __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
             if (elect_one()) {
@@ -600,6 +609,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         if (dbg && lane == 0) { dbg[22 + 2 * w] = w_full; dbg[26 + w] = w_body; }
 #endif
         if (dbg && lane == 0 && w == w_act - 1) dbg[4] = clock64();
+        if (dbg && lane == 0 && w == 0) dbg[30] = clock64();
     }
     tc_fence_before();
     __syncthreads();

@@ -79,16 +79,36 @@ struct MasParams {
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
 };
 
-// One cell of the recurrence; bit BITPOS of `bits` is set iff the diagonal predecessor wins.
-//   setp.gt p, v_prev, v_cur ; q = v_cur + v ; @p q = v_prev + v ; @p bits |= 1 << BITPOS
-// = (v_prev > v_cur ? v_prev : v_cur) + v in fp32 RN, NaN -> v_cur: core.pyx:22-30 with Cython's
-// max(v_cur, v_prev) lowering.  The select is folded into the two (independent) adds, so the
-// frame-to-frame dependency chain is compare -> predicated add.
+// One cell of the recurrence, two formulations (template parameter CK):
+//
+// kCellExact   setp.gt p, v_prev, v_cur ; q = v_cur + v ; @p q = v_prev + v ; @p bits |= 1 << BITPOS
+//   = (v_prev > v_cur ? v_prev : v_cur) + v in fp32 RN, NaN -> v_cur: core.pyx:22-30 with Cython's max(v_cur, v_prev)
+//   lowering, for ANY input (NaN, infinities, signed zeros).  The select is folded into the two (independent) adds, so
+//   the frame-to-frame dependency chain is compare -> predicated add.  Bit BITPOS of `bits` is set iff the diagonal
+//   predecessor wins.  This is what maximum_path(value, mask) runs: its values are the caller's.
+//
+// kCellSign    q = fmax(v_cur, v_prev) + v ; bits = (bits << 1) | signbit(v_cur - v_prev)
+//   predicate-free: the seven predicate registers no longer bound how many cells ptxas keeps in flight (static
+//   schedule 23.5 instead of 29.4 cycles per frame, measured 30.8 instead of 38.2 in isolation), and the word is
+//   accumulated by a funnel shift, newest frame at bit 0 -- after the 32 frames of a tile it IS the bit-reversed word
+//   the backtrack wants (no per-block shifts, no BREV, no reset).  Identical to kCellExact whenever no NaN enters the
+//   recurrence: for non-NaN operands fmax is the select (Q is never -0: (+0) + v and fmax of non-(-0) values are
+//   not -0, by induction from Q = 0 / max_neg_val), a - b of distinct floats never rounds to zero and a - a = +0, so
+//   signbit(v_cur - v_prev) == (v_prev > v_cur); inf - inf = NaN (canonical, sign 0) where inf > inf is false.
+//   A NaN operand differs (fmax drops a NaN v_cur, the select keeps it).  Used by the fused kernel, whose values are
+//   its own finite log-prior sums; tests/test_gpu_logprior.py checks its paths bit-exactly against the reference MAS
+//   of exactly those values.
 #ifndef MAS_CELL_VARIANT
 #define MAS_CELL_VARIANT 0
 #endif
-template <int BITPOS>
+constexpr int kCellExact = 0, kCellSign = 1;
+template <int CK, int BITPOS>
 __device__ __forceinline__ float mas_cell(float v_cur, float v_prev, float v, uint32_t &bits) {
+    if constexpr (CK == kCellSign) {
+        const float q = fmaxf(v_cur, v_prev) + v;
+        bits = __funnelshift_l(__float_as_uint(v_cur - v_prev), bits, 1);
+        return q;
+    } else {
 #if MAS_CELL_VARIANT == 0
     float q;
     asm("{\n"
@@ -120,6 +140,7 @@ __device__ __forceinline__ float mas_cell(float v_cur, float v_prev, float v, ui
     bits |= d ? (1u << BITPOS) : 0u;
     return (d ? v_prev : v_cur) + v;
 #endif
+    }
 }
 
 // Predicate registers are the scarce resource of the tile body: every cell needs one for its
@@ -167,7 +188,7 @@ __device__ __forceinline__ void load_group(float4 (&v)[R], const float *lane_til
 //   hq      Q of the row above the WARP at this frame (what lane 0 takes instead of a shuffle)
 //   dlb     DIAG only: lane_global - (first frame of the block) / R; the lane owns the diagonal cell of this
 //           frame, in row K % R, exactly when dlb == K / R      (R | 8 | first frame of the block)
-template <int R, int K, bool DIAG>
+template <int R, int K, bool DIAG, int CK>
 __device__ __forceinline__ void dp_frame(float (&q)[R], uint32_t (&acc)[R], float &up, const float (&v)[R], float hq,
                                          uint32_t lane0_mask, int dlb, float neg, uint32_t hout_addr) {
     float up_next = up;
@@ -176,7 +197,7 @@ __device__ __forceinline__ void dp_frame(float (&q)[R], uint32_t (&acc)[R], floa
         float v_cur = q[r];
         if (DIAG && r == K % R) v_cur = (dlb == K / R) ? neg : v_cur;      // x == y (core.pyx:19-20)
         const float v_prev = (r == 0) ? up : q[r - 1];
-        q[r] = mas_cell<24 + K>(v_cur, v_prev, v[r], acc[r]);
+        q[r] = mas_cell<CK, 24 + K>(v_cur, v_prev, v[r], acc[r]);
         if (r == R - 1) {
             sts_f32(hout_addr + 4u * K, q[R - 1]);
             const float s = __shfl_up_sync(kFullMask, q[R - 1], 1);
@@ -187,23 +208,23 @@ __device__ __forceinline__ void dp_frame(float (&q)[R], uint32_t (&acc)[R], floa
 }
 
 // four frames (group H = 0 / 1 of an 8-frame block)
-template <int R, int H, bool DIAG>
+template <int R, int H, bool DIAG, int CK>
 __device__ __forceinline__ void dp_group(float (&q)[R], uint32_t (&acc)[R], float &up, const float4 (&v4)[R],
                                          const float4 &h4, uint32_t lane0_mask, int dlb, float neg,
                                          uint32_t hout_addr) {
     float v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].x;
-    dp_frame<R, 4 * H + 0, DIAG>(q, acc, up, v, h4.x, lane0_mask, dlb, neg, hout_addr);
+    dp_frame<R, 4 * H + 0, DIAG, CK>(q, acc, up, v, h4.x, lane0_mask, dlb, neg, hout_addr);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].y;
-    dp_frame<R, 4 * H + 1, DIAG>(q, acc, up, v, h4.y, lane0_mask, dlb, neg, hout_addr);
+    dp_frame<R, 4 * H + 1, DIAG, CK>(q, acc, up, v, h4.y, lane0_mask, dlb, neg, hout_addr);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].z;
-    dp_frame<R, 4 * H + 2, DIAG>(q, acc, up, v, h4.z, lane0_mask, dlb, neg, hout_addr);
+    dp_frame<R, 4 * H + 2, DIAG, CK>(q, acc, up, v, h4.z, lane0_mask, dlb, neg, hout_addr);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = v4[r].w;
-    dp_frame<R, 4 * H + 3, DIAG>(q, acc, up, v, h4.w, lane0_mask, dlb, neg, hout_addr);
+    dp_frame<R, 4 * H + 3, DIAG, CK>(q, acc, up, v, h4.w, lane0_mask, dlb, neg, hout_addr);
 }
 
 // A whole 32-frame tile as a loop of four 8-frame blocks (value and halo groups register double-buffered across the
@@ -212,7 +233,8 @@ __device__ __forceinline__ void dp_group(float (&q)[R], uint32_t (&acc)[R], floa
 //   va, ha   group 0 of THIS tile, already loaded (dp_tile_prefetch: for tile j + 1 that happens before the tail work
 //            of tile j, so the tile starts without a shared-memory round trip); garbage on exit
 //   hin      32 floats in shared memory: Q of the row above the warp at the tile's frames
-//   acc      must be zero on entry; on exit bit k of acc[r] is the direction bit of frame k
+//   acc      kCellExact: must be zero on entry; on exit bit k of acc[r] is the direction bit of frame k
+//            kCellSign:  any value on entry; on exit bit 31 - k is the direction bit of frame k (dp_store_words)
 template <int R, int XP>
 __device__ __forceinline__ void dp_tile_prefetch(float4 (&va)[R], float4 &ha, const float *lane_tile, const float *hin,
                                                  int lane7) {
@@ -220,7 +242,7 @@ __device__ __forceinline__ void dp_tile_prefetch(float4 (&va)[R], float4 &ha, co
     ha = *reinterpret_cast<const float4 *>(hin);
 }
 
-template <int R, int XP, bool DIAG>
+template <int R, int XP, bool DIAG, int CK = kCellExact>
 __device__ __forceinline__ void dp_tile_pre(float (&q)[R], uint32_t (&acc)[R], float &up, float4 (&va)[R], float4 &ha,
                                             const float *lane_tile, const float *hin, int lane7, uint32_t lane0_mask,
                                             int dl0, float neg, uint32_t hout_addr) {
@@ -231,25 +253,42 @@ __device__ __forceinline__ void dp_tile_pre(float (&q)[R], uint32_t (&acc)[R], f
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         load_group<R, XP>(vb, lane_tile, lane7, 2 * i + 1); hb = h4[2 * i + 1];
+        if constexpr (CK == kCellExact) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] >>= 8;
-        dp_group<R, 0, DIAG>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+            for (int r = 0; r < R; ++r) acc[r] >>= 8;
+        }
+        dp_group<R, 0, DIAG, CK>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
         // next block's first group; the last block re-reads group 0 (no branch in the body)
         load_group<R, XP>(va, lane_tile, lane7, (2 * i + 2) & 7); ha = h4[(2 * i + 2) & 7];
-        dp_group<R, 1, DIAG>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+        dp_group<R, 1, DIAG, CK>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
         dl0 -= 8 / R;
         hout_addr += 32u;
     }
 }
 
-template <int R, int XP, bool DIAG>
+template <int R, int XP, bool DIAG, int CK = kCellExact>
 __device__ __forceinline__ void dp_tile(float (&q)[R], uint32_t (&acc)[R], float &up, const float *lane_tile,
                                         const float *hin, int lane7, uint32_t lane0_mask, int dl0, float neg,
                                         uint32_t hout_addr) {
     float4 va[R];
     float4 ha;
     dp_tile_prefetch<R, XP>(va, ha, lane_tile, hin, lane7);
-    dp_tile_pre<R, XP, DIAG>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, neg, hout_addr);
+    dp_tile_pre<R, XP, DIAG, CK>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, neg, hout_addr);
+}
+
+// Direction words of a finished tile, "walk ready" for the backtrack: bit-reversed (bit 31-k <-> frame 32j + k), the
+// forced move of the diagonal cell (index == y, core.pyx:34) OR-ed in, the word of token 0 (which never moves) zero.
+// Leaves acc ready for the next tile.
+template <int R, int CK>
+__device__ __forceinline__ void dp_finish_words(uint32_t (&acc)[R], uint32_t (&out)[R], int x0, int j, bool diag) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        uint32_t w = acc[r];
+        if constexpr (CK == kCellExact) { w = __brev(w); acc[r] = 0u; }
+        if (diag && ((x0 + r) >> 5) == j) w |= 0x80000000u >> ((x0 + r) & 31);
+        out[r] = w;
+    }
+    if (x0 == 0) out[0] = 0u;
 }
 
 template <int R>
@@ -369,26 +408,39 @@ __device__ __forceinline__ uint32_t bt_tile_mask(int j, int ntiles, int t_y) {
 // along such stretches too, so every chain is followed to its end (at most 32 tokens per tile).  The row
 // groups of a tile are split between the helper warp (groups [0, kGH)) and the TMA producer warp (the rest,
 // in the slack the NS-deep ring gives it); what the producer did not get to is shared by all warps after the DP.
+// Per token the chain is TWO dependent ALU ops: with m = word & mask,
+//     mask' = ~(m ^ (m - 1))          (the bits strictly above the lowest set bit of m; m == 0 -> mask' == 0, sticky)
+// and the next token's m' = word' & mask' folds into the same LOP3:  m' = word' & ~(m ^ (m - 1)).
 template <int NG>
 __device__ __forceinline__ void bt_transfer_groups(const uint32_t *p, unsigned char *nj, int xbase, int xmax, uint32_t mask0,
                                                    int lane) {
-    uint32_t mk[NG];
+    uint32_t m[NG], m1[NG];       // m of the previous token and m - 1 (start: m = mask + ... such that ~(m ^ m1) == mask)
     int n[NG];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) { mk[g] = (xbase + 32 * g + lane <= xmax) ? mask0 : 0u; n[g] = 0; }
+    for (int g = 0; g < NG; ++g) {
+        // ~(m ^ m1) = mask0 (or 0 for lanes beyond xmax): m = 0, m1 = ~mask
+        const uint32_t mk = (xbase + 32 * g + lane <= xmax) ? mask0 : 0u;
+        m[g] = 0u; m1[g] = ~mk; n[g] = 0;
+    }
     // token 0's word is zero, so a chain that reaches it stops there (sticky zero): indices below row 0 are
-    // only ever read with mk == 0 and need no bounds check (they stay inside the CTA's shared memory)
+    // only ever read with a zero mask and need no bounds check (they stay inside the CTA's shared memory)
     for (int k0 = 0; k0 < 32; k0 += 8) {
+        uint32_t w[8][NG];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+            for (int g = 0; g < NG; ++g) w[kk][g] = p[32 * g - (k0 + kk)];
         uint32_t alive = 0u;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-            const int k = k0 + kk;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                const uint32_t m = p[32 * g - k] & mk[g];
-                if (m != 0u) n[g] = k + 1;
-                mk[g] = m ^ (0u - m);
-                if (kk == 7) alive |= mk[g];
+                uint32_t mn;
+                asm("lop3.b32 %0, %1, %2, %3, 0x90;" : "=r"(mn) : "r"(w[kk][g]), "r"(m[g]), "r"(m1[g]));    // a & ~(b ^ c)
+                m[g] = mn;
+                m1[g] = mn - 1u;
+                if (mn != 0u) n[g] = k0 + kk + 1;
+                if (kk == 7) alive |= mn;
             }
         }
         if (!__any_sync(kFullMask, alive != 0u)) break;
@@ -411,6 +463,24 @@ __device__ __forceinline__ void bt_tile_transfer(const uint32_t *bits_j, unsigne
         else if (ng == 3) bt_transfer_groups<3>(p, nj, 32 * gq, xmax, mask0, lane);
         else if (ng == 2) bt_transfer_groups<2>(p, nj, 32 * gq, xmax, mask0, lane);
         else if (ng == 1) bt_transfer_groups<1>(p, nj, 32 * gq, xmax, mask0, lane);
+    }
+}
+
+// The same for a RUNTIME share of the tile's row groups: helper h of H takes groups [n*h/H, n*(h+1)/H) of the
+// n = (xmax >> 5) + 1 groups that hold enterable tokens, so the helpers' loads are balanced whatever t_x is.
+__device__ __forceinline__ void bt_tile_transfer_share(const uint32_t *bits_j, unsigned char *nj_j, int j, int t_x,
+                                                       uint32_t mask0, int lane, int h, int H) {
+    const int xmax = min(t_x - 1, 32 * j + 31);
+    const int n = (xmax >> 5) + 1;
+    const int g1 = (n * (h + 1)) / H;
+    for (int gq = (n * h) / H; gq < g1; gq += 4) {
+        const int ng = min(4, g1 - gq);                              // warp-uniform
+        const uint32_t *p = bits_j + 32 * gq + lane;
+        unsigned char *nj = nj_j + 32 * gq;
+        if (ng >= 4) bt_transfer_groups<4>(p, nj, 32 * gq, xmax, mask0, lane);
+        else if (ng == 3) bt_transfer_groups<3>(p, nj, 32 * gq, xmax, mask0, lane);
+        else if (ng == 2) bt_transfer_groups<2>(p, nj, 32 * gq, xmax, mask0, lane);
+        else bt_transfer_groups<1>(p, nj, 32 * gq, xmax, mask0, lane);
     }
 }
 
@@ -854,18 +924,10 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
 
                 // ---- direction words of this tile, walk-ready: forced move of the diagonal cell (index == y,
                 // core.pyx:34) OR-ed in, token 0 (never moves) cleared, bit-reversed (bit 31-k <-> frame k) ----
-                if (diag) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (((x0 + r) >> 5) == j) acc[r] |= 1u << ((x0 + r) & 31);
-                }
-                if (x0 == 0) acc[0] = 0u;
-#pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] = __brev(acc[r]);
-                if (SMEM_BITS) store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, acc);
-                else store_words<R>(gbits_b + (size_t)j * P.gbits_rows_pitch + x0, acc);
-#pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] = 0u;
+                uint32_t words[R];
+                dp_finish_words<R, kCellExact>(acc, words, x0, j, diag);
+                if (SMEM_BITS) store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, words);
+                else store_words<R>(gbits_b + (size_t)j * P.gbits_rows_pitch + x0, words);
 
                 __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
                 if (elect_one()) {                              // a fresh predicate every tile, nothing to hoist
