@@ -155,6 +155,9 @@ __device__ __forceinline__ float mas_cell(float v_cur, float v_prev, float v, ui
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
 }
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ float bitselect(uint32_t mask, float a, float b) {      // mask ? a : b, bitwise
     uint32_t r;
     asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(mask));
@@ -577,28 +580,40 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
     }
     __syncthreads();
     if (dbg && tid == 0) dbg[14] = clock64();
-    // one thread per tile: start frames.  Tile jt goes to lane jt / nwarps of warp jt % nwarps, so the (divergent,
-    // differently long) token chains of the tiles run on different warps instead of serialising inside warp 0.
-    constexpr int kNW = NTHREADS / 32;
-    for (int jt = warp + kNW * lane; jt < ntiles; jt += NTHREADS) {
-        const uint32_t *bj = bits_s + (size_t)jt * XP;
-        const int lo = jt > 0 ? xin[jt - 1] : 0;
-        uint32_t mk = bt_tile_mask(jt, ntiles, t_y);
-        // eight tokens per round: their words are fetched with independent loads, then each token costs two ALU ops
-        // (one dependent shared-memory load per token made a 25-token tile the whole tail)
-        for (int x = xin[jt]; x > lo; x -= 8) {
+    // one LANE per tile: start frames of the tokens (lo, xin[jt]] that begin in tile jt.  All lanes of a warp run the
+    // same loop (trip count = the largest token count among its tiles), eight tokens per round: their words are fetched
+    // with independent loads, then each token costs two dependent ALU ops (bt_transfer_groups' chain); a lane that has
+    // run out of tokens carries a zero m (sticky).
+    for (int j0 = warp * 32; j0 < ntiles; j0 += NTHREADS) {
+        const int jt = j0 + lane;
+        const bool live = jt < ntiles;
+        const uint32_t *bj = bits_s + (size_t)(live ? jt : 0) * XP;
+        const int hi = live ? xin[jt] : 0;
+        const int lo = (live && jt > 0) ? xin[jt - 1] : 0;
+        const int cnt = live ? hi - lo : 0;
+        const int maxcnt = __reduce_max_sync(kFullMask, cnt);
+        uint32_t m = 0u, m1 = ~(live ? bt_tile_mask(jt, ntiles, t_y) : 0u);      // ~(m ^ m1) == the tile's frame mask
+        const uint32_t tok_addr = smem_u32(tok + hi);
+        const bool heads_on = hd != nullptr;                                     // block-uniform
+        const uint32_t dump_addr = smem_u32(xin + (live ? jt : 0));
+        const int dump_val = xin[live ? jt : 0];
+        const uint32_t hd_addr = heads_on ? smem_u32(hd) : 0u;
+        for (int c = 0; c < maxcnt; c += 8) {
             uint32_t w[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = bj[max(x - k, 0)];
+            for (int k = 0; k < 8; ++k) w[k] = bj[max(hi - c - k, 0)];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                if (x - k > lo) {
-                    const uint32_t m = w[k] & mk;
-                    const int st = (jt << 5) + 32 - __ffs((int)m);
-                    tok[x - k] = st;
-                    if (hd != nullptr) hd[st] = x - k;
-                    mk = m ^ (0u - m);
-                }
+                uint32_t mn;
+                asm("lop3.b32 %0, %1, %2, %3, 0x90;" : "=r"(mn) : "r"(c + k < cnt ? w[k] : 0u), "r"(m), "r"(m1));   // a & ~(b ^ c)
+                m = mn;
+                m1 = mn - 1u;
+                // branch-free (eight divergent branches per round cost more than the whole chain): a lane without a
+                // token left stores its own xin entry back to where it read it from
+                const int st = (jt << 5) + 32 - __ffs((int)mn);
+                const bool on = mn != 0u;
+                sts_s32(on ? tok_addr - 4u * (uint32_t)(c + k) : dump_addr, on ? st : dump_val);
+                if (heads_on) sts_s32(on ? hd_addr + 4u * (uint32_t)st : dump_addr, on ? hi - c - k : dump_val);
             }
         }
         if (jt == 0 && hd != nullptr) hd[0] = 0;                           // token 0 starts at frame 0
