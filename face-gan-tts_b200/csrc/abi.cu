@@ -37,6 +37,8 @@ Opt g_opts[] = {
     {"fused_dump_ptr_lo", {0}},      // tests only: [B,Tx,Ty] float buffer receiving the fused kernel's value tiles (device pointer halves)
     {"fused_dump_ptr_hi", {0}},
     {"pdl", {1}},                    // 1: fused kernel / path expansion launch with programmatic stream serialization
+    {"fused_exp", {0}},              // diagnostics only (MASB200_PROF builds): bit 0 the DP warps ignore the readiness flags, bit 1 park the helper warps, bit 2 park the producers (results invalid)
+    {"fused_pair", {1}},             // 1: texts of 129..256 tokens run as a 2-CTA cluster per utterance when 2B <= SMs, 0: never, 2: always
     {"fused_impl", {0}},             // 0 auto (fused kernel when the shape is covered), 1 force the serial form
 };
 }  // namespace

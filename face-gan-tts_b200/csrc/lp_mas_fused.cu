@@ -64,15 +64,19 @@ struct FusedParams {
     const float *mu;     // [B,F,Tx]
     float cst;           // -0.5 * F * log(2 pi)
     float *value_dump;   // tests only: [B,Tx,Ty], receives the value tiles the search consumed (null normally)
+    int exp;             // diagnostics (MASB200_FUSED_PROF builds): see option fused_exp
 };
 
 // Shared-memory carve-up (bytes from a 1024-aligned base):
 //   [ring: NS value tiles][halo rings][raw y: 2][hi: 2][lo: 2][ysq partials][mbarriers][flags][zero buffer][direction words + transfer tables]
 // The [F][Tx] staging of mu_x for the prologue aliases the front (ring, halo, possibly raw).
-template <int KS, int W>
+// PAIR (2-CTA cluster per utterance, one M-tile per CTA): the home CTA (rank 0) keeps the direction words of BOTH
+// M-tiles (XPT rows); behind them every CTA has the one-shot mbarriers of the cross-CTA hand-offs and the peer's halo row.
+template <int KS, int W, bool PAIR = false>
 struct FusedSmem {
     static constexpr int F = 8 * KS;
     static constexpr int XP = 32 * kFR * W;
+    static constexpr int XPT = PAIR ? 2 * XP : XP;               // text rows of the utterance covered by the direction words
     using M = MasSmem<kFR, W>;
     static constexpr uint32_t kRaw = (uint32_t)F * 32u * 4u;      // one raw y tile [F][32 frames]
     static constexpr int FE = F + 8;                              // K extent of an operand tile: F mel bins + the extra K step
@@ -87,8 +91,32 @@ struct FusedSmem {
     __host__ __device__ static constexpr size_t off_zero(int ns) { return ((off_flags(ns) + 128 + 127) / 128) * 128; }
     __host__ __device__ static constexpr size_t off_bits(int ns) { return off_zero(ns) + kZeroBytes; }
     // direction words (4 B) + transfer table (1 B) per row and tile
-    __host__ __device__ static constexpr size_t total(int ns, int ntiles) { return off_bits(ns) + (size_t)5 * ntiles * XP; }
+    __host__ __device__ static constexpr size_t off_pair(int ns, int ntiles) { return ((off_bits(ns) + (size_t)5 * ntiles * XPT + 15) / 16) * 16; }
+    // PAIR: [ntiles] halo mbarriers + [ntiles] direction-word mbarriers + [ntiles][32] halo floats
+    __host__ __device__ static constexpr size_t total(int ns, int ntiles) {
+        return off_pair(ns, ntiles) + (PAIR ? (size_t)ntiles * (8 + 8 + 128) : 0);
+    }
 };
+
+// ---- 2-CTA cluster helpers (PAIR) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// the shared::cluster address of `p` (an address in THIS CTA's shared memory) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 16 bytes into a peer CTA's shared memory, counted on the peer's mbarrier when they have landed
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
+}
 
 // in-loop wait / body cycle accumulators (scripts/fused_phases.py); off in production builds: the clock reads sit in
 // the latency-critical loops
@@ -96,10 +124,12 @@ struct FusedSmem {
 #define MASB200_FUSED_PROF 0
 #endif
 #if MASB200_FUSED_PROF
+#define PROF_EXP(bit) ((FP.exp >> (bit)) & 1)
 #define PROF_DECL(...) long long __VA_ARGS__
 #define PROF_T(var) const long long var = clock64()
 #define PROF_ADD(acc, t0) acc += clock64() - (t0)
 #else
+#define PROF_EXP(bit) 0
 #define PROF_DECL(...)
 #define PROF_T(var)
 #define PROF_ADD(acc, t0)
@@ -114,13 +144,15 @@ __device__ __forceinline__ void add_f32x2(float &x0, float &x1, float a0, float 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
 }
 
-template <int KS, int W>
+template <int KS, int W, bool PAIR>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ymap) {
-    using FS = FusedSmem<KS, W>;
+    static_assert(!PAIR || W == 1, "a CTA of a pair holds one M-tile");
+    using FS = FusedSmem<KS, W, PAIR>;
     constexpr int R = kFR;
     constexpr int F = 8 * KS;
     constexpr int XP = FS::XP;
+    constexpr int XPT = FS::XPT;
     constexpr int NT = kTileFrames;
     constexpr int kTileFloats = XP * kTilePitch;
     constexpr uint32_t kSbo = (uint32_t)FS::FE * 32u;         // 8 frames x (F + 8) K values x 4 B per row group of an operand tile
@@ -149,7 +181,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     //   ((f*W + mt)*4 + q)*32 + (l ^ 8q)      -- coalesced global reads land conflict-free, and so do the readers
     float *mu_s = reinterpret_cast<float *>(smem_raw);
 
-    const int b = blockIdx.x;
+    // PAIR: CTA rank r of the cluster owns text rows [128 r, 128 r + 128) of utterance blockIdx.x / 2; rank 0 is the home
+    // CTA (direction words of all rows, backtrack, outputs)
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int row0 = PAIR ? 128 * rank : 0;
+    const int b = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);     // provably warp-uniform for ptxas
     const int lane = tid & 31;
@@ -165,6 +201,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 
     // ---- per-item validation (the reference is undefined here: core.pyx:34) ----
     if (t_x < 1 || t_y < 1 || t_x > P.Tx || t_y > P.Ty || t_x > t_y) {
+        if (rank != 0) return;
         for (int x = tid; x < P.Tx; x += kFusedThreads) { start_b[x] = 0; dur_b[x] = 0; }
         if (P.frame_token)
             for (int y = tid; y < P.Ty; y += kFusedThreads) P.frame_token[(size_t)b * P.Ty + y] = -1;
@@ -173,12 +210,20 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         write_path_any(P, b, start_b, dur_b, tid, kFusedThreads);
         return;
     }
-    if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_OK;
+    if (P.status && tid == 0 && rank == 0) P.status[b] = MAS_B200_ITEM_OK;
 
     const int ntiles = (t_y + NT - 1) / NT;
-    const int w_act = (t_x + 32 * R - 1) / (32 * R);          // active DP warps == M-tiles with valid rows
-    unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XP);   // [ntiles][XP] transfer table
-    long long *dbg = P.dbg ? P.dbg + (size_t)b * 32 : nullptr;   // diagnostics: phase stamps [0..15], wait cycles [16..31]
+    const int w_tot = (t_x + 32 * R - 1) / (32 * R);          // M-tiles of the utterance with valid rows
+    // a pair's second CTA has nothing to do for a text of <= 128 tokens: it leaves before any cluster-wide step (exited
+    // threads count as arrived at the cluster barrier)
+    if (PAIR && rank >= w_tot) return;
+    const int w_act = PAIR ? 1 : w_tot;                       // active DP warps == M-tiles of THIS CTA
+    const bool peer = PAIR && w_tot == 2;                     // the other CTA of the pair is at work too
+    unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XPT);  // [ntiles][XPT] transfer table
+    uint64_t *bar_h = reinterpret_cast<uint64_t *>(smem_raw + FS::off_pair(NS, ntiles));     // PAIR [ntiles]: halo row of tile j has landed (rank 1)
+    uint64_t *bar_b = bar_h + ntiles;                                                          // PAIR [ntiles]: rank 1's direction words of tile j have landed (rank 0)
+    float *halo_full = reinterpret_cast<float *>(bar_b + ntiles);                              // PAIR [ntiles][32]: Q of text row 127 (rank 1)
+    long long *dbg = P.dbg ? P.dbg + ((size_t)rank * P.B + b) * 32 : nullptr;   // diagnostics ([2B][32] for a pair): phase stamps [0..15], wait cycles [16..31]
     if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
     // the prologue's mu_x staging reaches into the raw y buffers: y tiles (and everything behind them) start late
     const bool late_start = (size_t)F * W * 128 * 4 > FS::off_raw(NS);
@@ -189,14 +234,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     constexpr int kMuCols = 4 * W;                            // 32-position column groups of a row
     float mu_reg[kMuRows][kMuCols];
     {
-        const float *mu_b = FP.mu + (size_t)b * F * P.Tx + lane;
+        const float *mu_b = FP.mu + (size_t)b * F * P.Tx + row0 + lane;
 #pragma unroll
         for (int k = 0; k < kMuRows; ++k) {
             const int f = warp + kFusedWarps * k;
             const float *rp = mu_b + (size_t)f * P.Tx;
 #pragma unroll
             for (int j = 0; j < kMuCols; ++j)
-                mu_reg[k][j] = (f < F && lane + 32 * j < t_x) ? __ldg(rp + 32 * j) : 0.f;
+                mu_reg[k][j] = (f < F && row0 + lane + 32 * j < t_x) ? __ldg(rp + 32 * j) : 0.f;
         }
     }
 
@@ -212,6 +257,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         hprog[W] = 0x7fffffff;                               // the flag a lane without anything to wait for polls
         hprog[W + 1] = 0;
         for (int i = 0; i < 4 * W; ++i) eprog[i] = 0;
+        mbar_fence_init();
+    }
+    if (PAIR && peer && tid >= 32 && tid < 32 + ntiles) {
+        // one-shot hand-off barriers, armed for the bytes the peer will send: rank 1 receives the halo row of every tile
+        // (32 floats), rank 0 rank 1's direction words (128 rows x 4 bytes)
+        uint64_t *bar = (rank == 0 ? bar_b : bar_h) + (tid - 32);
+        mbar_init(bar, 1);
+        mbar_arrive_expect_tx(bar, rank == 0 ? 512u : 128u);
         mbar_fence_init();
     }
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
@@ -239,6 +292,9 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(kFullMask, *tmem_slot, 0);
+    // both CTAs' hand-off barriers are armed (block barrier above): tell the peer; nothing is sent to it before the
+    // matching wait below, which the prologue hides
+    if (PAIR && peer) cluster_arrive();
     if (dbg && tid == 0) dbg[8] = clock64();
     // TMEM columns: M-tile mt: A hi at mt*(2F+8), A lo at +F, the extra K step at +2F; D of (stage p, M-tile mt) behind them
     auto col_a = [](int mt, int part) { return (uint32_t)(mt * (2 * F + 8) + part * F); };
@@ -306,8 +362,13 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         }
     }
     if (dbg && tid == 0) dbg[9] = clock64();
+    if (PAIR && peer) cluster_wait();
 
-    if (warp == kWarpMma) {
+    // diagnostics (fused_exp): what slows the DP warps down?  Roles can be parked; the DP warps then run over whatever is in the ring
+    const bool is_help = warp == kWarpHelpA || warp == kWarpHelpB || warp == kWarpHelpC;
+    const bool is_dp = warp >= kWarpDp && warp < kWarpDp + W;
+    const int rw = ((PROF_EXP(1) && is_help) || (PROF_EXP(2) && !is_help && !is_dp)) ? 99 : warp;
+    if (rw == kWarpMma) {
         // ======================= TMA loads + MMA issue (warp-uniform; one elected lane acts) =======================
         if (late_start) {
             mbar_wait_warp(&bar_aready[W - 1], 0);
@@ -374,7 +435,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 #if MASB200_FUSED_PROF
         if (dbg && lane == 0) { dbg[16] = w_split; dbg[17] = w_dempty; }
 #endif
-    } else if (warp == kWarpSplit || warp == kWarpSplit + 1) {
+    } else if (rw == kWarpSplit || rw == kWarpSplit + 1) {
         // ======================= operand split: raw [F][32] -> hi/lo K-major core matrices + the ysq K step =======================
         // thread = (frame n = lane, mel-bin chunks kc = sw, sw + 2, ...): 4 conflict-free LDS.32 down a column of the raw
         // tile, one STS.128 per operand into core matrix (n / 8, kc), row n % 8.
@@ -435,7 +496,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 #if MASB200_FUSED_PROF
         if (dbg && sw == 0 && lane == 0) { dbg[18] = w_bfree; dbg[19] = w_raw; }
 #endif
-    } else if (warp < 4) {
+    } else if (rw < 4) {
         // ======================= epilogue warps: TMEM lane quadrant = warp =======================
         // per tile: D (TMEM) = the finished log-prior values -> ring slot of this lane's text row
         const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
@@ -464,7 +525,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                     for (int c = 0; c < 8; ++c)
                         *reinterpret_cast<uint4 *>(rowp + ((c ^ (lane & 7)) << 2)) = make_uint4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
                     if (FP.value_dump != nullptr) {                // tests only
-                        const int x = 128 * mt + 4 * lane + warp;
+                        const int x = row0 + 128 * mt + 4 * lane + warp;
                         float *dst = FP.value_dump + ((size_t)b * P.Tx + x) * P.Ty + g * NT;
                         if (x < P.Tx)
                             for (int c = 0; c < 8; ++c)
@@ -480,9 +541,9 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 #if MASB200_FUSED_PROF
         if (dbg && tid == 0) { dbg[20] = w_dfull; dbg[21] = w_rempty; }
 #endif
-    } else if (warp == kWarpZero) {
+    } else if (rw == kWarpZero) {
         // ======================= dense path, part 1: the all-zero [Tx,Ty] block, in the shadow of the search =======================
-        if (P.path != nullptr) {
+        if (P.path != nullptr && rank == 0) {
             unsigned char *dst = reinterpret_cast<unsigned char *>(P.path) + (size_t)b * P.Tx * P.Ty * 4;
             const size_t total = (size_t)P.Tx * P.Ty * 4;                      // Ty % 4 == 0: a multiple of 16 bytes
             if (elect_one()) {
@@ -496,7 +557,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             }
             __syncwarp();
         }
-    } else if (warp == kWarpHelpA || warp == kWarpHelpB || warp == kWarpHelpC) {
+    } else if ((rw == kWarpHelpA || rw == kWarpHelpB || rw == kWarpHelpC) && rank == 0) {
         // ======================= backtrack helpers: transfer tables behind the LAST active DP warp =======================
         // three warps share the row groups of every finished tile evenly (they have to keep up with the DP warps: what
         // they have not done when the search ends is on the critical path)
@@ -510,11 +571,13 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 #ifdef MASB200_HELP_PROF
             const long long c0 = clock64();
             if (known < jt + 1) { known = flag_wait_ge_warp(flag_last, jt + 1); ++nwait; }
+            if (PAIR && peer) mbar_wait_warp(&bar_b[jt], 0);
             const long long c1 = clock64();
 #else
             if (known < jt + 1) known = flag_wait_ge_warp(flag_last, jt + 1);
+            if (PAIR && peer) mbar_wait_warp(&bar_b[jt], 0);             // the peer CTA's direction words of the tile are here
 #endif
-            bt_tile_transfer_share(bits_s + (size_t)jt * XP, nj_s + (size_t)jt * XP, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane, h, 3);
+            bt_tile_transfer_share(bits_s + (size_t)jt * XPT, nj_s + (size_t)jt * XPT, jt, t_x, bt_tile_mask(jt, ntiles, t_y), lane, h, 3);
 #ifdef MASB200_HELP_PROF
             hw += c1 - c0; hk += clock64() - c1;
 #endif
@@ -523,29 +586,51 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         if (dbg && lane == 0) { dbg[16 + 3 * h] = hw; dbg[17 + 3 * h] = hk; dbg[18 + 3 * h] = nwait; }
 #endif
         if (dbg && lane == 0 && h < 2) dbg[28 + h] = clock64();
-    } else if (warp >= kWarpDp && warp < kWarpDp + w_act) {
+    } else if (PAIR && rw == kWarpDp + 1 && rank == 0 && peer) {
+        // ======================= PAIR, rank 0: halo forwarding.  The DP warp leaves its bottom row (Q of text row 127) in
+        // the CTA's own halo buffer like a DP warp with a local consumer would; this warp sends every finished tile's
+        // 32 floats to the peer with st.async -- 16 bytes per lane, delivered into the peer's shared memory and counted on
+        // its mbarrier of the tile.  Nothing of the hand-off is in the DP warp's instruction stream. =======================
+        const uint32_t raddr = mapa_u32(halo_full, 1) + 16u * (lane & 7), rbar = mapa_u32(bar_h, 1);
+        // (polling the DP warp's progress flag, like the helpers: measured faster for the DP warp than sleeping on an mbarrier)
+        int known = 0;
+        for (int jt = 0; jt < ntiles; ++jt) {
+            if (known < jt + 1) known = flag_wait_ge_warp(hprog, jt + 1);
+            if (lane < 8) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(halo_full + jt * NT + 4 * lane);
+                st_async_v4(raddr + (uint32_t)jt * (NT * 4u), rbar + (uint32_t)jt * 8u, v.x, v.y, v.z, v.w);
+            }
+            __syncwarp();
+        }
+    } else if (rw >= kWarpDp && rw < kWarpDp + w_act) {
         // ======================= DP warps (see mas_forward_kernel: nothing in the tile loop may branch or predicate
         // on a loop-invariant condition; role differences are ADDRESSES) =======================
         const int w = warp - kWarpDp;
-        const int lane_cta = 32 * w + lane;
-        const int x0 = lane_cta * R;                             // lane's first text position
-        const int xw0 = 32 * R * w;                              // warp's first text position
+        const int lane_cta = 32 * w + lane;                      // lane among the CTA's DP lanes (ring rows)
+        const int lane_utt = row0 / R + lane_cta;                // lane among the utterance's (direction words, diagonal)
+        const int x0 = lane_utt * R;                             // lane's first text position
+        const int xw0 = row0 + 32 * R * w;                       // warp's first text position
         const int lane7 = lane & 7;
         const uint32_t lane0_mask = (lane == 0) ? 0xffffffffu : 0u;
-        const bool has_consumer = (w + 1 < w_act);
+        const bool has_consumer = PAIR ? (rank == 0 && peer) : (w + 1 < w_act);
         float *hconst = hbuf + (size_t)W * HS * NT;              // warp 0's halo input (one constant row)
         float *hdump = hconst + (size_t)HS * NT;                 // [W][160] where lanes without a consumer store
-        const float *hb_in = (w > 0) ? hbuf + (size_t)(w - 1) * HS * NT : hconst;
-        const int hin_step = (w > 0) ? NT : 0;
-        float *hb_out = hbuf + (size_t)w * HS * NT;
+        // halo input: the previous DP warp's ring; the constant row above text position 0; PAIR rank 1: the row the peer
+        // CTA's DP warp sends, one slot per tile
+        const bool halo_remote = PAIR && rank == 1;
+        const float *hb_in = halo_remote ? halo_full : ((w > 0) ? hbuf + (size_t)(w - 1) * HS * NT : hconst);
+        const int hin_step = (halo_remote || w > 0) ? NT : 0;
+        float *hb_out = PAIR ? halo_full : hbuf + (size_t)w * HS * NT;
         const uint32_t hout_base = (has_consumer && lane == 31) ? smem_u32(hb_out) : smem_u32(hdump + w * FS::M::kDumpFloats + 4 * lane);
         const uint32_t hout_step = (has_consumer && lane == 31) ? NT * 4u : 0u;
         int *flag_out = hprog + w;
+        // PAIR: shared::cluster addresses of what this warp sends to the peer CTA
+        const uint32_t words_raddr = PAIR ? mapa_u32(bits_s + lane_utt * R, 0) : 0u, words_rbar = PAIR ? mapa_u32(bar_b, 0) : 0u;
         // what tile j needs, one word per lane: lanes 0..3 the four epilogue warps' progress on this warp's M-tile
         // (>= j + 1: the tile is in the ring), lane 4 the progress of DP warp w - 1 (its halo row), the other lanes a
         // word that is always satisfied.  ONE shared-memory load covers everything, and the load for tile j + 1 is
         // issued before the body of tile j, so its latency never stalls the in-order warp.
-        const int *sync_word = (lane < 4) ? eprog + 4 * w + lane : ((lane == 4 && w > 0) ? hprog + (w - 1) : hprog + W);
+        const int *sync_word = PROF_EXP(0) ? hprog + W : ((lane < 4) ? eprog + 4 * w + lane : ((lane == 4 && w > 0) ? hprog + (w - 1) : hprog + W));
 
         float q[R];
         uint32_t acc[R];
@@ -558,11 +643,12 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         // the first tile of this warp's M-tile is in the ring: the prologue is over, and with it every read of the mu_x
         // staging that aliases the halo area -- only now may the halo rows be initialised
         flag_wait_ge_warp(sync_word, 1);
-        if (w == 0) {
+        if (halo_remote) mbar_wait_warp(&bar_h[0], 0);
+        if (w == 0 && !halo_remote) {
             hconst[lane] = P.neg;                                // the row above text position 0 (core.pyx:26-27)
             __syncwarp();
-            if (dbg && lane == 0) dbg[2] = clock64();
         }
+        if (dbg && lane == 0 && w == 0) dbg[2] = clock64();
         // the first two value / halo groups of a tile are loaded as soon as the tile is known to be in the ring --
         // for tile j + 1 that is before the tail work of tile j
         float4 va[R], ha;
@@ -570,15 +656,19 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         for (int j = 0; j < ntiles; ++j) {
             const int t0 = j * NT;
             const int sync_next = flag_acquire(sync_word);       // consumed after the body
+            // PAIR rank 1: has the peer's halo row of tile j + 1 landed?  (a non-blocking probe, consumed after the body too)
+            const bool halo_next = (halo_remote && j + 1 < ntiles) ? mbar_test_warp(&bar_h[j + 1], 0) : true;
             const int next_stage = (stage + 1 == NS) ? 0 : stage + 1;
-            const int next_hs = (hs + 1 == HS) ? 0 : hs + 1;
+            const int next_hs = halo_remote ? j + 1 : ((hs + 1 == HS) ? 0 : hs + 1);
 
             const float *lane_tile = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
             const float *hin = hb_in + hs * hin_step;
-            const uint32_t hout_addr = hout_base + hs * hout_step;
             const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
-            const int dl0 = lane_cta - t0 / R;
+            const int dl0 = lane_utt - t0 / R;
             PROF_T(cb0);
+            // PAIR rank 0: the bottom row goes to slot j of the CTA's own full-length halo buffer, from where the
+            // forwarding warp sends it to the peer
+            const uint32_t hout_addr = hout_base + (uint32_t)(PAIR ? j : hs) * hout_step;
             if (diag) dp_tile_pre<R, XP, true, kFusedCell>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             else dp_tile_pre<R, XP, false, kFusedCell>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             PROF_ADD(w_body, cb0);
@@ -586,7 +676,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             // way while this tile's direction words are stored and the tile is released
             PROF_T(cw0);
             if (j + 1 < ntiles) {
-                if (!__all_sync(kFullMask, sync_next >= j + 2)) flag_wait_ge_warp(sync_word, j + 2);
+                if (!__all_sync(kFullMask, sync_next >= j + 2 && halo_next)) {
+                    flag_wait_ge_warp(sync_word, j + 2);
+                    if (halo_remote) mbar_wait_warp(&bar_h[j + 1], 0);
+                }
                 dp_tile_prefetch<R, XP>(va, ha, ring + (size_t)next_stage * kTileFloats + lane_cta * kTilePitch,
                                         hb_in + next_hs * hin_step, lane7);
             }
@@ -595,7 +688,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             // direction words of this tile, walk-ready (see mas_forward_kernel)
             uint32_t words[R];
             dp_finish_words<R, kFusedCell>(acc, words, x0, j, diag);
-            store_words<R>(bits_s + (size_t)j * XP + lane_cta * R, words);
+            if (PAIR && rank == 1)      // to the home CTA, counted on its mbarrier of this tile
+                st_async_v4(words_raddr + (uint32_t)j * (XPT * 4u), words_rbar + (uint32_t)j * 8u, words[0], words[1], words[2], words[3]);
+            else
+                store_words<R>(bits_s + (size_t)j * XPT + lane_utt * R, words);
 
             __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
             if (elect_one()) {
@@ -615,13 +711,17 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kLpTmemCols); }
     if (dbg && tid == 0) dbg[3] = clock64();
+    // PAIR: rank 0's helpers have seen every tile's direction words of the peer land (and the block barrier above hands
+    // that to all threads); rank 1's DP warp has consumed every halo row rank 0 sent.  Nothing is in flight INTO either
+    // CTA any more, and nobody reads rank 1's shared memory: rank 1 is done.
+    if (PAIR && rank != 0) return;
 
     // ================================ backtrack + outputs (the ring is idle now) ================================
     int *tok = reinterpret_cast<int *>(ring);
-    int *xin = tok + XP;
+    int *xin = tok + XPT;
     int *hd = xin + ((ntiles + 3) & ~3);
     const bool heads = P.frame_token != nullptr;
-    mas_backtrack_smem<XP, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg, heads ? hd : nullptr);
+    mas_backtrack_smem<XPT, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg, heads ? hd : nullptr);
     if (dbg && tid == 0) dbg[5] = clock64();
     // dense path, part 2: the ones -- frame t belongs to token frame_token[t]; written by the thread that produces
     // frame_token[t] (when the caller wants no frame_token the per-token form below does it)
@@ -642,9 +742,9 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 
 constexpr size_t kFusedMaxSmem = 232448 - 1024;
 
-template <int KS, int W>
+template <int KS, int W, bool PAIR>
 int fused_plan(int Tx, int Ty, int *ns_out, size_t *smem_out) {
-    using FS = FusedSmem<KS, W>;
+    using FS = FusedSmem<KS, W, PAIR>;
     const int ntiles = (Ty + kTileFrames - 1) / kTileFrames;
     int cap = option("mas_ring_stages");
     if (cap <= 0 || cap > 6) cap = 6;
@@ -652,60 +752,91 @@ int fused_plan(int Tx, int Ty, int *ns_out, size_t *smem_out) {
     while (ns < cap && FS::total(ns + 1, ntiles) <= kFusedMaxSmem) ++ns;
     if (ns < 2) return MAS_B200_ERR_UNSUPPORTED;
     // the tail's scratch (token starts, tile entry tokens, frame heads) lives in the idle ring
-    if (mas_tail_scratch_ints(FS::XP, ntiles, Ty) * sizeof(int) > FS::M::ring_bytes(ns)) return MAS_B200_ERR_UNSUPPORTED;
+    if (mas_tail_scratch_ints(FS::XPT, ntiles, Ty) * sizeof(int) > FS::M::ring_bytes(ns)) return MAS_B200_ERR_UNSUPPORTED;
+    if (PAIR && ntiles > kFusedThreads - 32) return MAS_B200_ERR_UNSUPPORTED;      // one thread arms each hand-off barrier
     *ns_out = ns;
     *smem_out = FS::total(ns, ntiles);
     return MAS_B200_OK;
 }
 
-template <int KS, int W>
+template <int KS, int W, bool PAIR>
 int fused_launch(FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
     int ns = 0;
     size_t smem = 0;
-    int rc = fused_plan<KS, W>(FP.mas.Tx, FP.mas.Ty, &ns, &smem);
+    int rc = fused_plan<KS, W, PAIR>(FP.mas.Tx, FP.mas.Ty, &ns, &smem);
     if (rc != MAS_B200_OK || dry_run) return rc;
     FP.mas.ring_stages = ns;
     static std::atomic<int> configured[16];
     int dev = 0;
     MASB200_CUDA_TRY(cudaGetDevice(&dev));
-    auto kern = lp_mas_fused_kernel<KS, W>;
+    auto kern = lp_mas_fused_kernel<KS, W, PAIR>;
     if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
         MASB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedMaxSmem));
         if (dev >= 0 && dev < 16) configured[dev].store(1, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)FP.mas.B);
+    cfg.gridDim = dim3((unsigned)FP.mas.B * (PAIR ? 2u : 1u));
     cfg.blockDim = dim3(kFusedThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (PAIR) {          // the two CTAs of an utterance: one cluster, co-scheduled, shared memory reachable from each other
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (option("pdl") != 0) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = option("pdl") != 0 ? 1 : 0;
+    cfg.numAttrs = na;
     MASB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, FP, ymap));
     return MAS_B200_OK;
 }
 
-// TMEM budget: W M-tiles of A (hi, lo, extra K step: 2F + 8 columns each) + two D stages of W x 32 columns <= 512
-int fused_dispatch(int F, FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run) {
+// TMEM budget: W M-tiles of A (hi, lo, extra K step: 2F + 8 columns each) + two D stages of W x 32 columns <= 512.
+// pair: a text of more than 128 tokens as a 2-CTA cluster, one M-tile per CTA (see lp_mas_fused_pair_wanted)
+int fused_dispatch(int F, FusedParams &FP, const CUtensorMap &ymap, cudaStream_t stream, bool dry_run, bool pair) {
     const bool one = FP.mas.Tx <= 128;
+    if (!one && pair) {
+        switch (F) {
+            case 64: return fused_launch<8, 1, true>(FP, ymap, stream, dry_run);
+            case 80: return fused_launch<10, 1, true>(FP, ymap, stream, dry_run);
+            case 96: return fused_launch<12, 1, true>(FP, ymap, stream, dry_run);
+            case 128: return fused_launch<16, 1, true>(FP, ymap, stream, dry_run);
+            default: return MAS_B200_ERR_UNSUPPORTED;
+        }
+    }
     switch (F) {
-        case 64: return one ? fused_launch<8, 1>(FP, ymap, stream, dry_run) : fused_launch<8, 2>(FP, ymap, stream, dry_run);
-        case 80: return one ? fused_launch<10, 1>(FP, ymap, stream, dry_run) : fused_launch<10, 2>(FP, ymap, stream, dry_run);
-        case 96: return one ? fused_launch<12, 1>(FP, ymap, stream, dry_run) : MAS_B200_ERR_UNSUPPORTED;
-        case 128: return one ? fused_launch<16, 1>(FP, ymap, stream, dry_run) : MAS_B200_ERR_UNSUPPORTED;
+        case 64: return one ? fused_launch<8, 1, false>(FP, ymap, stream, dry_run) : fused_launch<8, 2, false>(FP, ymap, stream, dry_run);
+        case 80: return one ? fused_launch<10, 1, false>(FP, ymap, stream, dry_run) : fused_launch<10, 2, false>(FP, ymap, stream, dry_run);
+        case 96: return one ? fused_launch<12, 1, false>(FP, ymap, stream, dry_run) : MAS_B200_ERR_UNSUPPORTED;
+        case 128: return one ? fused_launch<16, 1, false>(FP, ymap, stream, dry_run) : MAS_B200_ERR_UNSUPPORTED;
         default: return MAS_B200_ERR_UNSUPPORTED;
     }
+}
+
+// A text of 129..256 tokens runs as a PAIR of CTAs (one 128-row M-tile, one DP warp each; the halo row and the direction
+// words cross between them with st.async) when both CTAs of every utterance are resident at once: two SMs per utterance
+// halve what the latency-critical DP warp has to share its SM with (62 -> ~48 cycles per frame) and F = 96 / 128 fit the
+// tensor memory.  Beyond that (2B > SMs) the batch is throughput-bound and one CTA per utterance does more per SM.
+bool fused_pair_wanted(int B, int Tx) {
+    if (Tx <= 128 || option("fused_pair") == 0) return false;
+    DeviceInfo di;
+    if (device_info(&di) != MAS_B200_OK) return false;
+    return 2 * B <= di.sm_count || option("fused_pair") == 2;
 }
 
 }  // namespace
 
 // Shapes the fused kernel covers (everything else runs the serial form: log-prior kernel -> HBM -> MAS kernel):
-// F in {64, 80} with Tx <= 256 (two M-tiles / two DP warps) or F in {64, 80, 96, 128} with Tx <= 128 (one M-tile) -- the
-// A operand (mu_x hi/lo + the extra K step) and two D stages have to fit the 512 TMEM columns --, Ty % 4 == 0 and
-// 16-byte aligned operands (TMA), direction words + a >= 2-stage ring within 227 KB of shared memory (Ty up to ~2900
-// frames at Tx <= 128, ~1500 at Tx <= 256).
+// F in {64, 80} with Tx <= 256 (two M-tiles / two DP warps in one CTA, or a pair of CTAs) or F in {64, 80, 96, 128} with
+// Tx <= 128 (one M-tile) or Tx <= 256 as a pair of CTAs -- the A operand (mu_x hi/lo + the extra K step) and two D
+// stages have to fit the 512 TMEM columns --, Ty % 4 == 0 and 16-byte aligned operands (TMA), direction words + a
+// >= 2-stage ring within 227 KB of shared memory (Ty up to ~2900 frames at Tx <= 128, ~1500 at Tx <= 256).
 bool lp_mas_fused_supported(const float *mu_x, const float *y, int B, int F, int Tx, int Ty) {
     if (!(F == 64 || F == 80 || F == 96 || F == 128) || Tx > 256 || Ty % 4 != 0 || B <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(mu_x) & 15)) return false;
@@ -713,7 +844,8 @@ bool lp_mas_fused_supported(const float *mu_x, const float *y, int B, int F, int
     FP.mas.Tx = Tx; FP.mas.Ty = Ty;
     CUtensorMap dummy;
     std::memset(&dummy, 0, sizeof(dummy));
-    return fused_dispatch(F, FP, dummy, nullptr, true) == MAS_B200_OK;
+    if (fused_pair_wanted(B, Tx) && fused_dispatch(F, FP, dummy, nullptr, true, true) == MAS_B200_OK) return true;
+    return fused_dispatch(F, FP, dummy, nullptr, true, false) == MAS_B200_OK;
 }
 
 int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const int *t_y, int B, int F, int Tx, int Ty,
@@ -760,7 +892,12 @@ int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const
         const unsigned lo = (unsigned)option("fused_dump_ptr_lo"), hi = (unsigned)option("fused_dump_ptr_hi");
         FP.value_dump = reinterpret_cast<float *>(((unsigned long long)hi << 32) | lo);
     }
-    rc = fused_dispatch(F, FP, ymap, stream, false);
+    FP.exp = option("fused_exp");
+    {
+        FusedParams probe = FP;
+        const bool pair = fused_pair_wanted(B, Tx) && fused_dispatch(F, probe, ymap, stream, true, true) == MAS_B200_OK;
+        rc = fused_dispatch(F, FP, ymap, stream, false, pair);
+    }
     if (rc != MAS_B200_OK) return rc;
     if (want_path && !fuse) return launch_path_expand(P.start, P.dur, B, Tx, Ty, path, path_dtype, stream);
     return MAS_B200_OK;
