@@ -39,6 +39,8 @@ FLAGS = [
     "-Xptxas", "-v",
 ]
 # diagnostics build: in-loop wait / body cycle counters of the fused kernel (scripts/fused_phases.py)
+if os.environ.get("MASB200_XFLAGS"):
+    FLAGS += os.environ["MASB200_XFLAGS"].split()
 if os.environ.get("MASB200_HELP_PROF"):
     FLAGS.append("-DMASB200_HELP_PROF=1")
 if os.environ.get("MASB200_PROF"):

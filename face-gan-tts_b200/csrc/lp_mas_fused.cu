@@ -183,17 +183,58 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
 
     // PAIR: CTA rank r of the cluster owns text rows [128 r, 128 r + 128) of utterance blockIdx.x / 2; rank 0 is the home
     // CTA (direction words of all rows, backtrack, outputs)
-    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int rank = PAIR ? __shfl_sync(kFullMask, (int)cluster_ctarank(), 0) : 0;     // provably warp-uniform for ptxas
     const int row0 = PAIR ? 128 * rank : 0;
     const int b = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);     // provably warp-uniform for ptxas
     const int lane = tid & 31;
-    // Programmatic dependent launch: this grid may have been placed while the previous kernel of the stream was
-    // still running (its launch latency is hidden); nothing it wrote is touched before this wait returns.  The next
-    // kernel of the stream may be placed as soon as every CTA of this grid is past the trigger.
-    pdl_wait();
+    // Programmatic dependent launch: this grid may have been placed while the previous kernel of the stream was still
+    // running (its launch latency and the set-up below are hidden); the next kernel of the stream may be placed as soon
+    // as every CTA of this grid is past the trigger.
     pdl_launch_dependents();
+    // ---- set-up that touches no global memory, BEFORE the wait on the previous kernel of the stream (programmatic
+    // dependent launch: this grid is usually resident while the previous one is still running)
+    if (tid == 0) {
+        mbar_init(&bar_aready[0], 8 * 32); mbar_init(&bar_aready[1], 8 * 32);
+        mbar_init(&bar_xready[0], 4 * 32); mbar_init(&bar_xready[1], 4 * 32);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_raw[i], 1); mbar_init(&bar_split[i], 64); mbar_init(&bar_bfree[i], 1); mbar_init(&bar_dempty[i], 128);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_dfull[i], 1);
+        for (int i = 0; i < 2 * NS; ++i) mbar_init(&ring_empty[i], 1);
+        for (int i = 0; i < W; ++i) hprog[i] = 0;
+        hprog[W] = 0x7fffffff;                               // the flag a lane without anything to wait for polls
+        hprog[W + 1] = 0;
+        for (int i = 0; i < 4 * W; ++i) eprog[i] = 0;
+        mbar_fence_init();
+    }
+    if (P.path != nullptr) {
+        for (uint32_t i = tid; i < kZeroBytes / 16; i += kFusedThreads) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();                            // generic-proxy zeros -> visible to the bulk stores reading them
+    }
+    // nothing the previous kernel may have written is touched before this wait returns
+    pdl_wait();
+    long long *dbg = P.dbg ? P.dbg + ((size_t)rank * P.B + b) * 32 : nullptr;   // diagnostics ([2B][32] for a pair): phase stamps [0..15], wait cycles [16..31]
+    if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
+
+    // ---- mu_x block of this utterance: coalesced global loads issued first (they do not wait for the lengths: the
+    // padding of a row is valid memory, masked once t_x is here), consumed after the set-up below.
+    // One warp per mel-bin row f (f = warp, warp + 15, ...), lane + 32j the text position: no index arithmetic per load.
+    constexpr int kMuRows = (F + kFusedWarps - 1) / kFusedWarps;
+    constexpr int kMuCols = 4 * W;                            // 32-position column groups of a row
+    float mu_reg[kMuRows][kMuCols];
+    {
+        const float *mu_b = FP.mu + (size_t)b * F * P.Tx + row0 + lane;
+#pragma unroll
+        for (int k = 0; k < kMuRows; ++k) {
+            const int f = warp + kFusedWarps * k;
+            const float *rp = mu_b + (size_t)f * P.Tx;
+#pragma unroll
+            for (int j = 0; j < kMuCols; ++j)
+                mu_reg[k][j] = (f < F && row0 + lane + 32 * j < P.Tx) ? __ldg(rp + 32 * j) : 0.f;
+        }
+    }
     const int t_x = __shfl_sync(kFullMask, P.t_x[b], 0);
     const int t_y = __shfl_sync(kFullMask, P.t_y[b], 0);
     int *start_b = P.start + (size_t)b * P.Tx;
@@ -212,53 +253,29 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     }
     if (P.status && tid == 0 && rank == 0) P.status[b] = MAS_B200_ITEM_OK;
 
-    const int ntiles = (t_y + NT - 1) / NT;
     const int w_tot = (t_x + 32 * R - 1) / (32 * R);          // M-tiles of the utterance with valid rows
     // a pair's second CTA has nothing to do for a text of <= 128 tokens: it leaves before any cluster-wide step (exited
-    // threads count as arrived at the cluster barrier)
+    // threads count as arrived at the cluster barrier) and before it owns tensor memory.  (Both early exits are plain
+    // returns on provably warp-uniform conditions; an exit that has to hand tensor memory back first -- a block barrier in
+    // the exit path -- makes ptxas give up on the convergence of every warp behind it, and the MMA warp then issues through
+    // the divergent elect fallback: ~90 instead of ~20 cycles per instruction.  Hence the allocation comes after them.)
     if (PAIR && rank >= w_tot) return;
+    const int ntiles = (t_y + NT - 1) / NT;
     const int w_act = PAIR ? 1 : w_tot;                       // active DP warps == M-tiles of THIS CTA
+    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
     const bool peer = PAIR && w_tot == 2;                     // the other CTA of the pair is at work too
     unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XPT);  // [ntiles][XPT] transfer table
     uint64_t *bar_h = reinterpret_cast<uint64_t *>(smem_raw + FS::off_pair(NS, ntiles));     // PAIR [ntiles]: halo row of tile j has landed (rank 1)
     uint64_t *bar_b = bar_h + ntiles;                                                          // PAIR [ntiles]: rank 1's direction words of tile j have landed (rank 0)
     float *halo_full = reinterpret_cast<float *>(bar_b + ntiles);                              // PAIR [ntiles][32]: Q of text row 127 (rank 1)
-    long long *dbg = P.dbg ? P.dbg + ((size_t)rank * P.B + b) * 32 : nullptr;   // diagnostics ([2B][32] for a pair): phase stamps [0..15], wait cycles [16..31]
-    if (dbg && tid == 0) { dbg[0] = clock64(); long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[12] = t; }
     // the prologue's mu_x staging reaches into the raw y buffers: y tiles (and everything behind them) start late
     const bool late_start = (size_t)F * W * 128 * 4 > FS::off_raw(NS);
-
-    // ---- mu_x block of this utterance: coalesced global loads issued first, consumed after the set-up below.
-    // One warp per mel-bin row f (f = warp, warp + 15, ...), lane + 32j the text position: no index arithmetic per load.
-    constexpr int kMuRows = (F + kFusedWarps - 1) / kFusedWarps;
-    constexpr int kMuCols = 4 * W;                            // 32-position column groups of a row
-    float mu_reg[kMuRows][kMuCols];
-    {
-        const float *mu_b = FP.mu + (size_t)b * F * P.Tx + row0 + lane;
 #pragma unroll
-        for (int k = 0; k < kMuRows; ++k) {
-            const int f = warp + kFusedWarps * k;
-            const float *rp = mu_b + (size_t)f * P.Tx;
+    for (int k = 0; k < kMuRows; ++k)
 #pragma unroll
-            for (int j = 0; j < kMuCols; ++j)
-                mu_reg[k][j] = (f < F && row0 + lane + 32 * j < t_x) ? __ldg(rp + 32 * j) : 0.f;
-        }
-    }
+        for (int j = 0; j < kMuCols; ++j)
+            if (row0 + lane + 32 * j >= t_x) mu_reg[k][j] = 0.f;
 
-    if (tid == 0) {
-        mbar_init(&bar_aready[0], 8 * 32); mbar_init(&bar_aready[1], 8 * 32);
-        mbar_init(&bar_xready[0], 4 * 32); mbar_init(&bar_xready[1], 4 * 32);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_raw[i], 1); mbar_init(&bar_split[i], 64); mbar_init(&bar_bfree[i], 1); mbar_init(&bar_dempty[i], 128);
-        }
-        for (int i = 0; i < 4; ++i) mbar_init(&bar_dfull[i], 1);
-        for (int i = 0; i < 2 * NS; ++i) mbar_init(&ring_empty[i], 1);
-        for (int i = 0; i < W; ++i) hprog[i] = 0;
-        hprog[W] = 0x7fffffff;                               // the flag a lane without anything to wait for polls
-        hprog[W + 1] = 0;
-        for (int i = 0; i < 4 * W; ++i) eprog[i] = 0;
-        mbar_fence_init();
-    }
     if (PAIR && peer && tid >= 32 && tid < 32 + ntiles) {
         // one-shot hand-off barriers, armed for the bytes the peer will send: rank 1 receives the halo row of every tile
         // (32 floats), rank 0 rank 1's direction words (128 rows x 4 bytes)
@@ -266,11 +283,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         mbar_init(bar, 1);
         mbar_arrive_expect_tx(bar, rank == 0 ? 512u : 128u);
         mbar_fence_init();
-    }
-    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
-    if (P.path != nullptr) {
-        for (uint32_t i = tid; i < kZeroBytes / 16; i += kFusedThreads) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
-        fence_proxy_async_smem();                            // generic-proxy zeros -> visible to the bulk stores reading them
     }
     {
         // x = 32j + lane = 128*mt + 4*l + q with mt = j >> 2, l = 8*(j & 3) + (lane >> 2), q = lane & 3:

@@ -139,3 +139,30 @@ def test_pack_batch_host_layout_matches_numpy():
     want = np.concatenate([mu_x[b, f, :t_x[b]].numpy() for b in range(B) for f in range(F)] +
                           [y[b, f, :t_y[b]].numpy() for b in range(B) for f in range(F)])
     np.testing.assert_array_equal(body, want)
+
+
+def test_tensor_core_issue_is_warp_uniform_in_the_shipped_sass():
+    """The tcgen05.mma issue loops must be straight uniform-datapath code.  When ptxas cannot prove that the issuing warp
+    is converged (e.g. after an early exit behind a block barrier) it wraps every elect-predicated UTCHMMA in a
+    divergent fallback loop (ELECT ... BRA.U.ANY): ~90 instead of ~20 cycles per instruction, which starves the
+    alignment search behind it (measured: 52 -> 85 cycles per frame).  Catch that regression in the binary."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    fn, mma, fallback = None, {}, {}
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif "UTCHMMA" in line:
+            mma[fn] = mma.get(fn, 0) + 1
+        elif "BRA.U.ANY" in line:
+            fallback[fn] = fallback.get(fn, 0) + 1
+    kernels = [f for f in mma if "lp_mas_fused_kernel" in f or "log_prior_tc_kernel" in f]
+    assert len(kernels) >= 8, kernels
+    for f in kernels:
+        assert fallback.get(f, 0) <= 1, f"{f}: {fallback[f]} divergent fallback loops around {mma[f]} UTCHMMA"
