@@ -94,7 +94,7 @@ struct FusedSmem {
     __host__ __device__ static constexpr size_t off_pair(int ns, int ntiles) { return ((off_bits(ns) + (size_t)5 * ntiles * XPT + 15) / 16) * 16; }
     // PAIR: [ntiles] halo mbarriers + [ntiles] direction-word mbarriers + [ntiles][32] halo floats
     __host__ __device__ static constexpr size_t total(int ns, int ntiles) {
-        return off_pair(ns, ntiles) + (PAIR ? (size_t)ntiles * (8 + 8 + 128) : 0);
+        return off_pair(ns, ntiles) + (PAIR ? (size_t)ntiles * (8 + 8 + 128) + 128 : 0);     // + one slot the prefetch after the last tile reads
     }
 };
 
@@ -665,53 +665,68 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         // for tile j + 1 that is before the tail work of tile j
         float4 va[R], ha;
         dp_tile_prefetch<R, XP>(va, ha, ring + lane_cta * kTilePitch, hb_in, lane7);
+        // Everything the tile loop needs beside the recurrence advances by additions (the per-tile overhead is serial with
+        // the T_mel-long chain: ~310 cycles of index arithmetic, votes and branches per 32 frames before this).
+        const float *const ring_lane = ring + lane_cta * kTilePitch;
+        const float *lane_tile = ring_lane;                         // this lane's rows of the current ring stage
+        const float *hin = hb_in;                                   // halo input row of the current tile
+        uint32_t hout_addr = hout_base;                             // where the bottom row of the current tile goes
+        const uint32_t hin_wrap = halo_remote ? 0x7fffffffu : (uint32_t)HS;   // halo slots before the ring wraps (PAIR rank 1: never)
+        const uint32_t hout_wrap = PAIR ? 0x7fffffffu : (uint32_t)HS;
+        const int jd0 = xw0 / NT;                                   // tiles [jd0, jd0 + 4) hold the diagonal cells of the warp's rows
+        int dl0 = lane_utt;                                         // lane_utt - (first frame of the tile) / R
+        uint32_t bits_addr = smem_u32(bits_s + lane_utt * R);       // the lane's direction words of the current tile
+        uint32_t words_ra = words_raddr, words_rb = words_rbar;     // ... in the home CTA (PAIR rank 1), and their mbarrier
+        uint64_t *empty_bar = &ring_empty[w];
         for (int j = 0; j < ntiles; ++j) {
-            const int t0 = j * NT;
             const int sync_next = flag_acquire(sync_word);       // consumed after the body
             // PAIR rank 1: has the peer's halo row of tile j + 1 landed?  (a non-blocking probe, consumed after the body too)
-            const bool halo_next = (halo_remote && j + 1 < ntiles) ? mbar_test_warp(&bar_h[j + 1], 0) : true;
-            const int next_stage = (stage + 1 == NS) ? 0 : stage + 1;
-            const int next_hs = halo_remote ? j + 1 : ((hs + 1 == HS) ? 0 : hs + 1);
-
-            const float *lane_tile = ring + (size_t)stage * kTileFloats + lane_cta * kTilePitch;
-            const float *hin = hb_in + hs * hin_step;
-            const bool diag = (t0 < xw0 + 32 * R) && (t0 + NT - 1 >= xw0);
-            const int dl0 = lane_utt - t0 / R;
+            const bool halo_next = halo_remote ? mbar_test_warp(&bar_h[min(j + 1, ntiles - 1)], 0) : true;
+            const bool wrap = stage + 1 == NS;
+            const int next_stage = wrap ? 0 : stage + 1;
+            const bool hwrap_in = (uint32_t)(hs + 1) == hin_wrap, hwrap_out = (uint32_t)(hs + 1) == hout_wrap;
+            const float *lane_tile_next = wrap ? ring_lane : lane_tile + kTileFloats;
+            const float *hin_next = hwrap_in ? hb_in : hin + hin_step;
+            const bool diag = (unsigned)(j - jd0) < (unsigned)((32 * R) / NT);
             PROF_T(cb0);
-            // PAIR rank 0: the bottom row goes to slot j of the CTA's own full-length halo buffer, from where the
-            // forwarding warp sends it to the peer
-            const uint32_t hout_addr = hout_base + (uint32_t)(PAIR ? j : hs) * hout_step;
             if (diag) dp_tile_pre<R, XP, true, kFusedCell>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             else dp_tile_pre<R, XP, false, kFusedCell>(q, acc, up, va, ha, lane_tile, hin, lane7, lane0_mask, dl0, P.neg, hout_addr);
             PROF_ADD(w_body, cb0);
             // tile j + 1 ready?  (normally yes: the flags were read before the body) -> its first groups are on their
-            // way while this tile's direction words are stored and the tile is released
+            // way while this tile's direction words are stored and the tile is released.  After the last tile the same
+            // code re-reads a resident stage (no branch on "last tile": one vote covers everything).
             PROF_T(cw0);
-            if (j + 1 < ntiles) {
-                if (!__all_sync(kFullMask, sync_next >= j + 2 && halo_next)) {
-                    flag_wait_ge_warp(sync_word, j + 2);
-                    if (halo_remote) mbar_wait_warp(&bar_h[j + 1], 0);
-                }
-                dp_tile_prefetch<R, XP>(va, ha, ring + (size_t)next_stage * kTileFloats + lane_cta * kTilePitch,
-                                        hb_in + next_hs * hin_step, lane7);
+            const int need = min(j + 2, ntiles);
+            if (!__all_sync(kFullMask, sync_next >= need && halo_next)) {
+                flag_wait_ge_warp(sync_word, need);
+                if (halo_remote) mbar_wait_warp(&bar_h[min(j + 1, ntiles - 1)], 0);
             }
+            dp_tile_prefetch<R, XP>(va, ha, lane_tile_next, hin_next, lane7);
             PROF_ADD(w_full, cw0);
 
             // direction words of this tile, walk-ready (see mas_forward_kernel)
             uint32_t words[R];
             dp_finish_words<R, kFusedCell>(acc, words, x0, j, diag);
             if (PAIR && rank == 1)      // to the home CTA, counted on its mbarrier of this tile
-                st_async_v4(words_raddr + (uint32_t)j * (XPT * 4u), words_rbar + (uint32_t)j * 8u, words[0], words[1], words[2], words[3]);
+                st_async_v4(words_ra, words_rb, words[0], words[1], words[2], words[3]);
             else
-                store_words<R>(bits_s + (size_t)j * XPT + lane_utt * R, words);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bits_addr), "r"(words[0]), "r"(words[1]), "r"(words[2]), "r"(words[3]) : "memory");
 
             __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
             if (elect_one()) {
                 flag_release(flag_out, j + 1);
-                mbar_arrive(&ring_empty[stage * 2 + w]);
+                mbar_arrive(empty_bar);
             }
             stage = next_stage;
-            hs = next_hs;
+            hs = (hwrap_in || hwrap_out) ? 0 : hs + 1;
+            lane_tile = lane_tile_next;
+            hin = hin_next;
+            hout_addr = hwrap_out ? hout_base : hout_addr + hout_step;
+            dl0 -= NT / R;
+            bits_addr += XPT * 4u;
+            words_ra += XPT * 4u;
+            words_rb += 8u;
+            empty_bar = wrap ? &ring_empty[w] : empty_bar + 2;
         }
 #if MASB200_FUSED_PROF
         if (dbg && lane == 0) { dbg[22 + 2 * w] = w_full; dbg[26 + w] = w_body; }
