@@ -608,6 +608,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         int known = 0;
         for (int jt = 0; jt < ntiles; ++jt) {
             if (known < jt + 1) known = flag_wait_ge_warp(hprog, jt + 1);
+            if (dbg && jt == 0 && lane == 0) dbg[27] = clock64();
             if (lane < 8) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(halo_full + jt * NT + 4 * lane);
                 st_async_v4(raddr + (uint32_t)jt * (NT * 4u), rbar + (uint32_t)jt * 8u, v.x, v.y, v.z, v.w);
@@ -713,6 +714,7 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bits_addr), "r"(words[0]), "r"(words[1]), "r"(words[2]), "r"(words[3]) : "memory");
 
             __syncwarp();                                   // lane 31's halo stores, everyone's ring reads
+            if (dbg && j == 0 && lane == 0) dbg[26] = clock64();
             if (elect_one()) {
                 flag_release(flag_out, j + 1);
                 mbar_arrive(empty_bar);
@@ -746,21 +748,14 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     // ================================ backtrack + outputs (the ring is idle now) ================================
     int *tok = reinterpret_cast<int *>(ring);
     int *xin = tok + XPT;
-    int *hd = xin + ((ntiles + 3) & ~3);
-    const bool heads = P.frame_token != nullptr;
-    mas_backtrack_smem<XPT, kFusedThreads, 0, 0>(bits_s, nj_s, tok, xin, ntiles, ntiles, t_x, t_y, tid, dbg, heads ? hd : nullptr);
+    uint32_t *sflags = reinterpret_cast<uint32_t *>(xin + ((ntiles + 3) & ~3));
+    mas_backtrack_smem<XPT, kFusedThreads, 0, 0>(bits_s, nj_s, xin, sflags, ntiles, ntiles, t_x, t_y, tid, dbg);
     if (dbg && tid == 0) dbg[5] = clock64();
-    // dense path, part 2: the ones -- frame t belongs to token frame_token[t]; written by the thread that produces
-    // frame_token[t] (when the caller wants no frame_token the per-token form below does it)
+    // durations, frame -> token index, and (dense path, part 2) the ones: frame t belongs to token frame_token[t], written
+    // by the thread that produces frame_token[t]
     uint32_t *pb = P.path != nullptr ? reinterpret_cast<uint32_t *>(P.path) + (size_t)b * P.Tx * P.Ty : nullptr;
     const uint32_t one = P.path_dtype == MAS_B200_PATH_F32 ? 0x3f800000u : 1u;
-    mas_emit_outputs_scan<kFusedThreads>(P, b, tok, hd, t_x, t_y, tid, dbg, heads, heads ? pb : nullptr, one);
-    if (pb != nullptr && !heads) {
-        for (int x = warp; x < t_x; x += kFusedWarps) {
-            const int s0 = tok[x], e0 = (x + 1 < t_x) ? tok[x + 1] : t_y;
-            for (int t = s0 + lane; t < e0; t += 32) pb[(size_t)x * P.Ty + t] = one;
-        }
-    }
+    mas_emit_outputs_flags<kFusedThreads>(P, b, tok, xin, sflags, ntiles, t_x, t_y, tid, dbg, pb, one);
     if (dbg && tid == 0) {
         dbg[6] = clock64(); dbg[7] = ((long long)t_x << 32) | (unsigned)t_y;
         long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[13] = t;

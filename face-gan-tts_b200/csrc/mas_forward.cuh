@@ -551,14 +551,15 @@ __device__ __forceinline__ bool backtrack_walk(const uint32_t *wb, int wpitch, i
 // ---------------------------------------------------------------------------------------------------
 // Backtrack over walk-ready direction words in shared memory: the transfer tables of row groups [G0, G1) still owed
 // for tiles [jt_owed, ntiles) are shared by all warps, then one dependent shared-memory load per TILE gives the
-// token each tile is entered with, then one thread per tile emits the start frames tok[x] of its tokens.
-//   hd   optional [t_y] frame "head" marks for mas_emit_outputs_scan (hd[start frame of token x] = x, -1 elsewhere):
-//        cleared by the idle threads while thread 0 walks the tile chain, set by the per-tile walkers -- saves the
-//        output stage two passes and two block barriers.
+// token each tile is entered with (xin[]), then one LANE per tile walks the tokens that begin in its tile and leaves
+// their start frames as one 32-bit START MASK per tile:
+//   sflags[j]  bit 31-k set  <=>  a token begins at frame 32j + k      (token 0, which begins at frame 0, has no bit)
+// The tokens that begin in tile j are (xin[j-1], xin[j]], in frame order; everything the outputs need follows from the
+// masks by population counts (mas_emit_outputs_flags) -- no per-token find-first-set, no scattered stores and no scan.
 template <int XP, int NTHREADS, int G0, int G1>
-__device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsigned char *nj_s, int *tok, int *xin,
+__device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsigned char *nj_s, int *xin, uint32_t *sflags,
                                                    int jt_owed, int ntiles, int t_x, int t_y, int tid,
-                                                   long long *dbg = nullptr, int *hd = nullptr) {
+                                                   long long *dbg = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     if constexpr (G0 < G1) {
         constexpr int nwarps = NTHREADS / 32;
@@ -573,17 +574,16 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
             const int n = nj_s[(size_t)jt * XP + x];
             x -= n;
         }
-        tok[0] = 0;
         if (dbg) dbg[10] = clock64();
-    } else if (hd != nullptr) {
-        for (int t = tid - 1; t < t_y; t += NTHREADS - 1) hd[t] = -1;
     }
     __syncthreads();
     if (dbg && tid == 0) dbg[14] = clock64();
-    // one LANE per tile: start frames of the tokens (lo, xin[jt]] that begin in tile jt.  All lanes of a warp run the
-    // same loop (trip count = the largest token count among its tiles), eight tokens per round: their words are fetched
-    // with independent loads, then each token costs two dependent ALU ops (bt_transfer_groups' chain); a lane that has
-    // run out of tokens carries a zero m (sticky).
+    // All lanes of a warp run the same loop (trip count = the largest token count among its tiles), eight tokens per
+    // round: their words are fetched with independent loads, then each token costs two dependent ALU ops
+    // (bt_transfer_groups' chain) and one more to add its lowest set bit -- its start frame -- to the mask.  A lane that
+    // has run out of tokens reads the word of token 0 of tile 0 instead, which is zero by construction: ONE address for
+    // all such lanes (a broadcast), where "its own tile, token hi" would be one bank for every tile a long token spans
+    // (a 25-way bank conflict per load on the LRS2-shaped batch).
     for (int j0 = warp * 32; j0 < ntiles; j0 += NTHREADS) {
         const int jt = j0 + lane;
         const bool live = jt < ntiles;
@@ -592,52 +592,72 @@ __device__ __forceinline__ void mas_backtrack_smem(const uint32_t *bits_s, unsig
         const int lo = (live && jt > 0) ? xin[jt - 1] : 0;
         const int cnt = live ? hi - lo : 0;
         const int maxcnt = __reduce_max_sync(kFullMask, cnt);
+        if (dbg && tid == 0) dbg[31] = maxcnt;
         uint32_t m = 0u, m1 = ~(live ? bt_tile_mask(jt, ntiles, t_y) : 0u);      // ~(m ^ m1) == the tile's frame mask
-        const uint32_t tok_addr = smem_u32(tok + hi);
-        const bool heads_on = hd != nullptr;                                     // block-uniform
-        const uint32_t dump_addr = smem_u32(xin + (live ? jt : 0));
-        const int dump_val = xin[live ? jt : 0];
-        const uint32_t hd_addr = heads_on ? smem_u32(hd) : 0u;
+        uint32_t starts = 0u;
         for (int c = 0; c < maxcnt; c += 8) {
             uint32_t w[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = bj[max(hi - c - k, 0)];
+            for (int k = 0; k < 8; ++k) w[k] = (c + k < cnt) ? bj[hi - c - k] : bits_s[0];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 uint32_t mn;
-                asm("lop3.b32 %0, %1, %2, %3, 0x90;" : "=r"(mn) : "r"(c + k < cnt ? w[k] : 0u), "r"(m), "r"(m1));   // a & ~(b ^ c)
+                asm("lop3.b32 %0, %1, %2, %3, 0x90;" : "=r"(mn) : "r"(w[k]), "r"(m), "r"(m1));   // a & ~(b ^ c)
                 m = mn;
                 m1 = mn - 1u;
-                // branch-free (eight divergent branches per round cost more than the whole chain): a lane without a
-                // token left stores its own xin entry back to where it read it from
-                const int st = (jt << 5) + 32 - __ffs((int)mn);
-                const bool on = mn != 0u;
-                sts_s32(on ? tok_addr - 4u * (uint32_t)(c + k) : dump_addr, on ? st : dump_val);
-                if (heads_on) sts_s32(on ? hd_addr + 4u * (uint32_t)st : dump_addr, on ? hi - c - k : dump_val);
+                starts |= mn & ~m1;                                        // lowest set bit of mn: where the token begins
             }
         }
-        if (jt == 0 && hd != nullptr) hd[0] = 0;                           // token 0 starts at frame 0
+        if (live) sflags[jt] = starts;
     }
     if (dbg && tid == 0) dbg[15] = clock64();
     __syncthreads();
 }
 
-// [start, duration] per token from the start frames tok[] (shared memory), then frame -> token index.
-// Tokens are non-decreasing along the frames, so frame -> token is a running MAX over "head" marks
-// (hd[start frame of x] = x): one thread per 8 frames, warp shuffle scan, 16-byte stores -- instead of one thread
-// per token walking its frames (a 200-frame silence token was the whole tail).
-//   hd   scratch in shared memory: [(Ty + 3) & ~3] heads + [32] warp totals
-//   heads_ready   hd[] was already filled by mas_backtrack_smem
-//   path_ones     optional: the (already zero-filled) dense path [Tx,Ty] of this utterance as 32-bit words; every frame's
-//                 thread stores `one` at (its token, its frame) -- 8 independent stores per thread, no per-token loop
+// Outputs from the per-tile start masks.  The tokens are consecutive along the frames, so with S = sflags[j], hi = xin[j]
+//     frame_token[32j + k] = hi - popc(S & ((1 << (31-k)) - 1))        (the starts at LATER frames of the tile)
+// one independent population count per frame: no scan, no head marks.  A frame whose own bit is set is the first frame
+// of its token (tok[]); [start, duration] per token follow from tok[].  One thread per 4 frames (16-byte stores).
+//   tok        scratch in shared memory [XP]: start frame per token
+//   path_ones  optional: the (already zero-filled) dense path [Tx,Ty] of this utterance as 32-bit words; every frame's
+//              thread stores `one` at (its token, its frame)
 template <int NTHREADS>
-__device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b, const int *tok, int *hd, int t_x, int t_y,
-                                                      int tid, long long *dbg = nullptr, bool heads_ready = false,
-                                                      uint32_t *path_ones = nullptr, uint32_t one = 0u) {
-    const int warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ void mas_emit_outputs_flags(const MasParams &P, int b, int *tok, const int *xin, const uint32_t *sflags,
+                                                       int ntiles, int t_x, int t_y, int tid, long long *dbg = nullptr,
+                                                       uint32_t *path_ones = nullptr, uint32_t one = 0u) {
     int *start_b = P.start + (size_t)b * P.Tx;
     int *dur_b = P.dur + (size_t)b * P.Tx;
     int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
+    const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
+    if (tid == 0) tok[0] = 0;                                              // token 0 begins at frame 0 (it has no bit)
+    for (int t0 = 4 * tid; t0 < P.Ty; t0 += 4 * NTHREADS) {
+        const int j = t0 >> 5;
+        const bool in_tiles = j < ntiles;
+        const uint32_t S = in_tiles ? sflags[j] : 0u;
+        const int hi = in_tiles ? xin[j] : 0;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t = t0 + k;
+            const uint32_t bit = 0x80000000u >> (t & 31);
+            const int x = hi - __popc(S & (bit - 1u));
+            const bool valid = t < t_y;
+            if (valid && (S & bit) != 0u) tok[x] = t;
+            if (path_ones != nullptr && valid) path_ones[(size_t)x * P.Ty + t] = one;
+            v[k] = valid ? x : -1;
+        }
+        if (ft != nullptr) {
+            if (vec) {
+                *reinterpret_cast<int4 *>(ft + t0) = make_int4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (t0 + k < P.Ty) ft[t0 + k] = v[k];
+            }
+        }
+    }
+    if (dbg && tid == 0) dbg[11] = clock64();
+    __syncthreads();
     for (int x = tid; x < P.Tx; x += NTHREADS) {
         int s = 0, d = 0;
         if (x < t_x) {
@@ -647,73 +667,12 @@ __device__ __forceinline__ void mas_emit_outputs_scan(const MasParams &P, int b,
         start_b[x] = s;
         dur_b[x] = d;
     }
-    if (ft) {
-        int *wt = hd + ((P.Ty + 3) & ~3);
-        if (!heads_ready) {
-            for (int t = tid; t < t_y; t += NTHREADS) hd[t] = -1;
-            __syncthreads();
-            for (int x = tid; x < t_x; x += NTHREADS) {
-                const int s = tok[x];
-                const int e = (x + 1 < t_x) ? tok[x + 1] : t_y;
-                if (e > s) hd[s] = x;
-            }
-            __syncthreads();
-        }
-        if (dbg && tid == 0) dbg[11] = clock64();
-        const bool vec = ((P.Ty & 3) == 0) && ((reinterpret_cast<uintptr_t>(ft) & 15) == 0);
-        constexpr int nw = NTHREADS >> 5;
-        int carry = -1;
-        for (int base_t = 0; base_t < P.Ty; base_t += NTHREADS * 8) {
-            const int t0 = base_t + tid * 8;
-            int v[8], run = -1;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int t = t0 + k;
-                const int h = (t < t_y) ? hd[t] : -1;
-                run = max(run, h);
-                v[k] = run;
-            }
-            int inc = run;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                const int n = __shfl_up_sync(kFullMask, inc, dlt);
-                if (lane >= dlt) inc = max(inc, n);
-            }
-            int exc = __shfl_up_sync(kFullMask, inc, 1);
-            if (lane == 0) exc = -1;
-            if (lane == 31) wt[warp] = inc;
-            __syncthreads();
-            int basev = max(carry, exc), nc = carry;
-            for (int w2 = 0; w2 < nw; ++w2) {
-                const int wv = wt[w2];
-                if (w2 < warp) basev = max(basev, wv);
-                nc = max(nc, wv);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = (t0 + k < t_y) ? max(basev, v[k]) : -1;
-            if (path_ones != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (v[k] >= 0) path_ones[(size_t)v[k] * P.Ty + t0 + k] = one;
-            }
-            if (vec && t0 + 7 < P.Ty) {
-                *reinterpret_cast<int4 *>(ft + t0) = make_int4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<int4 *>(ft + t0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (t0 + k < P.Ty) ft[t0 + k] = v[k];
-            }
-            __syncthreads();                 // wt is reused by the next round
-            carry = nc;
-        }
-    }
     __syncthreads();                         // start_b / dur_b of every thread are in place for the path writer
 }
 
-// ints of shared-memory scratch the two functions above need: tok [XP] + xin [tiles] + heads [Ty] + warp totals [32]
-__host__ __device__ constexpr size_t mas_tail_scratch_ints(int XP, int ntiles, int Ty) {
-    return (size_t)XP + (size_t)((ntiles + 3) & ~3) + (size_t)((Ty + 3) & ~3) + 32;
+// ints of shared-memory scratch the two functions above need: tok [XP] + xin [tiles] + start masks [tiles]
+__host__ __device__ constexpr size_t mas_tail_scratch_ints(int XP, int ntiles, int /*Ty*/) {
+    return (size_t)XP + 2 * (size_t)((ntiles + 3) & ~3);
 }
 
 // MULTIPASS: text longer than XP rows (carry line between row passes); its runtime role flags cost
@@ -971,14 +930,11 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     // (4*(Tx + tiles) bytes always fit below two value tiles there), else global (start table, carry line)
     int *tok = SMEM_BITS ? reinterpret_cast<int *>(ring) : start_b;
     int *xin = SMEM_BITS ? tok + XP : reinterpret_cast<int *>(gline_b);
-    // scratch of the output scan, in the (idle) ring behind tok / xin: heads [Ty], warp totals [32]
-    int *hd = xin + ((ntiles + 3) & ~3);
-    const bool scan_ft = SMEM_BITS && (mas_tail_scratch_ints(XP, ntiles, P.Ty) * sizeof(int) <= S::ring_bytes(NS));
-    const bool heads = scan_ft && P.frame_token != nullptr;
+    // per-tile start masks of the tokens, behind tok / xin
+    uint32_t *sflags = reinterpret_cast<uint32_t *>(xin + ((ntiles + 3) & ~3));
     if constexpr (SMEM_BITS) {
         // transfer tables (upper row groups) the producer warp did not get to, tile entry tokens, start frames
-        mas_backtrack_smem<XP, nthreads, kGH, kG>(bits_s, nj_s, tok, xin, bt_state[3], ntiles, t_x, t_y, tid, nullptr,
-                                                  heads ? hd : nullptr);
+        mas_backtrack_smem<XP, nthreads, kGH, kG>(bits_s, nj_s, xin, sflags, bt_state[3], ntiles, t_x, t_y, tid, nullptr);
     } else {
         const int rows_pitch = P.gbits_rows_pitch;
         uint32_t *stage_bits = reinterpret_cast<uint32_t *>(ring);           // the ring is idle now
@@ -1028,8 +984,8 @@ mas_forward_kernel(const MasParams P, const __grid_constant__ CUtensorMap tmap) 
     // ================================= outputs =================================
     // [start, duration] per token from the start frames; frame -> token index; dense path
     int *ft = P.frame_token ? P.frame_token + (size_t)b * P.Ty : nullptr;
-    if (scan_ft) {
-        mas_emit_outputs_scan<nthreads>(P, b, tok, hd, t_x, t_y, tid, nullptr, heads);
+    if (SMEM_BITS) {
+        mas_emit_outputs_flags<nthreads>(P, b, tok, xin, sflags, ntiles, t_x, t_y, tid);
     } else {
         for (int x = tid; x < P.Tx; x += nthreads) {
             int s = 0, d = 0;

@@ -30,12 +30,12 @@ def run(B, F, Tx, Ty, full=False):
         s = d[b].tolist()
         txb, tyb = s[7] >> 32, s[7] & 0xFFFFFFFF
         print(f"{b:3d} {txb:4d} {tyb:5d} | ({s[8]-s[0]:5d} {s[9]-s[8]:5d} {s[1]-s[9]:5d}) {s[1]-s[0]:8d} {s[2]-s[0]:10d} {s[4]-s[2]:10d} {(s[4]-s[2])/max(tyb,1):10.1f} | "
-              f"{s[3]-s[4]:5d} {s[5]-s[3]:9d} ({s[10]-s[3]:5d} {s[14]-s[10]:4d} {s[15]-s[14]:4d} {s[5]-s[15]:4d}) {s[6]-s[5]:7d} ({s[11]-s[5]:5d}) | {s[6]-s[0]:9d} {(s[13]-s[12])/1e3:8.1f}  (start +{(s[12]-t0)/1e3:.1f} us)  dp0/helpA/helpB done at {s[30]-s[0]} {s[28]-s[0]} {s[29]-s[0]}, DP done {s[4]-s[0]}")
+              f"{s[3]-s[4]:5d} {s[5]-s[3]:9d} ({s[10]-s[3]:5d} {s[14]-s[10]:4d} {s[15]-s[14]:4d} {s[5]-s[15]:4d}) {s[6]-s[5]:7d} ({s[11]-s[5]:5d}) | {s[6]-s[0]:9d} {(s[13]-s[12])/1e3:8.1f}  (start +{(s[12]-t0)/1e3:.1f} us)  dp0/helpA/helpB done at {s[30]-s[0]} {s[28]-s[0]} {s[29]-s[0]}, DP done {s[4]-s[0]}, walk rounds of 8 for {s[31]} tokens")
     if int(d[B, 0]) != 0:      # pair kernel: the second CTA of each utterance
         for b in range(min(B, 4)):
             s = d[B + b].tolist(); r0 = d[b].tolist()
             if s[0]:
-                print(f"    rank 1 of {b}: start {s[0]-r0[0]:+d} vs rank 0 (different SM clocks!), first tile at {s[2]-s[0]}, DP {s[4]-s[2]} cycles, joined at {s[3]-s[0]}")
+                print(f"    rank 1 of {b}: start {s[0]-r0[0]:+d} vs rank 0 (different SM clocks!), first tile at {s[2]-s[0]}, DP {s[4]-s[2]} cycles, joined at {s[3]-s[0]}; rank 0: tile 0 released at {r0[26]-r0[0]}, forwarded at {r0[27]-r0[0]}")
     print("  wait cycles per frame:  mma<-split mma<-dempty | split<-bfree split<-raw | epi<-dfull epi<-ring_empty | dp0<-ring_full dp0<-flag dp1<-ring_full dp1<-flag | dp0 body dp1 body")
     for b in list(range(min(B, 8))):
         s = d[b].tolist(); tyb = max(s[7] & 0xFFFFFFFF, 1)
