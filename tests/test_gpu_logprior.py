@@ -91,9 +91,12 @@ def _agreement(ft, ref_ft):
     return float((ft[valid] == ref_ft[valid]).mean())
 
 
-# (B, F, Tx, Ty): the LRS2 bench shape, the reference default n_feats = 128 with short texts (one M-tile), F = 64 / 96
+# (B, F, Tx, Ty): the LRS2 bench shape (a pair of CTAs per utterance at these batch sizes), the reference default
+# n_feats = 128 with short texts (one M-tile) and at the LRS2 shape (pair form only), F = 64 / 96, a second CTA with a
+# single text row (Tx = 129), a batch too large for the pair form (one CTA with two M-tiles per utterance)
 FUSED_SHAPES = [(8, 80, 190, 1000), (32, 80, 190, 1000), (32, 128, 128, 1000), (5, 64, 256, 512), (6, 96, 100, 600),
-                (3, 80, 31, 64), (4, 80, 129, 1400)]
+                (3, 80, 31, 64), (4, 80, 129, 1400), (32, 128, 190, 1000), (5, 96, 200, 600), (3, 80, 256, 1400),
+                (80, 80, 190, 1000)]
 
 
 @pytest.mark.parametrize("B,F,Tx,Ty", FUSED_SHAPES)
@@ -257,13 +260,14 @@ def test_tcgen05_kernel_is_the_one_running_and_matches_ffma():
         fgt.log_prior(mu_x.to(DEV), y.to(DEV), impl="tcgen05")          # n_feats not instantiated: raises, no fallback
 
 
-@pytest.mark.parametrize("B,F,Tx", [(3, 80, 190), (32, 80, 190), (80, 80, 190), (300, 80, 190), (32, 128, 128), (3, 128, 190), (50, 128, 190)])
+@pytest.mark.parametrize("B,F,Tx", [(3, 80, 190), (32, 80, 190), (80, 80, 190), (300, 80, 190), (32, 128, 128), (3, 128, 190), (50, 128, 190), (90, 128, 190)])
 def test_fused_kernel_vs_serial_form(B, F, Tx):
     """mas_b200_log_prior_maximum_path: the fused kernel (default where the shape is covered) and the serial form
     (fused_impl=1: log-prior kernel -> HBM -> MAS kernel -> path expansion) are two schedules of the same computation.
     Their log-priors differ in the last bits (the fused kernel folds the y^2 / mu^2 terms into the contraction), so the
     paths may differ at near-ties: status and structure must be identical, frames must agree > 99.9 %.  Shapes the fused
-    kernel does not cover (F = 128 with two M-tiles) take the serial form in both modes: identical outputs."""
+    kernel does not cover (F = 128 with two M-tiles in a batch too large for the pair form) take the serial form in both
+    modes: identical outputs."""
     from face_gan_tts_b200 import _lib
 
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=1000, seed=11)
@@ -287,8 +291,33 @@ def test_fused_kernel_vs_serial_form(B, F, Tx):
     assert torch.equal(valid, a.frame_token >= 0)
     agree = float((a.frame_token[valid] == b.frame_token[valid]).float().mean())
     assert agree > 0.999
-    if F == 128 and Tx > 128:
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    if F == 128 and Tx > 128 and 2 * B > sms:        # no pair form, no one-CTA form: the serial form in both modes
         assert torch.equal(a.path, b.path) and torch.equal(a.frame_token, b.frame_token)
+
+
+@pytest.mark.parametrize("B,F,Tx,Ty", [(32, 80, 190, 1000), (7, 64, 256, 800), (100, 80, 190, 600)])
+def test_pair_form_equals_one_cta_form(B, F, Tx, Ty):
+    """A text of 129..256 tokens as a 2-CTA cluster (one M-tile and one DP warp per CTA, halo row and direction words
+    crossing with st.async) and as one CTA with two M-tiles: the same values, the same search -- identical outputs, bit for
+    bit.  B = 100 forces the pair form on a batch that does not fit the SMs at once (clusters run in waves)."""
+    from face_gan_tts_b200 import _lib
+
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=5, tx_lo=20, ty_lo=max(Tx, Ty // 4))
+    mu_d, y_d = mu_x.to(DEV), y.to(DEV)
+    outs = []
+    for mode in (0, 2):
+        prev = _lib.set_option("fused_pair", mode)
+        try:
+            r, dump = _fused_with_value_dump(mu_d, y_d, t_x, t_y, path_dtype=torch.float32)
+            outs.append((r, dump))
+        finally:
+            _lib.set_option("fused_pair", prev)
+    (a, da), (b, db) = outs
+    assert not torch.isnan(da[0, 0, 0]) and not torch.isnan(db[0, 0, 0])
+    assert torch.equal(torch.nan_to_num(da), torch.nan_to_num(db)), "the two forms computed different log-prior values"
+    assert int(a.status.abs().sum()) == 0 and torch.equal(a.status, b.status)
+    assert torch.equal(a.path, b.path) and torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token)
 
 
 def test_long_text_takes_the_serial_form():
