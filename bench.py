@@ -434,6 +434,18 @@ def run_cuda(args):
             _lib.LP_AUTO, sp if on is None else on.cuda_stream)
         _lib.check(rc, "mas_b200_log_prior_maximum_path")
 
+    # multi-GPU duration gather: one-sided (the fused kernel stores its durations into every rank's symmetric-memory
+    # buffer over NVLink: no collective kernel, no torch.distributed call per step) when symmetric memory is available,
+    # else an asynchronous NCCL all-gather per step on a side stream
+    put = None
+    if dist and not args.nccl_gather and not os.environ.get("MAS_B200_BENCH_NO_GATHER"):
+        try:
+            put = sharding.OneSidedDurationGather(B, TX, dev)
+            if args.put_in_kernel:
+                put.enable()         # the fused kernel stores its durations itself (+ the NVLink round trip at its end)
+        except Exception as ex:
+            sys.stderr.write(f"bench.py: one-sided duration gather unavailable ({ex!r}); NCCL all-gather per step\n")
+            put = None
     graphs = [None]      # multi-GPU: CUDA graphs of the fused call, one per buffer set (see below)
     gathered = [torch.empty((world * B, TX), dtype=torch.int32, device=dev) for _ in range(2)] if dist else None
     comm_stream = torch.cuda.Stream(dev) if dist else None
@@ -445,7 +457,13 @@ def run_cuda(args):
             graphs[0][i % NSETS].replay()
         else:
             fused(d, wss[i % NSETS])
-        if dist:
+        if dist and put is not None and not args.put_in_kernel:
+            # one-sided gather off the step's critical path: a small copy kernel on a side stream, ordered behind the step
+            ev = step_done[i % 4]
+            ev.record(stream)
+            comm_stream.wait_event(ev)
+            put.put(d["dur"], comm_stream)
+        if dist and put is None and not os.environ.get("MAS_B200_BENCH_NO_GATHER"):
             # loss-bookkeeping collective: durations of every rank, asynchronous on a side stream
             ev = step_done[i % 4]
             ev.record(stream)
@@ -465,7 +483,7 @@ def run_cuda(args):
     # step does not, but costs almost no host time.  Replay graphs only when the host cannot enqueue a step (fused call +
     # NCCL all-gather) in less time than the GPU needs for it.
     use_graph = False
-    if dist and not args.no_graph:
+    if dist and not args.no_graph and put is None:
         e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_a.record(stream)
         t0 = time.perf_counter()
@@ -479,8 +497,8 @@ def run_cuda(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)          # every rank takes the same decision
         use_graph = bool(flag.item() > 0) or args.graph
     if dist and use_graph:
-        # With the NCCL enqueue beside it a step costs more host time than GPU time, so the fused call (ONE kernel node)
-        # is replayed from a CUDA graph per buffer set; the all-gather stays an eager NCCL call on its own stream.
+        # the fused call (ONE kernel node) replayed from a CUDA graph per buffer set; the all-gather stays an eager NCCL
+        # call on its own stream.
         try:
             cap = torch.cuda.Stream(dev)
             cap.wait_stream(stream)
@@ -509,12 +527,20 @@ def run_cuda(args):
     for i in range(K):
         step(W + i)
     host_enqueue_us = (time.perf_counter() - host_t0) / K * 1e6      # host time to enqueue one step (no sync inside)
-    if dist:
-        stream.wait_stream(comm_stream)      # all gathers complete inside the timed region
+    if dist and (put is None or not args.put_in_kernel):
+        stream.wait_stream(comm_stream)      # all gathers / puts complete inside the timed region
     e1.record(stream)
-    barrier()
+    barrier()                                # one-sided gather: every rank's puts are complete and visible after this
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    if put is not None:
+        # every rank's block of the gather buffer holds real durations (each utterance's sum to its t_y: 1..TY), and this
+        # rank's block is what its own last step produced
+        g = put.gathered.view(world, B, TX)
+        sums = g.sum(-1)
+        assert bool(((sums >= 1) & (sums <= TY)).all()), "one-sided gather: a rank's durations did not arrive"
+        assert torch.equal(g[rank], sets[(W + K - 1) % NSETS]["dur"]), "one-sided gather: own block differs"
+        put.disable()
     if dist:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -757,7 +783,7 @@ def run_cuda(args):
                        "n_feats": F, "T_text": TX, "T_mel": TY, "valid_cells_per_step": valid_cells,
                        "outputs": "dense fp32 path [B,Tx,Ty] + durations [B,Tx] + frame->token index [B,Ty]",
                        "cache": f"inputs rotate over {NSETS} buffer sets (~{NSETS * 37} MB) larger than the 126 MB L2",
-                       "parallelism": f"utterance shards x{world}, async NCCL all-gather of durations" if world > 1
+                       "parallelism": (f"utterance shards x{world}, " + (("one-sided duration gather over NVLink into every rank's symmetric-memory buffer: " + ("by the fused kernel itself" if args.put_in_kernel else "a copy kernel on a side stream, no collective")) if put is not None else "async NCCL all-gather of durations")) if world > 1
                        else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "path_agreement": agreement, "sweep": sweep,
             "strong_scaling_configs4": strong, "compute_loss_block": block,
@@ -784,6 +810,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="multi-GPU: always eager launches")
     ap.add_argument("--graph", action="store_true", help="multi-GPU: always replay the fused call from a CUDA graph")
+    ap.add_argument("--put-in-kernel", action="store_true", help="multi-GPU: the fused kernel stores its durations into the peers' buffers itself")
+    ap.add_argument("--nccl-gather", action="store_true", help="multi-GPU: NCCL all-gather of the durations per step instead of the one-sided gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,6 +38,10 @@ Opt g_opts[] = {
     {"fused_dump_ptr_hi", {0}},
     {"pdl", {1}},                    // 1: fused kernel / path expansion launch with programmatic stream serialization
     {"fused_exp", {0}},              // diagnostics only (MASB200_PROF builds): bit 0 the DP warps ignore the readiness flags, bit 1 park the helper warps, bit 2 park the producers (results invalid)
+    {"peer_dur_ptrs_lo", {0}},       // one-sided duration gather of the fused call (multi-GPU): DEVICE array of peer_world pointers, rank r's
+    {"peer_dur_ptrs_hi", {0}},       //   [peer_world * B, Tx] int32 gather buffer as mapped on this device (mas_b200_set_pointer_option "peer_dur_ptrs")
+    {"peer_world", {0}},             //   number of ranks (0 = off)
+    {"peer_rank", {0}},              //   this rank: its durations go to rows [peer_rank * B, +B) of every buffer
     {"fused_pair", {1}},             // 1: texts of 129..256 tokens run as a 2-CTA cluster per utterance when 2B <= SMs, 0: never, 2: always
     {"fused_impl", {0}},             // 0 auto (fused kernel when the shape is covered), 1 force the serial form
 };
@@ -211,6 +215,11 @@ int mas_b200_generate_path_f32(const float *durations_dev, const int *t_x_dev, c
                                void *path_dev, int path_dtype, int *frame_token_dev, void *stream) {
     return launch_generate_path(durations_dev, 1, t_x_dev, t_y_dev, B, Tx, Ty, path_dev, path_dtype, frame_token_dev,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_put_durations(const int *durations_dev, int B, int Tx, void *const *peer_ptrs_dev, int world, int rank,
+                           void *stream) {
+    return launch_put_rows(durations_dev, B, Tx, peer_ptrs_dev, world, rank, static_cast<cudaStream_t>(stream));
 }
 
 int mas_b200_sequence_mask(const int *lengths_dev, int B, int T, float *mask_dev, void *stream) {

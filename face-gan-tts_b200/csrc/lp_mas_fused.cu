@@ -243,7 +243,11 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     // ---- per-item validation (the reference is undefined here: core.pyx:34) ----
     if (t_x < 1 || t_y < 1 || t_x > P.Tx || t_y > P.Ty || t_x > t_y) {
         if (rank != 0) return;
-        for (int x = tid; x < P.Tx; x += kFusedThreads) { start_b[x] = 0; dur_b[x] = 0; }
+        for (int x = tid; x < P.Tx; x += kFusedThreads) {
+            start_b[x] = 0; dur_b[x] = 0;
+            if (P.peer_dur != nullptr)
+                for (int r = 0; r < P.peer_world; ++r) P.peer_dur[r][((size_t)P.peer_rank * P.B + b) * P.Tx + x] = 0;
+        }
         if (P.frame_token)
             for (int y = tid; y < P.Ty; y += kFusedThreads) P.frame_token[(size_t)b * P.Ty + y] = -1;
         if (P.status && tid == 0) P.status[b] = MAS_B200_ITEM_BAD_LENGTH;
@@ -915,6 +919,13 @@ int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const
         FP.value_dump = reinterpret_cast<float *>(((unsigned long long)hi << 32) | lo);
     }
     FP.exp = option("fused_exp");
+    if (option("peer_world") > 0) {      // one-sided duration gather (see MasParams::peer_dur)
+        const unsigned lo = (unsigned)option("peer_dur_ptrs_lo"), hi = (unsigned)option("peer_dur_ptrs_hi");
+        P.peer_dur = reinterpret_cast<int *const *>(((unsigned long long)hi << 32) | lo);
+        P.peer_world = option("peer_world");
+        P.peer_rank = option("peer_rank");
+        if (P.peer_dur == nullptr || P.peer_rank < 0 || P.peer_rank >= P.peer_world) return MAS_B200_ERR_ARG;
+    }
     {
         FusedParams probe = FP;
         const bool pair = fused_pair_wanted(B, Tx) && fused_dispatch(F, probe, ymap, stream, true, true) == MAS_B200_OK;

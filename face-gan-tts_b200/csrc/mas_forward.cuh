@@ -77,6 +77,11 @@ struct MasParams {
     void *path;              // optional in-kernel dense path write
     int path_dtype;          // MAS_B200_PATH_*
     long long *dbg;          // diagnostics: [B][8] clock64 phase stamps (nullptr normally)
+    // one-sided duration gather (multi-GPU, optional): peer_dur[r] = rank r's [peer_world * B, Tx] int32 buffer as mapped into
+    // THIS device's address space (peer-to-peer over NVLink); this rank's durations also go to rows [peer_rank * B, +B) of
+    // every one of them, straight from the output stage -- no collective kernel, nothing on the host path of a step
+    int *const *peer_dur;
+    int peer_world, peer_rank;
 };
 
 // One cell of the recurrence, two formulations (template parameter CK):
@@ -666,6 +671,10 @@ __device__ __forceinline__ void mas_emit_outputs_flags(const MasParams &P, int b
         }
         start_b[x] = s;
         dur_b[x] = d;
+        if (P.peer_dur != nullptr) {
+            const size_t row = ((size_t)P.peer_rank * P.B + b) * P.Tx + x;
+            for (int r = 0; r < P.peer_world; ++r) P.peer_dur[r][row] = d;
+        }
     }
     __syncthreads();                         // start_b / dur_b of every thread are in place for the path writer
 }

@@ -63,6 +63,7 @@ const int *mas_start_table(void *workspace, int B, int Tx, int Ty);
 const int *mas_dur_table(void *workspace, int B, int Tx, int Ty, const int *user_durations);
 int launch_mas(const MasLaunch &L);
 
+int launch_put_rows(const int *src, int rows, int cols, void *const *peer_ptrs_dev, int world, int rank, cudaStream_t stream);
 int launch_path_expand(const int *start, const int *dur, int B, int Tx, int Ty, void *path, int path_dtype,
                        cudaStream_t stream);
 int launch_debug_spin(int ctas, long long cycles, cudaStream_t stream);   // tests only (path_ops.cu)

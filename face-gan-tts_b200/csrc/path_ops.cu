@@ -2,6 +2,7 @@
 //   path_expand       [start,dur] table -> dense [B,Tx,Ty] path (pure streaming write, all SMs)
 //   lengths_from_mask dense prefix mask -> t_x, t_y   (reference monotonic_align/__init__.py:20-21)
 //   generate_path     integer durations -> dense path (reference model/utils.py:27-40)
+#include <algorithm>
 #include <atomic>
 
 #include "mas_forward.cuh"
@@ -174,6 +175,38 @@ int launch_generate_path(const void *durations, int dur_is_float, const int *t_x
         if (pi) generate_path_kernel<int, int><<<B, 256, smem, stream>>>(d, t_x, t_y, Tx, Ty, pi, frame_token);
         else generate_path_kernel<float, int><<<B, 256, smem, stream>>>(d, t_x, t_y, Tx, Ty, pf, frame_token);
     }
+    MASB200_CUDA_TRY(cudaGetLastError());
+    return MAS_B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// One-sided gather of a [rows, cols] int32 block (the durations of this rank) into every rank's
+// [world * rows, cols] buffer: peer[r] is rank r's buffer as mapped into THIS device's address space
+// (symmetric memory, peer-to-peer stores over NVLink).  Multi-GPU loss bookkeeping without a collective:
+// utterances are sharded across ranks (reference config.py:144-145 shards the batch the same way) and
+// nothing else is ever exchanged.  16-byte stores when the block allows.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) put_rows_kernel(const int *__restrict__ src, int *const *__restrict__ peer, long long n,
+                                                       long long dst_off, int world) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const bool vec = (n & 3) == 0 && (dst_off & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    for (int r = 0; r < world; ++r) {
+        int *dst = peer[r] + dst_off;
+        if (vec && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            for (long long i = i0; i < (n >> 2); i += stride)
+                reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(src)[i];
+        } else {
+            for (long long i = i0; i < n; i += stride) dst[i] = src[i];
+        }
+    }
+}
+
+int launch_put_rows(const int *src, int rows, int cols, void *const *peer_ptrs_dev, int world, int rank, cudaStream_t stream) {
+    if (!src || !peer_ptrs_dev || rows <= 0 || cols <= 0 || world <= 0 || rank < 0 || rank >= world) return MAS_B200_ERR_ARG;
+    const long long n = (long long)rows * cols;
+    const int blocks = (int)std::min<long long>(32, (n / 4 + 255) / 256 + 1);
+    put_rows_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<int *const *>(peer_ptrs_dev), n, (long long)rank * n, world);
     MASB200_CUDA_TRY(cudaGetLastError());
     return MAS_B200_OK;
 }

@@ -43,6 +43,7 @@ SIGNATURES = {
     "mas_b200_log_prior_maximum_path": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                 c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_size_t, c_int, c_void_p]),
+    "mas_b200_put_durations": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "mas_b200_generate_path": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mas_b200_generate_path_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                            c_void_p]),

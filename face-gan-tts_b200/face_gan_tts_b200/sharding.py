@@ -72,3 +72,63 @@ def all_gather_durations_into(out: torch.Tensor, dur_local: torch.Tensor, group:
     """Equal-shard fast path with a caller-owned output [world * B_local, Tx]: one collective, no size exchange
     (what bench.py issues every step on its side stream)."""
     return dist.all_gather_into_tensor(out, dur_local.contiguous(), group=group)
+
+
+class OneSidedDurationGather:
+    """The duration all-gather without a collective: every rank's fused kernel stores its [B_local, Tx] durations
+    straight into rows [rank * B_local, +B_local) of EVERY rank's gather buffer (peer-to-peer stores over NVLink from the
+    kernel's output stage; `MasParams::peer_dur` in csrc/mas_forward.cuh).  No NCCL kernel runs beside the next step and
+    nothing sits on the host path of a step -- torch.distributed costs ~25 us of host time per call, more than half of
+    the 37 us step it would accompany.
+
+    The buffers are symmetric memory (torch.distributed._symmetric_memory: one allocation per rank, mapped into every
+    peer's address space).  `gathered` holds the durations of the LAST step every rank has completed; a reader
+    synchronises with the writers the way it would for any one-sided put: stream-sync + `barrier()` (or any later
+    collective) before it reads, and before the step after next overwrites the rows.
+
+    GPU only (NVLink / PCIe peer access between the ranks' devices); raises if symmetric memory cannot be set up --
+    callers fall back to `all_gather_durations_into`."""
+
+    def __init__(self, b_local: int, tx: int, device, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm
+
+        group = group or dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.gathered = symm.empty((self.world * b_local, tx), dtype=torch.int32, device=device)
+        self.gathered.zero_()
+        self.handle = symm.rendezvous(self.gathered, group)
+        self._ptrs_dev = int(self.handle.buffer_ptrs_dev)
+        self._on = False
+
+    def put(self, dur_local: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Stream-ordered put of this rank's durations [B_local, Tx] into every rank's buffer by a small copy kernel
+        (mas_b200_put_durations) -- for callers that keep the gather off the step's critical path on a side stream."""
+        from . import _lib
+
+        st = stream if stream is not None else torch.cuda.current_stream(dur_local.device)
+        _lib.check(_lib.lib().mas_b200_put_durations(dur_local.data_ptr(), dur_local.shape[0], dur_local.shape[1], self._ptrs_dev,
+                                                     self.world, self.rank, st.cuda_stream), "mas_b200_put_durations")
+
+    def enable(self) -> None:
+        """From now on the fused kernel of this process stores its durations itself (no extra launch; the remote stores
+        add their NVLink round trip to the end of the kernel: +4 us per step measured at N = 2)."""
+        from . import _lib
+
+        _lib.check(_lib.lib().mas_b200_set_pointer_option(b"peer_dur_ptrs", self._ptrs_dev), "mas_b200_set_pointer_option")
+        _lib.set_option("peer_rank", self.rank)
+        _lib.set_option("peer_world", self.world)
+        self._on = True
+
+    def disable(self) -> None:
+        from . import _lib
+
+        if self._on:
+            _lib.set_option("peer_world", 0)
+            _lib.check(_lib.lib().mas_b200_set_pointer_option(b"peer_dur_ptrs", None), "mas_b200_set_pointer_option")
+            self._on = False
+
+    def barrier(self) -> None:
+        """All ranks' puts issued before this point (on their current streams) are complete and visible."""
+        torch.cuda.current_stream(self.gathered.device).synchronize()
+        dist.barrier()

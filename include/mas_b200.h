@@ -153,6 +153,19 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev,
                                     int impl, void *stream);
 
 /*
+ * Multi-GPU loss bookkeeping: one-sided gather of this rank's durations [B,Tx] into every rank's
+ * [world*B, Tx] int32 buffer, rows [rank*B, +B).  peer_ptrs_dev: DEVICE array of `world` pointers, entry r = rank
+ * r's buffer as mapped into this device's address space (symmetric memory / cudaIpc / cuMem peer mapping; the
+ * kernel stores over NVLink).  Replaces nothing in the reference -- its DDP ranks align their own
+ * per_gpu_batchsize shard (config.py:144-145) and never exchange alignments -- but is what a caller needs for global
+ * duration statistics; it takes the place of an NCCL all-gather whose host-side cost exceeds the alignment step itself.
+ * Completion is stream-ordered on the WRITER; readers synchronise as for any one-sided put (barrier / later collective).
+ * The same gather can ride in the fused kernel itself: options peer_dur_ptrs / peer_world / peer_rank.
+ */
+int mas_b200_put_durations(const int *durations_dev, int B, int Tx, void *const *peer_ptrs_dev, int world, int rank,
+                           void *stream);
+
+/*
  * Dense path from integer durations (the inverse op, used at inference).
  * Replaces: generate_path(duration, mask)  model/utils.py:27-40
  *   path[b,x,y] = 1 iff cum[b,x-1] <= y < cum[b,x], x < t_x, y < t_y

@@ -463,3 +463,38 @@ def test_upload_batch_rejects_pageable_memory():
     rc = L.mas_b200_upload_batch(mu_x.data_ptr(), y.data_ptr(), t_x.data_ptr(), t_y.data_ptr(), 2, 80, 21, 64,
                                  d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), None)
     assert rc == fgt._lib.ERR_ARG
+
+
+@pytest.mark.parametrize("B,Tx", [(6, 190), (5, 100)])
+def test_one_sided_duration_gather_writes_every_peer_buffer(B, Tx):
+    """Multi-GPU duration gather without a collective: with peer_world > 0 the fused kernel also stores its durations
+    into rows [peer_rank * B, +B) of every buffer in `peer_dur_ptrs` (on a multi-GPU box: every rank's symmetric-memory
+    gather buffer, face_gan_tts_b200.sharding.OneSidedDurationGather).  Here: three local buffers standing in for three
+    ranks' mappings, this process as rank 1 -- pair form (Tx = 190) and one-CTA form, incl. an item the kernel rejects."""
+    from face_gan_tts_b200 import _lib
+
+    world, rank = 3, 1
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=80, Tx=Tx, Ty=600, seed=9, tx_lo=20, ty_lo=Tx)
+    t_x[2] = int(t_y[2]) + 1 if int(t_y[2]) < Tx else t_x[2]          # may be a bad item (t_x > t_y) -> zeros
+    bufs = [torch.full((world * B, Tx), -7, dtype=torch.int32, device=DEV) for _ in range(world)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    _lib.set_pointer_option("peer_dur_ptrs", ptrs)
+    _lib.set_option("peer_rank", rank)
+    _lib.set_option("peer_world", world)
+    try:
+        r = fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, dense_path=False)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("peer_world", 0)
+        _lib.set_pointer_option("peer_dur_ptrs", None)
+    for b in bufs:
+        assert torch.equal(b[rank * B:(rank + 1) * B], r.durations)
+        assert bool((b[:rank * B] == -7).all()) and bool((b[(rank + 1) * B:] == -7).all())
+    # the same gather as a separate, stream-ordered put (mas_b200_put_durations)
+    bufs2 = [torch.full((world * B, Tx), -7, dtype=torch.int32, device=DEV) for _ in range(world)]
+    ptrs2 = torch.tensor([b.data_ptr() for b in bufs2], dtype=torch.int64, device=DEV)
+    _lib.check(_lib.lib().mas_b200_put_durations(r.durations.data_ptr(), B, Tx, ptrs2.data_ptr(), world, rank,
+                                                 torch.cuda.current_stream().cuda_stream), "mas_b200_put_durations")
+    torch.cuda.synchronize()
+    for b, b2 in zip(bufs, bufs2):
+        assert torch.equal(b, b2)
