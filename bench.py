@@ -11,7 +11,7 @@ Metric: alignment cells/s = B*T_text*T_mel / time (padded cells), whole job over
 
   value     inputs already resident in HBM; K steps back to back on one stream between two
             CUDA events; a step is ONE kernel (lp_mas_fused_kernel: tcgen05 log-prior -> shared-memory
-            ring -> MAS -> backtrack -> dense path); the steps rotate over NSETS independent buffer
+            ring -> MAS -> backtrack -> dense path; at this batch size a 2-CTA cluster per utterance); the steps rotate over NSETS independent buffer
             sets whose footprint exceeds L2, so no step finds its inputs in cache.
   e2e       the same step through the public API with HOST buffers: every step moves the batch from
             pinned host memory (packed ragged form, one copy-engine transfer + device unpack), runs
@@ -28,9 +28,14 @@ Metric: alignment cells/s = B*T_text*T_mel / time (padded cells), whole job over
 
 Multi-GPU (torchrun, one rank per GPU): utterances are independent, so each rank aligns its
 own 32-utterance shard (weak scaling, no data-path collective); the per-token durations are
-returned to every rank with one asynchronous NCCL all-gather per step (loss bookkeeping),
-overlapped with the next step and completed inside the timed region.  `strong_scaling_configs4`
-adds BASELINE configs[4]: a fixed total batch (64..1024) split over the ranks.
+returned to every rank every step (loss bookkeeping) by a ONE-SIDED gather: every rank's
+[world*B, Tx] buffer is symmetric memory mapped into all peers, and a rank's durations are
+stored into all of them over NVLink -- by a small copy kernel on a side stream (default: off the
+step's critical path) or by the fused kernel's own output stage (--put-in-kernel) -- overlapped
+with the next step and completed inside the timed region.  No collective kernel, no
+torch.distributed call per step (an NCCL all-gather per step costs more host time than the
+step takes on the GPU; --nccl-gather keeps that path).  `strong_scaling_configs4` adds BASELINE
+configs[4]: a fixed total batch (64..1024) split over the ranks.
 """
 import argparse
 import json
@@ -323,6 +328,19 @@ def run_sweep(dev, peak, K):
         out.append(e)
 
     reps = max(5, min(K, 20))
+    # ---- the reference's default n_feats = 128 at the LRS2 batch shape: the fused kernel's pair form (a 2-CTA cluster per
+    # utterance; one CTA cannot hold two M-tiles of A in tensor memory at F = 128)
+    Bn, Fn, Tx, Ty = B, 128, TX, TY
+    mu_x, y, t_x, t_y = synthetic.lrs2_batch(Bn, Fn, Tx, Ty, seed=98)
+    mu_d, y_d, tx_d, ty_d = mu_x.to(dev), y.to(dev), t_x.to(dev), t_y.to(dev)
+    vc = int((t_x.long() * t_y.long()).sum())
+    plans = [fgt.AlignmentPlan(Bn, Fn, Tx, Ty, device=dev, dense_path=True) for _ in range(4)]     # rotate > L2
+    ms = cuda_time(stream, dev, lambda i: plans[i % 4](mu_d, y_d, tx_d, ty_d), max(reps, 20))
+    entry("configs[1] shape at the reference default n_feats=128", "fused kernel (pair form), dense fp32 path", Bn, Fn, Tx, Ty, ms,
+          4 * Fn * Bn * (Tx + Ty) + 4 * Bn * Tx * Ty + 4 * Bn * (Tx + Ty),
+          4 * Fn * int((t_x.long() + t_y.long()).sum()) + 4 * Bn * Tx * Ty + 4 * Bn * (Tx + Ty), vc,
+          note="round 1 / the one-CTA kernel: serial form (split-M log-prior -> HBM -> MAS -> expand), 69 us")
+    del plans, mu_d, y_d
     # ---- configs[4] at one GPU: B = 1024 of the LRS2 shape
     Bn, Fn, Tx, Ty = 1024, F, TX, TY
     mu_x, y, t_x, t_y = synthetic.lrs2_batch(Bn, Fn, Tx, Ty, seed=99)
@@ -561,13 +579,21 @@ def run_cuda(args):
             args_d = (mu_x.to(dev), y.to(dev), t_x.to(dev), t_y.to(dev))
             plan = fgt.AlignmentPlan(bl, F, TX, TY, device=dev, dense_path=True)
             gat = torch.empty((b_total, TX), dtype=torch.int32, device=dev)
+            sput = None
+            if put is not None:
+                try:        # the fused kernel stores its durations into every rank's buffer itself: one launch per step
+                    sput = sharding.OneSidedDurationGather(bl, TX, dev)
+                    sput.enable()
+                except Exception:
+                    sput = None
 
             def sstep(i):
                 r = plan(*args_d)
-                comm_stream.wait_stream(stream)
-                with torch.cuda.stream(comm_stream):
-                    sharding.all_gather_durations_into(gat, r.durations)
-                stream.wait_stream(comm_stream)      # the next step overwrites plan.durations
+                if sput is None:
+                    comm_stream.wait_stream(stream)
+                    with torch.cuda.stream(comm_stream):
+                        sharding.all_gather_durations_into(gat, r.durations)
+                    stream.wait_stream(comm_stream)      # the next step overwrites plan.durations
 
             for i in range(3):
                 sstep(i)
@@ -582,8 +608,12 @@ def run_cuda(args):
             t = torch.tensor([a_.elapsed_time(b_) / reps], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             strong.append({"B_total": b_total, "B_per_gpu": bl, "ms_per_step": float(t.item()),
-                           "cells_per_s": b_total * TX * TY / (float(t.item()) * 1e-3)})
-            del plan, gat, args_d
+                           "cells_per_s": b_total * TX * TY / (float(t.item()) * 1e-3),
+                           "gather": "one-sided, by the fused kernel" if sput is not None else "NCCL all-gather"})
+            if sput is not None:
+                assert bool((sput.gathered.view(world, bl, TX).sum(-1) >= 1).all()), "strong scaling: a rank's durations did not arrive"
+                sput.disable()
+            del plan, gat, args_d, sput
         torch.cuda.empty_cache()
 
     # ---- e2e (every rank): HOST buffers in, results back to pinned host memory, every step, inside the timed region.
@@ -717,9 +747,10 @@ def run_cuda(args):
         step_bytes = 4 * F * B * (TX + TY) + 4 * CELLS + 4 * B * (TX + TY)
         step_bytes_valid = valid_in + 4 * CELLS + 4 * B * (TX + TY)
         achieved = step_bytes / (t_fused * 1e-3) / 1e9
-        traffic = ncu_dram_bytes("r2_ncu_fused_B32.json")
+        traffic = ncu_dram_bytes("r2_ncu_fused_pair_B32.json") or ncu_dram_bytes("r2_ncu_fused_B32.json")
         roofline = {
-            "bound": "hbm", "kernel": "lp_mas_fused_kernel<10,2> (log-prior + MAS + dense path, one CTA per utterance)",
+            "bound": "hbm", "kernel": "lp_mas_fused_kernel<10,1,pair> (log-prior + MAS + dense path; a 2-CTA cluster per utterance: one 128-row "
+                                      "M-tile and one DP warp per CTA, halo row / direction words cross with st.async)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "achieved_valid": step_bytes_valid / (t_fused * 1e-3) / 1e9,
             "frac_valid": step_bytes_valid / (t_fused * 1e-3) / 1e9 / peak,
@@ -729,9 +760,10 @@ def run_cuda(args):
                            "serial form: log_prior + mas_forward + path_expand": t_serial,
                            "log_prior alone (tcgen05, -> HBM)": t_lp, "mas_forward alone (index outputs)": t_mas,
                            "mas_forward + path_expand": t_mas_dense},
-            "tensor_pipe": "3xTF32 tcgen05.mma, A in TMEM: 62 MMAs (M=128,N=32,K=8) per 32-frame tile of an utterance",
-            "note": "B=32 CTAs on 148 SMs: the step is bound by the T_mel-long dependency chain of the DP "
-                    "(~50 cycles/frame in one warp per 128 text rows), not by HBM; the throughput regime is in `sweep`",
+            "tensor_pipe": "3xTF32 tcgen05.mma, A in TMEM: 31 MMAs (M=128,N=32,K=8) per 32-frame tile and CTA",
+            "note": "2B=64 CTAs on 148 SMs: the step is bound by the T_mel-long dependency chain of the DP "
+                    "(~50 cycles/frame in one warp per 128 text rows; profiles/r2_phase_cycles.txt), not by HBM; the throughput "
+                    "regime is in `sweep`",
         }
         if traffic:
             roofline["frac_dram"] = traffic / (t_fused * 1e-3) / 1e9 / peak
@@ -788,9 +820,10 @@ def run_cuda(args):
             "roofline": roofline, "cpu_baseline": cpu, "path_agreement": agreement, "sweep": sweep,
             "strong_scaling_configs4": strong, "compute_loss_block": block,
             "e2e": e2e, "e2e_padded_copy": e2e_padded, "e2e_dense_path": e2e_dense,
-            "gpu_launches": K, "launches_per_step": 1,
+            "gpu_launches": K * (2 if (dist and put is not None and not args.put_in_kernel) else 1),
+            "launches_per_step": 2 if (dist and put is not None and not args.put_in_kernel) else 1,
             "pipeline": "ONE kernel per step: lp_mas_fused_kernel (tcgen05 log-prior -> shared-memory ring -> MAS -> backtrack "
-                        "-> dense path), programmatic dependent launch",
+                        "-> dense path), programmatic dependent launch" + ("; + the duration put kernel on a side stream" if (dist and put is not None and not args.put_in_kernel) else ""),
             "host_enqueue_us_per_step": host_enqueue_us, "host_cores_per_rank": host_cores,
             "launch": "CUDA graph replay of the fused call + eager NCCL all-gather" if graphs[0] is not None else "eager",
             "clocks": clocks,
