@@ -190,14 +190,17 @@ int mas_b200_log_prior_maximum_path(const float *mu_x_dev, const float *y_dev, c
     const size_t mas_ws = align_up(workspace_layout(B, Tx, Ty).total, 256);
     float *value = reinterpret_cast<float *>(static_cast<char *>(workspace_dev) + mas_ws);
 
-    // One kernel, one CTA per utterance: the tcgen05 epilogue writes the value tiles into the shared-memory ring
-    // of the alignment search (lp_mas_fused.cu).  Shapes it does not cover (n_feats = 128, texts longer than 256
-    // tokens, very long utterances) run the serial form: log-prior kernel -> [B,Tx,Ty] in the workspace -> MAS kernel.
+    // One kernel -- one CTA, or a 2-CTA cluster, per utterance: the tcgen05 epilogue writes the value tiles into the
+    // shared-memory ring of the alignment search (lp_mas_fused.cu).  Shapes it does not cover (texts longer than 256
+    // tokens, n_feats = 96 / 128 with more than 128 tokens in a batch too large for the pair form, very long utterances)
+    // run the serial form: log-prior kernel -> [B,Tx,Ty] in the workspace -> MAS kernel.
     const bool tc_wanted = (impl == MAS_B200_LP_AUTO || impl == MAS_B200_LP_TCGEN05) && option("lp_impl") != MAS_B200_LP_FFMA;
-    if (tc_wanted && option("fused_impl") != 1 && lp_mas_fused_supported(mu_x_dev, y_dev, B, F, Tx, Ty))
-        return launch_lp_mas_fused(mu_x_dev, y_dev, t_x_dev, t_y_dev, B, F, Tx, Ty, max_neg_val, path_dev, path_dtype,
-                                   durations_dev, frame_token_dev, status_dev, workspace_dev, mas_ws,
-                                   static_cast<cudaStream_t>(stream));
+    if (tc_wanted && option("fused_impl") != 1 && lp_mas_fused_supported(mu_x_dev, y_dev, B, F, Tx, Ty)) {
+        const int rc = launch_lp_mas_fused(mu_x_dev, y_dev, t_x_dev, t_y_dev, B, F, Tx, Ty, max_neg_val, path_dev, path_dtype,
+                                           durations_dev, frame_token_dev, status_dev, workspace_dev, mas_ws,
+                                           static_cast<cudaStream_t>(stream));
+        if (rc != MAS_B200_ERR_UNSUPPORTED) return rc;      // (a refused cluster launch without a one-CTA form: serial form)
+    }
     int rc = mas_b200_log_prior(mu_x_dev, y_dev, B, F, Tx, Ty, value, impl, stream);
     if (rc != MAS_B200_OK) return rc;
     return mas_b200_maximum_path(value, (long long)Tx * Ty, Ty, t_x_dev, t_y_dev, B, Tx, Ty, max_neg_val, path_dev,

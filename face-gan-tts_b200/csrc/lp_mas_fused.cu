@@ -930,6 +930,14 @@ int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const
         FusedParams probe = FP;
         const bool pair = fused_pair_wanted(B, Tx) && fused_dispatch(F, probe, ymap, stream, true, true) == MAS_B200_OK;
         rc = fused_dispatch(F, FP, ymap, stream, false, pair);
+        if (pair && rc == MAS_B200_ERR_CUDA) {
+            // the cluster launch was refused (e.g. a partitioned device that cannot co-schedule two such CTAs): the same
+            // computation as one CTA per utterance where that form exists, else the caller's serial form
+            (void)cudaGetLastError();
+            FusedParams retry = FP;
+            if (fused_dispatch(F, retry, ymap, stream, true, false) != MAS_B200_OK) return MAS_B200_ERR_UNSUPPORTED;
+            rc = fused_dispatch(F, FP, ymap, stream, false, false);
+        }
     }
     if (rc != MAS_B200_OK) return rc;
     if (want_path && !fuse) return launch_path_expand(P.start, P.dur, B, Tx, Ty, path, path_dtype, stream);

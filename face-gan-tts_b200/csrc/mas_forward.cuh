@@ -265,12 +265,14 @@ __device__ __forceinline__ void dp_tile_pre(float (&q)[R], uint32_t (&acc)[R], f
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] >>= 8;
         }
-        dp_group<R, 0, DIAG, CK>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_addr);
+        // the block's halo address is formed afresh from the loop index: advancing ONE register in place right behind the
+        // halo STS.128 made the add wait for the store to read its address operand (2 cycles per frame in the profile)
+        const uint32_t hout_i = hout_addr + 32u * (uint32_t)i;
+        dp_group<R, 0, DIAG, CK>(q, acc, up, va, ha, lane0_mask, dl0, neg, hout_i);
         // next block's first group; the last block re-reads group 0 (no branch in the body)
         load_group<R, XP>(va, lane_tile, lane7, (2 * i + 2) & 7); ha = h4[(2 * i + 2) & 7];
-        dp_group<R, 1, DIAG, CK>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_addr);
+        dp_group<R, 1, DIAG, CK>(q, acc, up, vb, hb, lane0_mask, dl0, neg, hout_i);
         dl0 -= 8 / R;
-        hout_addr += 32u;
     }
 }
 

@@ -10,7 +10,7 @@ mu, y, tx, ty = synthetic.lrs2_batch(B=B, F=80, Tx=190, Ty=1000, seed=1234)
 if full:
     tx[:] = 190; ty[:] = 1000
 mu, y, tx, ty = mu.cuda(), y.cuda(), tx.cuda().int(), ty.cuda().int()
-plan = fgt.AlignmentPlan(B, 80, 190, 1000, device="cuda:0", dense_path=False)
+plan = fgt.AlignmentPlan(B, 80, 190, 1000, device="cuda:0", dense_path=os.environ.get("FUSED_DENSE", "0") == "1")
 for _ in range(4):
     r = plan(mu, y, tx, ty)
 torch.cuda.synchronize()
