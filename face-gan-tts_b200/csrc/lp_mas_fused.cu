@@ -1,7 +1,8 @@
-// lp_mas_fused.cu -- the fused log-prior + Monotonic Alignment Search kernel: ONE CTA per utterance, ONE launch,
-// the [Tx,Ty] value matrix never leaves the SM.
+// lp_mas_fused.cu -- the fused log-prior + Monotonic Alignment Search kernel: ONE launch, one CTA -- or, for texts of
+// 129..256 tokens in batches that fit the SMs twice, a 2-CTA cluster (PAIR: one 128-row M-tile and one DP warp per CTA,
+// the halo row and the direction words cross with st.async) -- per utterance; the [Tx,Ty] value matrix never leaves the SM.
 //
-// Replaces reference model/face_tts.py:165-174 (log_prior -> maximum_path) for F = n_feats in {64, 80, 96} and
+// Replaces reference model/face_tts.py:165-174 (log_prior -> maximum_path) for F = n_feats in {64, 80, 96, 128} and
 // Tx <= 256 (the LRS2 training shapes).  The tcgen05 front end (TMA y tiles -> exact tf32 hi/lo split -> 3xTF32
 // tcgen05.mma with A = mu_x parked in TENSOR MEMORY, lp_tc_frontend.cuh) produces the value matrix one 32-frame
 // tile at a time; its epilogue writes every tile STRAIGHT INTO THE SHARED-MEMORY RING the alignment search reads
@@ -10,7 +11,8 @@
 //   A_extra[x] = (1, 1, mc_hi, mc_lo, 0, 0, 0, 0),  B_extra[t] = (ysq_hi, ysq_lo, 1, 1, 0, 0, 0, 0),   mc = musq[x] + const,
 // (exact tf32 pairs again), so the accumulator leaves TMEM as the finished log-prior value and the epilogue is a pure
 // TMEM -> shared-memory copy: it shares its scheduler partition with a DP warp and must stay out of its way.
-// The path is the bit-exact MAS of exactly these values (tests dump them through the fused_dump_ptr option).
+// The path is the bit-exact MAS of exactly these values (tests dump them through the fused_dump_ptr option); the search
+// runs the predicate-free cell (mas_forward.cuh: kCellSign), identical to the reference's for the finite values it sees.
 //
 // Warp roles (16 warps; warp % 4 = scheduler partition, the arbiter favours the higher warp id):
 //    0..3   epilogue: per tile TMEM -> registers -> ring (in the prologue: musq + const)
@@ -18,6 +20,7 @@
 //    10     TMA loads (mu_x block, y tiles) + tcgen05.mma issue
 //    11, 14, 15 backtrack helpers: per-tile transfer tables in the shadow of the DP (an even share of the row groups each)
 //    12, 13 DP warps (text rows 0..127 / 128..255): alone with one epilogue warp on partitions 0 / 1, highest ids there
+//           (PAIR: warp 12 is the CTA's DP warp; warp 13 of rank 0 forwards the halo row to the peer CTA)
 //    9      dense path (when requested): streams the all-zero [Tx,Ty] block out with bulk copies from an 8 KB zero
 //           buffer while the search runs -- the result only adds ~t_y ones to it (written by all warps in the tail)
 //    4, 5, 8  parked until the tail (they only keep the latency-critical DP warps' partitions quiet)

@@ -130,8 +130,10 @@ int mas_b200_log_prior(const float *mu_x_dev, const float *y_dev,
 /*
  * Fused log-prior + MAS: mu_x, y -> path / durations / frame_token in one call, entirely on the device.
  * Replaces: model/face_tts.py:165-174 (log-prior block + maximum_path call).
- * ONE kernel, one CTA per utterance (lp_mas_fused.cu), for n_feats in {64, 80} with Tx <= 256 or n_feats in
- * {64, 80, 96, 128} with Tx <= 128, Ty % 4 == 0, 16-byte aligned mu_x / y: tcgen05 3xTF32 contraction with mu_x parked
+ * ONE kernel (lp_mas_fused.cu): one CTA per utterance for n_feats in {64, 80} with Tx <= 256 or n_feats in
+ * {64, 80, 96, 128} with Tx <= 128; a 2-CTA cluster per utterance (one 128-row M-tile each) for Tx in 129..256 when
+ * both CTAs of every utterance are resident at once (2B <= SMs; option fused_pair), which also covers n_feats 96 / 128
+ * there.  Ty % 4 == 0, 16-byte aligned mu_x / y.  tcgen05 3xTF32 contraction with mu_x parked
  * in tensor memory, its accumulator written tile by tile straight into the shared-memory ring the alignment search
  * reads -- the [Tx,Ty] value matrix never exists in global memory --, then backtrack, durations, frame_token and (if
  * requested) the dense path, whose zeros are streamed out while the search runs.  The path is the bit-exact MAS
