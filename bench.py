@@ -465,6 +465,7 @@ def run_cuda(args):
             sys.stderr.write(f"bench.py: one-sided duration gather unavailable ({ex!r}); NCCL all-gather per step\n")
             put = None
     graphs = [None]      # multi-GPU: CUDA graphs of the fused call, one per buffer set (see below)
+    gl = g_ = None
     gathered = [torch.empty((world * B, TX), dtype=torch.int32, device=dev) for _ in range(2)] if dist else None
     comm_stream = torch.cuda.Stream(dev) if dist else None
     step_done = [torch.cuda.Event() for _ in range(4)] if dist else None
@@ -830,6 +831,13 @@ def run_cuda(args):
         }
     if dist:
         dist.barrier()
+        # CUDA graphs go before the communicator does: destroy_process_group() never returns while a graph that captured
+        # NCCL work is alive (scripts/diag/graph_nccl_probe.py) -- none of the graphs here does, but keep the order
+        graphs[0] = None
+        gl = g_ = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(dev)
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))
