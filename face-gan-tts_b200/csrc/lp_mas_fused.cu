@@ -67,6 +67,7 @@ struct FusedParams {
     const float *mu;     // [B,F,Tx]
     float cst;           // -0.5 * F * log(2 pi)
     float *value_dump;   // tests only: [B,Tx,Ty], receives the value tiles the search consumed (null normally)
+    const float *y_pf;   // y [B,F,Ty]: only for the L2 prefetch hints ahead of the dependent-launch wait (the tiles come by TMA)
     int exp;             // diagnostics (MASB200_FUSED_PROF builds): see option fused_exp
 };
 
@@ -216,6 +217,17 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         for (uint32_t i = tid; i < kZeroBytes / 16; i += kFusedThreads) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async_smem();                            // generic-proxy zeros -> visible to the bulk stores reading them
     }
+    // ... and L2 prefetches of what the prologue is about to read (hints, not accesses: L2 is the point of coherence, a
+    // line the previous kernel still writes is simply updated there): the lengths, this CTA's mu_x block, the first two y
+    // tiles, the tensor map.  After the wait the prologue's loads are L2 hits instead of HBM round trips.
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ymap)) : "memory");
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.t_x + b));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.t_y + b));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(FP.mu + (size_t)b * F * P.Tx), "r"((uint32_t)(F * P.Tx * 4)) : "memory");
+    }
+    if (tid >= 32 && tid < 32 + 2 * F && 64 <= P.Ty)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(FP.y_pf + ((size_t)b * F + ((tid - 32) >> 1)) * P.Ty + 32 * ((tid - 32) & 1)));
     // nothing the previous kernel may have written is touched before this wait returns
     pdl_wait();
     long long *dbg = P.dbg ? P.dbg + ((size_t)rank * P.B + b) * 32 : nullptr;   // diagnostics ([2B][32] for a pair): phase stamps [0..15], wait cycles [16..31]
@@ -916,6 +928,7 @@ int launch_lp_mas_fused(const float *mu_x, const float *y, const int *t_x, const
     P.path = (want_path && fuse) ? path : nullptr;
     P.path_dtype = (want_path && fuse) ? path_dtype : MAS_B200_PATH_NONE;
     FP.mu = mu_x;
+    FP.y_pf = y;
     FP.cst = log_prior_const(F);
     {   // tests only: device pointer to a [B,Tx,Ty] buffer that receives the value tiles (two int options)
         const unsigned lo = (unsigned)option("fused_dump_ptr_lo"), hi = (unsigned)option("fused_dump_ptr_hi");
