@@ -717,10 +717,10 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
             // code re-reads a resident stage (no branch on "last tile": one vote covers everything).
             PROF_T(cw0);
             const int need = min(j + 2, ntiles);
-            if (!__all_sync(kFullMask, sync_next >= need && halo_next)) {
-                flag_wait_ge_warp(sync_word, need);
-                if (halo_remote) mbar_wait_warp(&bar_h[min(j + 1, ntiles - 1)], 0);
-            }
+            if (!__all_sync(kFullMask, sync_next >= need)) flag_wait_ge_warp(sync_word, need);
+            // pair rank 1 runs one to two tiles behind rank 0, so the early probe of the peer's halo row fails about every
+            // other tile: wait for it alone (the probe's result is warp-uniform), not for the flags again
+            if (!halo_next) mbar_wait_warp(&bar_h[min(j + 1, ntiles - 1)], 0);
             dp_tile_prefetch<R, XP>(va, ha, lane_tile_next, hin_next, lane7);
             PROF_ADD(w_full, cw0);
 
