@@ -10,4 +10,4 @@ PB=1024 timeout 200 ncu --set full --clock-control none --import-source on -k re
 PB=32 timeout 200 ncu --set full --clock-control none --import-source on -k regex:mas_forward -c 1 -s 3 -f -o gpurun_out/r2_mas_forward_B32 python scripts/profile_mas.py > gpurun_out/ncu5.log 2>&1
 FUSED_FULL=1 FUSED_B=74 timeout 300 ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k regex:lp_mas_fused -c 1 -s 3 -f -o gpurun_out/r2_fused_pair_b74_si0 python scripts/fused_once.py > gpurun_out/ncu4.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -8
-tail -2 gpurun_out/ncu1.log gpurun_out/ncu4.log
+tail -n 2 gpurun_out/ncu1.log; tail -n 2 gpurun_out/ncu4.log
