@@ -498,3 +498,34 @@ def test_one_sided_duration_gather_writes_every_peer_buffer(B, Tx):
     torch.cuda.synchronize()
     for b, b2 in zip(bufs, bufs2):
         assert torch.equal(b, b2)
+
+
+def test_pair_form_fuzz_equals_one_cta_form():
+    """Randomised shapes on the M-tile / tile edges (Tx in {129, 130, 191..193, 255, 256}, Ty up to 1404, B up to 74, items
+    with t_x = 128 / 129 / Tx): the 2-CTA-cluster form and the one-CTA form must agree bit for bit."""
+    import random
+    from face_gan_tts_b200 import _lib
+
+    rng = random.Random(7)
+    for it in range(24):
+        B = rng.choice([1, 2, 3, 5, 9, 33, 74])
+        F = rng.choice([64, 80])
+        Tx = rng.choice([129, 130, 160, 191, 192, 193, 224, 255, 256])
+        Ty = max(rng.choice([260, 288, 320, 516, 1000, 1028, 1404]), ((Tx + 3) // 4) * 4)
+        mu_x, y, t_x, t_y = synthetic.lrs2_batch(B=B, F=F, Tx=Tx, Ty=Ty, seed=100 + it, tx_lo=1, ty_lo=min(Ty, max(4, Tx // 2)))
+        t_x[0], t_y[0] = Tx, Ty
+        if B > 1:
+            t_x[1], t_y[1] = 129, max(int(t_y[1]), 129)
+        if B > 2:
+            t_x[2], t_y[2] = 128, max(int(t_y[2]), 128)
+        outs = []
+        for mode in (0, 2):
+            prev = _lib.set_option("fused_pair", mode)
+            try:
+                outs.append(fgt.log_prior_maximum_path(mu_x.to(DEV), y.to(DEV), t_x, t_y, path_dtype=torch.int32))
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_option("fused_pair", prev)
+        a, b = outs
+        assert int(a.status.abs().sum()) == 0 and torch.equal(a.status, b.status), (B, F, Tx, Ty)
+        assert torch.equal(a.durations, b.durations) and torch.equal(a.frame_token, b.frame_token) and torch.equal(a.path, b.path), (B, F, Tx, Ty)
