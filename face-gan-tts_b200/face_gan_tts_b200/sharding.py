@@ -5,7 +5,10 @@ data-path collective.  The only exchange is the optional all-gather of the per-t
 (each aligns its own per_gpu_batchsize shard, config.py:145) but a caller that wants global duration
 statistics needs.
 
-Backend-agnostic (`nccl` on GPUs, `gloo` in the CPU tests): only torch.distributed calls, no kernels.
+`all_gather_durations*` are backend-agnostic (`nccl` on GPUs, `gloo` in the CPU tests): only torch.distributed calls, no
+kernels.  `OneSidedDurationGather` is the GPU form the bench uses: symmetric-memory buffers and stores over NVLink
+(mas_b200_put_durations, or the fused kernel's own output stage) instead of a collective -- a torch.distributed call per
+step costs more host time than the alignment step takes on a B200.
 """
 from __future__ import annotations
 
