@@ -569,6 +569,15 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # the clock sampler opens NVML (tens of ms) BEFORE the warm-up, so that nothing but the barrier sits between the warm-up
+    # steps and the timed region
+    try:
+        dev_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
+    if rank == 0 and os.environ.get("MAS_B200_BENCH_CLOCKS", "on") != "off":
+        sampler.start()
     for i in range(W):
         step(i)
     barrier()
@@ -610,13 +619,6 @@ def run_cuda(args):
             sys.stderr.write(f"bench.py: CUDA-graph capture failed ({ex!r}); eager launches\n")
             graphs[0] = None
             torch.cuda.synchronize(dev)
-    try:
-        dev_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
-    except Exception:
-        dev_uuid = None
-    sampler = ClockSampler(local_rank, dev_uuid)
-    if rank == 0:
-        sampler.start()
     mark = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
