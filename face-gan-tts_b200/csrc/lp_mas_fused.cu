@@ -228,6 +228,24 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     }
     if (tid >= 32 && tid < 32 + 2 * F && 64 <= P.Ty)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(FP.y_pf + ((size_t)b * F + ((tid - 32) >> 1)) * P.Ty + 32 * ((tid - 32) & 1)));
+    // PAIR: the one-shot hand-off barriers -- one per tile the PADDED length allows, so that nothing here depends on the
+    // lengths -- are armed for the bytes the peer will send (rank 1 receives the halo row of every tile: 32 floats; rank 0
+    // rank 1's direction words: 128 rows x 4 bytes), and the peer is told (cluster barrier, arrive half; the matching wait
+    // sits behind the prologue).  The cluster-scope fence + release cost ~1.2 k cycles when they sat behind the wait.
+    // Barriers of tiles beyond t_y, or of an utterance whose second CTA has nothing to do, simply stay armed.
+    const int ntmax = (P.Ty + NT - 1) / NT;
+    uint64_t *bar_h = reinterpret_cast<uint64_t *>(smem_raw + FS::off_pair(NS, ntmax));      // PAIR [ntmax]: halo row of tile j has landed (rank 1)
+    uint64_t *bar_b = bar_h + ntmax;                                                           // PAIR [ntmax]: rank 1's direction words of tile j have landed (rank 0)
+    float *halo_full = reinterpret_cast<float *>(bar_b + ntmax);                               // PAIR [ntmax][32]: Q of text row 127 (rank 1)
+    if (PAIR) {
+        if (tid >= 32 && tid < 32 + ntmax) {
+            uint64_t *bar = (rank == 0 ? bar_b : bar_h) + (tid - 32);
+            mbar_init(bar, 1);
+            mbar_arrive_expect_tx(bar, rank == 0 ? 512u : 128u);
+            mbar_fence_init();
+        }
+        cluster_arrive();
+    }
     // nothing the previous kernel may have written is touched before this wait returns
     pdl_wait();
     long long *dbg = P.dbg ? P.dbg + ((size_t)rank * P.B + b) * 32 : nullptr;   // diagnostics ([2B][32] for a pair): phase stamps [0..15], wait cycles [16..31]
@@ -273,8 +291,8 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     if (P.status && tid == 0 && rank == 0) P.status[b] = MAS_B200_ITEM_OK;
 
     const int w_tot = (t_x + 32 * R - 1) / (32 * R);          // M-tiles of the utterance with valid rows
-    // a pair's second CTA has nothing to do for a text of <= 128 tokens: it leaves before any cluster-wide step (exited
-    // threads count as arrived at the cluster barrier) and before it owns tensor memory.  (Both early exits are plain
+    // a pair's second CTA has nothing to do for a text of <= 128 tokens: it leaves (its half of the cluster barrier is
+    // done: the arrive ahead of the launch wait; nobody waits for it) before it owns tensor memory.  (Both early exits are plain
     // returns on provably warp-uniform conditions; an exit that has to hand tensor memory back first -- a block barrier in
     // the exit path -- makes ptxas give up on the convergence of every warp behind it, and the MMA warp then issues through
     // the divergent elect fallback: ~90 instead of ~20 cycles per instruction.  Hence the allocation comes after them.)
@@ -284,9 +302,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kLpTmemCols); tmem_relinquish(); }
     const bool peer = PAIR && w_tot == 2;                     // the other CTA of the pair is at work too
     unsigned char *nj_s = reinterpret_cast<unsigned char *>(bits_s + (size_t)ntiles * XPT);  // [ntiles][XPT] transfer table
-    uint64_t *bar_h = reinterpret_cast<uint64_t *>(smem_raw + FS::off_pair(NS, ntiles));     // PAIR [ntiles]: halo row of tile j has landed (rank 1)
-    uint64_t *bar_b = bar_h + ntiles;                                                          // PAIR [ntiles]: rank 1's direction words of tile j have landed (rank 0)
-    float *halo_full = reinterpret_cast<float *>(bar_b + ntiles);                              // PAIR [ntiles][32]: Q of text row 127 (rank 1)
     // the prologue's mu_x staging reaches into the raw y buffers: y tiles (and everything behind them) start late
     const bool late_start = (size_t)F * W * 128 * 4 > FS::off_raw(NS);
 #pragma unroll
@@ -295,14 +310,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
         for (int j = 0; j < kMuCols; ++j)
             if (row0 + lane + 32 * j >= t_x) mu_reg[k][j] = 0.f;
 
-    if (PAIR && peer && tid >= 32 && tid < 32 + ntiles) {
-        // one-shot hand-off barriers, armed for the bytes the peer will send: rank 1 receives the halo row of every tile
-        // (32 floats), rank 0 rank 1's direction words (128 rows x 4 bytes)
-        uint64_t *bar = (rank == 0 ? bar_b : bar_h) + (tid - 32);
-        mbar_init(bar, 1);
-        mbar_arrive_expect_tx(bar, rank == 0 ? 512u : 128u);
-        mbar_fence_init();
-    }
     {
         // x = 32j + lane = 128*mt + 4*l + q with mt = j >> 2, l = 8*(j & 3) + (lane >> 2), q = lane & 3:
         //   position ((f*W + mt)*4 + q)*32 + (l ^ 8q) = f*W*128 + mt*128 + [q*32 + (lane >> 2) + ((8*(j & 3)) ^ 8q)]
@@ -323,9 +330,6 @@ lp_mas_fused_kernel(const FusedParams FP, const __grid_constant__ CUtensorMap ym
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(kFullMask, *tmem_slot, 0);
-    // both CTAs' hand-off barriers are armed (block barrier above): tell the peer; nothing is sent to it before the
-    // matching wait below, which the prologue hides
-    if (PAIR && peer) cluster_arrive();
     if (dbg && tid == 0) dbg[8] = clock64();
     // TMEM columns: M-tile mt: A hi at mt*(2F+8), A lo at +F, the extra K step at +2F; D of (stage p, M-tile mt) behind them
     auto col_a = [](int mt, int part) { return (uint32_t)(mt * (2 * F + 8) + part * F); };
