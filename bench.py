@@ -712,7 +712,6 @@ def run_cuda(args):
     NH = 3
     host_in = [[t.pin_memory() for t in synthetic.lrs2_batch(B, F, TX, TY, seed=4321 + 100 * rank + k)] for k in range(NH)]
     host_packed = [fgt.pack_batch(*h) for h in host_in]          # outside the timed region: this IS the input format
-    staging = [torch.empty((max(p.numel() for p in host_packed),), dtype=torch.uint8, device=dev) for _ in range(2)]
     dur_h = [torch.empty((B, TX), dtype=torch.int32).pin_memory() for _ in range(2)]
     ft_h = [torch.empty((B, TY), dtype=torch.int32).pin_memory() for _ in range(2)]
     path_h = [torch.empty((B, TX, TY), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -720,34 +719,50 @@ def run_cuda(args):
     plans = [fgt.AlignmentPlan(B, F, TX, TY, device=dev, dense_path=True) for _ in range(2)]
     plans_idx = [fgt.AlignmentPlan(B, F, TX, TY, device=dev, dense_path=False) for _ in range(2)]
 
+    NST = 3                                               # device staging buffers of the packed batch
+    staging = [torch.empty((max(p.numel() for p in host_packed),), dtype=torch.uint8, device=dev) for _ in range(NST)]
+    # events are REUSED (small rings): creating a fresh event per step inside the loop costs a driver call per step, and
+    # with 4-8 ranks on one host those calls serialise across the processes (scripts/diag/e2e_multirank.py: 169 -> 285 us
+    # per step at 4 ranks although every GPU still gets its 54 GB/s of PCIe, scripts/diag/h2d_multiproc.py)
+    EV = 4
+    h2d_done = [torch.cuda.Event() for _ in range(EV)]
+    unpacked = [torch.cuda.Event() for _ in range(NST)]
+    res_done = [torch.cuda.Event() for _ in range(2)]
+
     def run_e2e(nsteps, dense_d2h, mode):
-        h2d_done = [torch.cuda.Event() for _ in range(nsteps)]
-        res_done = [torch.cuda.Event() for _ in range(2)]
         checksum = 0
 
         def enqueue_h2d(i):
             d = sets[i % NSETS]
             with torch.cuda.stream(copy_stream):
                 if mode == "packed":
-                    fgt.upload_packed_batch(host_packed[i % NH], B, F, TX, TY, device=dev, out=(d["mu"], d["y"], d["tx"], d["ty"]),
-                                            staging=staging[i & 1])
+                    # the copy stream carries NOTHING but the host->device copies, so the copy engine runs back to back;
+                    # the unpack kernel of step i runs on the compute stream in front of the step.  Staging buffer reuse:
+                    # copy i overwrites what unpack i - NST read.
+                    if i >= NST:
+                        copy_stream.wait_event(unpacked[i % NST])
+                    p = host_packed[i % NH]
+                    staging[i % NST][:p.numel()].copy_(p, non_blocking=True)
                 else:
+                    if i >= 2:
+                        copy_stream.wait_event(res_done[i & 1])        # input set reuse: step i-2 is done with its tensors
                     mu_h, y_h, tx_h, ty_h = host_in[i % NH]
                     d["mu"].copy_(mu_h, non_blocking=True)
                     d["y"].copy_(y_h, non_blocking=True)
                     d["tx"].copy_(tx_h, non_blocking=True)
                     d["ty"].copy_(ty_h, non_blocking=True)
-                h2d_done[i].record(copy_stream)
+                h2d_done[i % EV].record(copy_stream)
 
         pl = plans if dense_d2h else plans_idx
         enqueue_h2d(0)
         for i in range(nsteps):
             if i + 1 < nsteps:
-                if i >= 1:
-                    copy_stream.wait_event(res_done[(i - 1) & 1])      # staging / input set reuse: step i-1 is done with them
                 enqueue_h2d(i + 1)
             d = sets[i % NSETS]
-            stream.wait_event(h2d_done[i])
+            stream.wait_event(h2d_done[i % EV])
+            if mode == "packed":
+                fgt.unpack_batch(staging[i % NST], B, F, TX, TY, out=(d["mu"], d["y"], d["tx"], d["ty"]))
+                unpacked[i % NST].record(stream)
             res = pl[i & 1](d["mu"], d["y"], d["tx"], d["ty"])          # AlignmentPlan: reusable outputs + workspace
             dur_h[i & 1].copy_(res.durations, non_blocking=True)
             ft_h[i & 1].copy_(res.frame_token, non_blocking=True)
@@ -783,9 +798,9 @@ def run_cuda(args):
            "d2h_bytes_per_step": d2h_idx, "ms_per_step": sec_e2e * 1e3,
            "input": "packed ragged batch in pinned host memory (lengths + valid part of every mu_x / y row: what a collate "
                     "that does not pad produces, fgt.pack_batch layout)",
-           "h2d": "ONE cudaMemcpyAsync (copy engine) + mas_b200_unpack_batch on the device (zero-padded tensors)",
+           "h2d": "ONE cudaMemcpyAsync per step on a stream that carries nothing else (copy engine back to back) + mas_b200_unpack_batch on the compute stream in front of the step (zero-padded tensors)",
            "result": "durations [B,Tx] + frame->token index [B,Ty] to pinned host memory (the dense path stays in HBM for mu_y)",
-           "pipelining": "H2D + unpack of step i+1 on a copy stream under step i; host consumes result i-1 while step i runs"}
+           "pipelining": "H2D of step i+1 on a copy stream under step i; host consumes result i-1 while step i runs; events reused from small rings"}
     e2e_padded = {"value": world * CELLS / sec_e2e_padded, "unit": UNIT, "h2d_bytes_per_step": h2d_padded,
                   "d2h_bytes_per_step": d2h_idx, "ms_per_step": sec_e2e_padded * 1e3,
                   "h2d": "cudaMemcpyAsync of the padded pinned tensors (what relocate_input does, face_tts.py:85-89)"}

@@ -19,6 +19,7 @@ from .alignment import (  # noqa: F401
     pack_batch,
     upload_batch,
     upload_packed_batch,
+    unpack_batch,
 )
 from .install import install, uninstall  # noqa: F401
 from .losses import (  # noqa: F401
@@ -33,6 +34,6 @@ from .losses import (  # noqa: F401
 
 __all__ = [
     "monotonic_align", "AlignmentPlan", "AlignmentResult", "align", "log_prior", "log_prior_maximum_path", "generate_path",
-    "durations_to_logw", "expand_durations", "upload_batch", "pack_batch", "upload_packed_batch", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
+    "durations_to_logw", "expand_durations", "upload_batch", "pack_batch", "upload_packed_batch", "unpack_batch", "install", "uninstall", "losses", "AlignmentLosses", "alignment_losses", "crop_frames",
     "duration_loss", "gather_mu_y", "prior_loss", "sequence_mask",
 ]

@@ -370,6 +370,22 @@ def upload_packed_batch(packed: torch.Tensor, B: int, F: int, Tx: int, Ty: int, 
                    torch.empty((B, F, Ty), dtype=torch.float32, device=dev),
                    torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
         staging[:packed.numel()].copy_(packed, non_blocking=True)
+        return unpack_batch(staging, B, F, Tx, Ty, out=out)
+
+
+def unpack_batch(staging: torch.Tensor, B: int, F: int, Tx: int, Ty: int, *, out=None):
+    """The device half of `upload_packed_batch` on its own (mas_b200_unpack_batch): a packed ragged batch already in
+    device memory (`staging`, CUDA uint8, pack_batch layout) -> zero-padded (mu_x [B,F,Tx], y [B,F,Ty], t_x [B], t_y [B]).
+    Asynchronous on the current stream.  A pipelined loop keeps the copy stream for the host->device copies alone (so
+    that the copy engine runs back to back) and calls this on the compute stream in front of the step."""
+    if not staging.is_cuda or staging.dtype != torch.uint8 or not staging.is_contiguous():
+        raise ValueError("staging must be a contiguous CUDA uint8 tensor holding a packed batch")
+    dev = staging.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = (torch.empty((B, F, Tx), dtype=torch.float32, device=dev),
+                   torch.empty((B, F, Ty), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
         _lib.check(_lib.lib().mas_b200_unpack_batch(staging.data_ptr(), B, F, Tx, Ty, out[0].data_ptr(), out[1].data_ptr(),
                                                     out[2].data_ptr(), out[3].data_ptr(), _stream_ptr(dev)),
                    "mas_b200_unpack_batch")
