@@ -507,6 +507,7 @@ def run_cuda(args):
     dev = torch.device("cuda", local_rank)
     L = _lib.lib()
     K, W = args.steps, max(args.warmup, 3)
+    SETTLE = 96    # untimed steps ahead of the warm-up (a multiple of the buffer-set and event rings)
     NSETS = 6      # ~37 MB per set (inputs + dense path): 6 sets = 220 MB > 126 MB L2
 
     # ---- device-resident buffer sets (each rank its own utterances: independent shards)
@@ -585,6 +586,11 @@ def run_cuda(args):
     sampler = ClockSampler(local_rank, dev_uuid)
     if rank == 0 and os.environ.get("MAS_B200_BENCH_CLOCKS", "on") != "off":
         sampler.start()
+    # SETTLE untimed steps ahead of the W warm-up steps: the first window of a process is slower than every later one
+    # (N = 2, 20 steps: 824 us against 780 us for the same window ~100 steps later, scripts/diag/step_profile_dist.py), and
+    # W = 5 steps do not even touch all NSETS buffer sets.  Reported in the JSON line (`settle_steps_untimed`).
+    for i in range(SETTLE):
+        step(i)
     for i in range(W):
         step(i)
     barrier()
@@ -917,7 +923,7 @@ def run_cuda(args):
                 sweep = {"error": repr(ex)[:300]}
 
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "settle_steps_untimed": SETTLE,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {**workload_config(), "valid_cells_per_step": valid_cells,
