@@ -166,3 +166,23 @@ def test_tensor_core_issue_is_warp_uniform_in_the_shipped_sass():
     assert len(kernels) >= 8, kernels
     for f in kernels:
         assert fallback.get(f, 0) <= 1, f"{f}: {fallback[f]} divergent fallback loops around {mma[f]} UTCHMMA"
+
+
+def test_host_side_entry_points_refuse_cpu_tensors_before_touching_the_library():
+    """No CPU path: the device halves of the public API raise on host tensors (they never fall back to computing on
+    the CPU), and the host halves raise on device-side misuse they can detect without a GPU."""
+    import torch
+    import face_gan_tts_b200 as fgt
+
+    with pytest.raises(ValueError):
+        fgt.unpack_batch(torch.zeros(64, dtype=torch.uint8), 1, 1, 1, 1)             # staging must be a CUDA buffer
+    with pytest.raises(ValueError):
+        fgt.align(torch.zeros(1, 2, 3), torch.tensor([2]), torch.tensor([3]))
+    with pytest.raises(ValueError):
+        fgt.log_prior(torch.zeros(1, 80, 4), torch.zeros(1, 80, 8))
+    with pytest.raises(ValueError):
+        fgt.log_prior_maximum_path(torch.zeros(1, 80, 4), torch.zeros(1, 80, 8), torch.tensor([4]), torch.tensor([8]))
+    with pytest.raises(ValueError):
+        fgt.pack_batch(torch.zeros(1, 2, 3), torch.zeros(1, 2, 4), torch.tensor([3]), torch.tensor([4]))   # int64 lengths
+    with pytest.raises((RuntimeError, ValueError)):
+        fgt.monotonic_align.maximum_path(torch.zeros(1, 2, 3), torch.ones(1, 2, 3))
